@@ -1,0 +1,219 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures in this directory by running the UNMODIFIED reference.
+
+Run in the build container only (``/root/reference`` is mounted there and nowhere
+else):  ``python tests/golden/make_golden.py``.  The reference is imported from
+``/root/reference/code`` through a stub shim for the packages that are not
+installed (apex, tensorboardX, albumentations, numpy.lib.type_check, np.bool) --
+none of the stubs touch the arithmetic of the hot path.  Every fixture is the
+output of the reference's own functions on seeded inputs:
+
+* ias_*.npz       IASPseudoGenerator.run        workflows/pseudo_label_generator.py:181-213
+* loss_*.npz      SelfTrainingSegmentor.compute_loss + autograd
+                                                sseg/models/segmentors/self_training_segmentor.py:30-53
+* metric_*.npz    intersectionAndUnionGPU       utils/metrics.py:6-19
+* copy_paste.npz  CopyPaste.run_original        sseg/datasets/preprocessor.py:79-122
+
+Inputs that are large are not stored: they are regenerated from a seeded CPU
+``torch.Generator`` by ``tests/golden_inputs.py`` (same torch build on the GPU
+box); a sha256 of the input is stored so that drift is detected, not trusted.
+"""
+
+from __future__ import annotations
+
+import hashlib
+import os
+import sys
+import tempfile
+from types import ModuleType, SimpleNamespace
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+import golden_inputs as gi  # noqa: E402
+
+REF = '/root/reference/code'
+
+
+def install_shim():
+    sys.dont_write_bytecode = True
+    sys.path.insert(0, REF)
+    apex = ModuleType('apex')
+    apex.amp = ModuleType('apex.amp')
+    apex.parallel = ModuleType('apex.parallel')
+    apex.parallel.SyncBatchNorm = type('SyncBatchNorm', (), {})
+    apex.parallel.convert_syncbn_model = lambda m: m
+    apex.parallel.DistributedDataParallel = object
+    sys.modules.update({'apex': apex, 'apex.amp': apex.amp, 'apex.parallel': apex.parallel})
+    tbx = ModuleType('tensorboardX')
+    tbx.SummaryWriter = object
+    sys.modules['tensorboardX'] = tbx
+    sys.modules['albumentations'] = ModuleType('albumentations')
+    tc = ModuleType('numpy.lib.type_check')
+    tc.common_type = np.common_type
+    sys.modules['numpy.lib.type_check'] = tc
+    np.bool = np.bool_
+    torch.Tensor.cuda = lambda self, *a, **k: self  # CPU run of code that calls .cuda()
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+# ----------------------------------------------------------------------------- IAS
+def run_reference_ias(batches, C, alpha, beta, gamma, cp_gamma):
+    from workflows import pseudo_label_generator as plg
+
+    class Identity:
+        def eval(self):
+            return self
+
+        def __call__(self, x):
+            return {'logits': x}
+
+    class Harness(plg.IASPseudoGenerator):
+        def initialize(self):
+            self.model = Identity()
+            self.t_loader = [{'images': lg, 'image_paths': paths} for lg, paths in batches]
+            self.t_dataset = [None] * sum(len(p) for _, p in batches)
+            self.pseudo_label_save_dir = tempfile.mkdtemp()
+            self.captured = []
+            self.thr_per_image = []
+
+        def save_pseudo_label(self, plbl, img_path):
+            self.captured.append(plbl.astype(np.uint8))   # the PNG payload of :46
+            self.thr_per_image.append(self.class_threshold.copy())
+
+        def save_data(self):
+            pass
+
+    cfg = SimpleNamespace(
+        dataset=SimpleNamespace(num_classes=C),
+        pseudo_policy=SimpleNamespace(type='IAS', ias=SimpleNamespace(alpha=alpha, beta=beta, gamma=gamma)),
+        preprocessor=SimpleNamespace(copy_paste=SimpleNamespace(gamma=cp_gamma)))
+    import contextlib
+    import io
+    gen = Harness(cfg)
+    with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+        gen.run()
+    return gen
+
+
+def ias_fixture(name, spec, store_conf=True):
+    batches = gi.ias_batches(spec)
+    gen = run_reference_ias(batches, spec['C'], spec['alpha'], spec['beta'], spec['gamma'], spec['cp_gamma'])
+    n_img = sum(len(p) for _, p in batches)
+    C = spec['C']
+    first = np.cumsum([0] + [len(p) for _, p in batches])[:-1]
+    gen.thr_trace = [gen.thr_per_image[i] for i in first]   # threshold in force for each batch
+    counts = np.zeros((n_img, C), dtype=np.int64)
+    for i, st in enumerate(gen.sample_stats):
+        for k, v in st.items():
+            if k != 'file':
+                counts[i, k] = v
+    out = dict(
+        spec=np.array(repr(spec)),
+        logits_sha=np.array([sha(lg.numpy()) for lg, _ in batches]),
+        thr_trace=np.stack(gen.thr_trace),                      # f64 [G, C] after each batch
+        class_threshold=gen.class_threshold,                    # f64 [C]
+        class_mean_probs=gen.class_mean_probs,                  # f64 [C]
+        statics_class=np.asarray(gen.statics_class, dtype=np.int64),
+        counts=counts,
+        plbl_sha=np.array([sha(p) for p in gen.captured]),
+    )
+    assert len(gen.thr_trace) == len(batches), (len(gen.thr_trace), len(batches))
+    if store_conf:
+        from torch.nn import functional as F
+        confs, labels = [], []
+        for lg, _ in batches:
+            c, l = F.softmax(lg, dim=1).max(dim=1)
+            confs.append(c.numpy())
+            labels.append(l.numpy().astype(np.uint8))
+        out['conf'] = np.concatenate(confs)
+        out['label'] = np.concatenate(labels)
+        out['plbl'] = np.stack(gen.captured)
+    np.savez_compressed(os.path.join(HERE, name + '.npz'), **out)
+    print(name, 'thr', gen.class_threshold[:4], 'kept', counts.sum(), 'of', n_img * spec['H'] * spec['W'])
+
+
+# ---------------------------------------------------------------------------- loss
+def loss_fixture(name, spec):
+    from sseg.models.modules import losses
+    from sseg.models.segmentors import self_training_segmentor as sts
+    z, t, plbl, s_z, s_lbl = gi.loss_inputs(spec)
+    z = z.clone().requires_grad_(True)
+    if s_z is not None:
+        s_z = s_z.clone().requires_grad_(True)
+    cfg = SimpleNamespace(
+        model=SimpleNamespace(predictor=SimpleNamespace(
+            seg_loss=SimpleNamespace(target_pseudo_weight=spec['w_seg']),
+            kld_loss=SimpleNamespace(weight=spec['w_kld']),
+            ent_loss=SimpleNamespace(weight=spec['w_ent']))),
+        cst_training=SimpleNamespace(is_enabled=True, cst_loss=SimpleNamespace(
+            weight=spec['w_cst'], region=spec['region'])))
+    self_ = SimpleNamespace(cfg=cfg, seg_loss_fun=losses.ce, kld_loss_fun=sts._kld,
+                            ent_loss_fun=sts._entropy, cst_loss_fun=losses.soft_ce)
+    out = sts.SelfTrainingSegmentor.compute_loss(self_, z, plbl, t, s_z, s_lbl)
+    total = sum(v.mean() for v in out.values())     # base_trainer.py:129
+    total.backward()
+    res = dict(spec=np.array(repr(spec)), z=z.detach().numpy(), t=t.numpy(), plbl=plbl.numpy(),
+               grad=z.grad.numpy(), keys=np.array(list(out.keys())),
+               values=np.array([v.item() for v in out.values()], dtype=np.float64))
+    if s_z is not None:
+        res.update(s_z=s_z.detach().numpy(), s_lbl=s_lbl.numpy(), s_grad=s_z.grad.numpy())
+    np.savez_compressed(os.path.join(HERE, name + '.npz'), **res)
+    print(name, {k: float(v) for k, v in out.items()})
+
+
+# -------------------------------------------------------------------------- metric
+def metric_fixture(name, spec):
+    from utils import metrics
+    pred, target = gi.metric_inputs(spec)
+    p = pred.clone()
+    inter, union = metrics.intersectionAndUnionGPU(p, target, spec['K'])
+    np.savez_compressed(os.path.join(HERE, name + '.npz'), spec=np.array(repr(spec)),
+                        pred=pred.numpy(), target=target.numpy(), pred_after=p.numpy(),
+                        intersection=inter.numpy(), union=union.numpy())
+    print(name, inter.numpy()[:5], union.numpy()[:5])
+
+
+# ---------------------------------------------------------------------- copy-paste
+def copy_paste_fixture(name, spec):
+    from sseg.datasets import preprocessor
+    ds = gi.CopyPasteDataset(spec)
+    cfg = SimpleNamespace(
+        dataset=SimpleNamespace(source=SimpleNamespace(type='GTAV'), num_classes=spec['C']),
+        preprocessor=SimpleNamespace(copy_paste=SimpleNamespace(
+            selected_num_classes=spec['selected'], mode='original')))
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        cp = preprocessor.CopyPaste(cfg, ds, gi.copy_paste_class_value(spec))
+    res = dict(spec=np.array(repr(spec)), hard=np.asarray(cp.hard_classes), probs=cp.class_probs)
+    np.random.seed(spec['seed'])
+    for i in range(spec['n_run']):
+        img, lbl, _ = ds.load_data(i)
+        img, lbl = img.copy(), lbl.copy()
+        o_img, o_lbl, o_mask = cp.run(img, lbl)
+        res['img_%d' % i] = o_img
+        res['lbl_%d' % i] = o_lbl
+        res['mask_%d' % i] = o_mask
+    np.savez_compressed(os.path.join(HERE, name + '.npz'), **res)
+    print(name, 'hard', cp.hard_classes)
+
+
+def main():
+    install_shim()
+    for name, spec in gi.IAS_SPECS.items():
+        ias_fixture(name, spec, store_conf=spec.get('store_conf', True))
+    for name, spec in gi.LOSS_SPECS.items():
+        loss_fixture(name, spec)
+    for name, spec in gi.METRIC_SPECS.items():
+        metric_fixture(name, spec)
+    copy_paste_fixture('copy_paste', gi.COPY_PASTE_SPEC)
+
+
+if __name__ == '__main__':
+    main()
