@@ -1,0 +1,197 @@
+// (4) Evaluation confusion matrix / intersection-union as a shared-memory privatised bincount.
+//
+// Reference: utils/metrics.py:6-19 (intersectionAndUnionGPU: pred[target==255]=255, then three
+// torch.histc over [0,K-1]); callers workflows/trainer/base_trainer.py:173-177 and
+// workflows/validator.py:96-100.  A (K+1)x(K+1) int64 confusion matrix (index K = value outside
+// [0,K)) over the pixels with target != ignore reproduces the three histograms as
+// diag / column sums / row sums (tests/test_oracle_golden.py pins that identity).
+//
+// HBM stream of 2 x elem_bytes per pixel (16 B/px as the reference calls it, int64 + int64;
+// 4C+8 B/px for the fused argmax-from-logits form).  Contention (most pixels land on a handful
+// of diagonal cells) is removed with warp match.any aggregation + a per-CTA shared matrix;
+// int64 global atomics only once per CTA per non-zero cell.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace hiast {
+
+constexpr int kThreadsM = 256;
+constexpr int kMaxSharedCells = 12288;  // 48 KB of uint32
+
+struct CmSink {
+  unsigned* s;          // shared cells or nullptr
+  long long* g;         // global matrix
+  __device__ __forceinline__ void add(bool valid, int cell) const {
+    const unsigned active = __ballot_sync(0xffffffffu, valid);
+    if (!valid) return;
+    const unsigned peers = __match_any_sync(active, cell);
+    if (lane_id() == __ffs(peers) - 1) {
+      const unsigned n = __popc(peers);
+      if (s) atomicAdd(s + cell, n);
+      else atomicAdd(reinterpret_cast<unsigned long long*>(g) + cell, static_cast<unsigned long long>(n));
+    }
+  }
+};
+
+__device__ __forceinline__ int clamp_class(long long v, int K) { return (v >= 0 && v < K) ? static_cast<int>(v) : K; }
+
+template <typename T>
+__global__ void __launch_bounds__(kThreadsM) k_confusion(const T* __restrict__ pred, const T* __restrict__ target,
+                                                         long long n, int K, int ignore_index, T* __restrict__ pred_out,
+                                                         long long* __restrict__ cm, int use_shared) {
+  extern __shared__ unsigned s_cm[];
+  const int cells = (K + 1) * (K + 1);
+  if (use_shared) {
+    for (int i = threadIdx.x; i < cells; i += kThreadsM) s_cm[i] = 0;
+    __syncthreads();
+  }
+  CmSink sink = {use_shared ? s_cm : nullptr, cm};
+  // per-CTA contiguous chunk, rounded so that every warp iteration is full except the last one
+  const long long per = ((n + gridDim.x - 1) / gridDim.x + kThreadsM - 1) / kThreadsM * kThreadsM;
+  const long long i0 = per * blockIdx.x;
+  const long long i1 = min(n, i0 + per);
+  for (long long base = i0; base < i1; base += kThreadsM) {
+    const long long i = base + threadIdx.x;
+    const bool in = i < i1;
+    long long p = 0, t = ignore_index;
+    if (in) {
+      p = static_cast<long long>(pred[i]);
+      t = static_cast<long long>(target[i]);
+    }
+    const bool keep = in && (t != ignore_index);
+    if (in && pred_out) pred_out[i] = keep ? static_cast<T>(p) : static_cast<T>(ignore_index);
+    sink.add(keep, clamp_class(t, K) * (K + 1) + clamp_class(p, K));
+  }
+  if (use_shared) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < cells; i += kThreadsM) {
+      const unsigned v = s_cm[i];
+      if (v) atomicAdd(reinterpret_cast<unsigned long long*>(cm) + i, static_cast<unsigned long long>(v));
+    }
+  }
+}
+
+// pred = first-index argmax over C of logits [B,C,HW] (torch.argmax(dim=1), base_trainer.py:173)
+template <typename T>
+__global__ void __launch_bounds__(kThreadsM) k_confusion_logits(const float* __restrict__ logits, const T* __restrict__ target,
+                                                                int B, int C, int64_t HW, int K, int ignore_index,
+                                                                long long* __restrict__ cm, int use_shared) {
+  extern __shared__ unsigned s_cm[];
+  const int cells = (K + 1) * (K + 1);
+  if (use_shared) {
+    for (int i = threadIdx.x; i < cells; i += kThreadsM) s_cm[i] = 0;
+    __syncthreads();
+  }
+  CmSink sink = {use_shared ? s_cm : nullptr, cm};
+  const long long n = static_cast<long long>(B) * HW;
+  const long long per = ((n + gridDim.x - 1) / gridDim.x + kThreadsM - 1) / kThreadsM * kThreadsM;
+  const long long i0 = per * blockIdx.x;
+  const long long i1 = min(n, i0 + per);
+  for (long long base = i0; base < i1; base += kThreadsM) {
+    const long long i = base + threadIdx.x;
+    const bool in = i < i1;
+    long long t = ignore_index;
+    int p = 0;
+    if (in) {
+      t = static_cast<long long>(target[i]);
+      const int b = static_cast<int>(i / HW);
+      const float* zp = logits + static_cast<size_t>(b) * C * HW + (i - static_cast<long long>(b) * HW);
+      float best = __ldcs(zp);
+      for (int c = 1; c < C; ++c) {
+        const float v = __ldcs(zp + static_cast<size_t>(c) * HW);
+        if (v > best || (v != v && best == best)) {  // torch.argmax treats NaN as the maximum
+          best = v;
+          p = c;
+        }
+      }
+    }
+    const bool keep = in && (t != ignore_index);
+    sink.add(keep, clamp_class(t, K) * (K + 1) + clamp_class(p, K));
+  }
+  if (use_shared) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < cells; i += kThreadsM) {
+      const unsigned v = s_cm[i];
+      if (v) atomicAdd(reinterpret_cast<unsigned long long*>(cm) + i, static_cast<unsigned long long>(v));
+    }
+  }
+}
+
+__global__ void k_iou_from_cm(const long long* __restrict__ cm, int K, float* __restrict__ inter, float* __restrict__ uni) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  long long row = 0, col = 0;
+  for (int j = 0; j <= K; ++j) {
+    row += cm[k * (K + 1) + j];   // target == k
+    col += cm[j * (K + 1) + k];   // pred == k (target not ignored)
+  }
+  const long long d = cm[k * (K + 1) + k];
+  // the reference's values are float32 histc counts: float(I), float(O) + float(T) - float(I)
+  const float fi = static_cast<float>(d);
+  inter[k] = fi;
+  uni[k] = __fsub_rn(__fadd_rn(static_cast<float>(col), static_cast<float>(row)), fi);
+}
+
+int cm_grid(long long n) {
+  const long long want = (n + kThreadsM * 8 - 1) / (kThreadsM * 8);
+  return static_cast<int>(std::max<long long>(1, std::min<long long>(want, static_cast<long long>(sm_count()) * 8)));
+}
+
+}  // namespace hiast
+
+using namespace hiast;
+
+extern "C" int hiast_confusion_matrix(const void* pred, const void* target, int elem_bytes, int64_t n, int K,
+                                      int ignore_index, void* pred_masked_out, int64_t* cm, void* stream) {
+  if (!pred || !target || !cm) return HIAST_ERR_INVALID_ARG;
+  if (elem_bytes != 1 && elem_bytes != 8) return HIAST_ERR_INVALID_ARG;
+  if (n < 0 || K < 1 || K > HIAST_MAX_CLASSES) return HIAST_ERR_INVALID_ARG;
+  if (n == 0) return HIAST_OK;
+  const int cells = (K + 1) * (K + 1);
+  const int use_shared = cells <= kMaxSharedCells;
+  const size_t smem = use_shared ? cells * sizeof(unsigned) : 0;
+  const int grid = cm_grid(n);
+  cudaStream_t st = as_stream(stream);
+  if (elem_bytes == 8)
+    k_confusion<long long><<<grid, kThreadsM, smem, st>>>(static_cast<const long long*>(pred),
+                                                          static_cast<const long long*>(target), n, K, ignore_index,
+                                                          static_cast<long long*>(pred_masked_out),
+                                                          reinterpret_cast<long long*>(cm), use_shared);
+  else
+    k_confusion<uint8_t><<<grid, kThreadsM, smem, st>>>(static_cast<const uint8_t*>(pred),
+                                                        static_cast<const uint8_t*>(target), n, K, ignore_index,
+                                                        static_cast<uint8_t*>(pred_masked_out),
+                                                        reinterpret_cast<long long*>(cm), use_shared);
+  HIAST_CHECK_LAUNCH();
+  return HIAST_OK;
+}
+
+extern "C" int hiast_confusion_from_logits(const float* logits, const void* target, int target_bytes, int B, int C,
+                                           int64_t HW, int K, int ignore_index, int64_t* cm, void* stream) {
+  if (!logits || !target || !cm) return HIAST_ERR_INVALID_ARG;
+  if (target_bytes != 1 && target_bytes != 8) return HIAST_ERR_INVALID_ARG;
+  if (B < 0 || C < 1 || HW < 1 || K < 1 || K > HIAST_MAX_CLASSES) return HIAST_ERR_INVALID_ARG;
+  if (B == 0) return HIAST_OK;
+  const int cells = (K + 1) * (K + 1);
+  const int use_shared = cells <= kMaxSharedCells;
+  const size_t smem = use_shared ? cells * sizeof(unsigned) : 0;
+  const int grid = cm_grid(static_cast<long long>(B) * HW);
+  cudaStream_t st = as_stream(stream);
+  if (target_bytes == 8)
+    k_confusion_logits<long long><<<grid, kThreadsM, smem, st>>>(logits, static_cast<const long long*>(target), B, C, HW,
+                                                                 K, ignore_index, reinterpret_cast<long long*>(cm), use_shared);
+  else
+    k_confusion_logits<uint8_t><<<grid, kThreadsM, smem, st>>>(logits, static_cast<const uint8_t*>(target), B, C, HW, K,
+                                                               ignore_index, reinterpret_cast<long long*>(cm), use_shared);
+  HIAST_CHECK_LAUNCH();
+  return HIAST_OK;
+}
+
+extern "C" int hiast_iou_from_confusion(const int64_t* cm, int K, float* intersection, float* area_union, void* stream) {
+  if (!cm || !intersection || !area_union || K < 1 || K > HIAST_MAX_CLASSES) return HIAST_ERR_INVALID_ARG;
+  k_iou_from_cm<<<(K + 63) / 64, 64, 0, as_stream(stream)>>>(reinterpret_cast<const long long*>(cm), K, intersection,
+                                                             area_union);
+  HIAST_CHECK_LAUNCH();
+  return HIAST_OK;
+}

@@ -1,0 +1,456 @@
+// (3) Region-adaptive regularisation + consistency losses, fused forward and backward (sm_100a).
+//
+// Reference: sseg/models/segmentors/self_training_segmentor.py:30-53 (compute_loss),
+// :128-137 (build_region_weight), :140-150 (_entropy), :153-163 (_kld);
+// sseg/models/modules/losses.py:32-36 (ce), :39-61 (soft_ce / SoftCELoss), :75-89
+// (compute_loss_by_selected_pixel).  Closed forms: SURVEY.md Appendix A.6.
+//
+// The reference launches ~25 full-tensor kernels forward (three [B,C,H,W] weight tensors, three
+// log_softmax, a softmax, masked products, bool-index compactions for the divisors) and about as
+// many backward.  Here: ONE forward pass over (z, t, plbl) computes the log-softmax of a pixel once
+// and feeds all four masked reductions + the three integer divisors; ONE backward pass recomputes
+// it and writes grad_z.  Both are pure HBM streams:
+//   forward  reads 4C (z) + 4C (t) + 1|8 (plbl) B/px
+//   backward reads the same and writes 4C B/px
+// The log-softmax uses the same fp32 op sequence as ATen's spatial kernel (sequential max, sum of
+// expf(z-max) in channel order, z - max - logf(sum)) so that the data-dependent SoftCE divisor
+// (#non-zero products, losses.py:89) is reproduced exactly.
+#include <math.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace hiast {
+
+constexpr int kThreadsL = 256;
+constexpr int kPxL = 2;  // pixels per thread (one 64-bit load per channel)
+
+struct LossArgs {
+  const float* z;
+  const float* t;
+  const void* plbl;
+  int plbl_bytes;
+  int B;
+  int C;
+  int64_t HW;
+  int region;
+  int terms;
+};
+
+__device__ __forceinline__ int load_label(const void* p, int bytes, size_t i) {
+  if (bytes == 1) return static_cast<const uint8_t*>(p)[i];
+  const long long v = static_cast<const long long*>(p)[i];
+  return (v < 0 || v > 255) ? 256 : static_cast<int>(v);  // 256 = out of range, not ignore
+}
+
+__device__ __forceinline__ bool in_region(int region, bool ignored) {
+  return region == HIAST_REGION_ALL || (region == HIAST_REGION_IGNORED ? ignored : !ignored);
+}
+
+struct PixelSums {
+  double ce, kld, ent, cst;
+  long long n_conf, n_ign, n_nz;
+};
+
+// log-softmax pieces of one pixel held in registers
+template <int C>
+struct PixelLS {
+  float m, logs, inv_s;
+  __device__ __forceinline__ void init(const float (&z)[C]) {
+    m = z[0];
+#pragma unroll
+    for (int c = 1; c < C; ++c) m = fmaxf(m, z[c]);
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) s += expf(z[c] - m);
+    logs = logf(s);
+    inv_s = 1.0f / s;
+  }
+  __device__ __forceinline__ float logp(float zc) const { return (zc - m) - logs; }
+  __device__ __forceinline__ float p(float zc) const { return expf(zc - m) * inv_s; }
+};
+
+template <int C>
+__device__ __forceinline__ void pixel_forward(const float (&z)[C], const float (&t)[C], int y, int region, int terms,
+                                              PixelSums& acc) {
+  PixelLS<C> ls;
+  ls.init(z);
+  const bool ignored = (y == HIAST_IGNORE_LABEL);
+  if (ignored) acc.n_ign += 1; else acc.n_conf += 1;
+  if (!ignored) {
+    if (terms & HIAST_TERM_CE) {
+      float lp = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) lp = (c == y) ? ls.logp(z[c]) : lp;
+      acc.ce += static_cast<double>(-lp);
+    }
+    if (terms & HIAST_TERM_KLD) {
+      float sl = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) sl += ls.logp(z[c]);
+      acc.kld += static_cast<double>(-sl * (1.0f / C));
+    }
+  } else if (terms & HIAST_TERM_ENT) {
+    float h = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) h += ls.p(z[c]) * ls.logp(z[c]);
+    acc.ent += static_cast<double>(-h);
+  }
+  if ((terms & HIAST_TERM_CST) && in_region(region, ignored)) {
+    float sc = 0.f;
+    int nz = 0;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float prod = __fmul_rn(-ls.logp(z[c]), t[c]);
+      nz += (prod != 0.f);
+      sc += prod;
+    }
+    acc.cst += static_cast<double>(sc);
+    acc.n_nz += nz;
+  }
+}
+
+template <int C>
+__device__ __forceinline__ void pixel_backward(const float (&z)[C], const float (&t)[C], int y, int region, int terms,
+                                               const float (&sc)[4], float (&g)[C]) {
+  PixelLS<C> ls;
+  ls.init(z);
+  const bool ignored = (y == HIAST_IGNORE_LABEL);
+  float p[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    p[c] = ls.p(z[c]);
+    g[c] = 0.f;
+  }
+  if (!ignored) {
+    const float a = ((terms & HIAST_TERM_CE) ? sc[0] : 0.f) + ((terms & HIAST_TERM_KLD) ? sc[1] : 0.f);
+    const float kb = (terms & HIAST_TERM_KLD) ? sc[1] * (1.0f / C) : 0.f;
+    const float ce = (terms & HIAST_TERM_CE) ? sc[0] : 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) g[c] = a * p[c] - kb - ((c == y) ? ce : 0.f);
+  } else if (terms & HIAST_TERM_ENT) {
+    float h = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) h += p[c] * ls.logp(z[c]);  // = -H
+#pragma unroll
+    for (int c = 0; c < C; ++c) g[c] = -sc[2] * p[c] * (ls.logp(z[c]) - h);
+  }
+  if ((terms & HIAST_TERM_CST) && in_region(region, ignored)) {
+    float T = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) T += t[c];
+#pragma unroll
+    for (int c = 0; c < C; ++c) g[c] += sc[3] * (p[c] * T - t[c]);
+  }
+}
+
+struct Partial {
+  double s[4];
+  long long n[3];
+  long long pad;
+};
+
+__device__ __forceinline__ void block_reduce_store(const PixelSums& acc, Partial* out) {
+  __shared__ Partial s_part[kThreadsL / 32];
+  double s0 = warp_sum(acc.ce), s1 = warp_sum(acc.kld), s2 = warp_sum(acc.ent), s3 = warp_sum(acc.cst);
+  long long n0 = warp_sum(acc.n_conf), n1 = warp_sum(acc.n_ign), n2 = warp_sum(acc.n_nz);
+  if (lane_id() == 0) {
+    Partial& p = s_part[threadIdx.x >> 5];
+    p.s[0] = s0; p.s[1] = s1; p.s[2] = s2; p.s[3] = s3;
+    p.n[0] = n0; p.n[1] = n1; p.n[2] = n2;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    Partial r = s_part[0];
+    for (int w = 1; w < kThreadsL / 32; ++w) {
+      for (int k = 0; k < 4; ++k) r.s[k] += s_part[w].s[k];
+      for (int k = 0; k < 3; ++k) r.n[k] += s_part[w].n[k];
+    }
+    r.pad = 0;
+    out[blockIdx.x] = r;
+  }
+}
+
+// Vector path: HW even, C compile-time.  Grid-stride over pairs of pixels.
+template <int C>
+__global__ void __launch_bounds__(kThreadsL) k_loss_fwd(LossArgs a, Partial* __restrict__ partials) {
+  const int64_t HW2 = a.HW / kPxL;
+  const long long total = static_cast<long long>(a.B) * HW2;
+  PixelSums acc = {0.0, 0.0, 0.0, 0.0, 0, 0, 0};
+  const bool need_t = (a.terms & HIAST_TERM_CST) != 0;
+  for (long long i = static_cast<long long>(blockIdx.x) * kThreadsL + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * kThreadsL) {
+    const int b = static_cast<int>(i / HW2);
+    const int64_t p2 = i - static_cast<long long>(b) * HW2;
+    const float2* zs = reinterpret_cast<const float2*>(a.z + static_cast<size_t>(b) * C * a.HW) + p2;
+    float z[kPxL][C], t[kPxL][C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float2 q = __ldcs(zs + static_cast<size_t>(c) * HW2);
+      z[0][c] = q.x; z[1][c] = q.y;
+    }
+    if (need_t) {
+      const float2* ts = reinterpret_cast<const float2*>(a.t + static_cast<size_t>(b) * C * a.HW) + p2;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const float2 q = __ldcs(ts + static_cast<size_t>(c) * HW2);
+        t[0][c] = q.x; t[1][c] = q.y;
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < C; ++c) t[0][c] = t[1][c] = 0.f;
+    }
+    const size_t lp = static_cast<size_t>(b) * a.HW + p2 * kPxL;
+#pragma unroll
+    for (int j = 0; j < kPxL; ++j) pixel_forward<C>(z[j], t[j], load_label(a.plbl, a.plbl_bytes, lp + j), a.region, a.terms, acc);
+  }
+  block_reduce_store(acc, partials);
+}
+
+template <int C>
+__global__ void __launch_bounds__(kThreadsL) k_loss_bwd(LossArgs a, const float* __restrict__ scales,
+                                                        float* __restrict__ grad) {
+  const int64_t HW2 = a.HW / kPxL;
+  const long long total = static_cast<long long>(a.B) * HW2;
+  const float sc[4] = {scales[0], scales[1], scales[2], scales[3]};
+  const bool need_t = (a.terms & HIAST_TERM_CST) != 0;
+  // The reference divides a masked sum by an element count: an empty region makes its scale inf/NaN and
+  // autograd then yields NaN for EVERY element (inf * 0).  `poison` is 0 unless some enabled scale is
+  // non-finite, in which case it is NaN.
+  float poison = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (a.terms & (1 << k)) poison += 0.f * sc[k];
+  for (long long i = static_cast<long long>(blockIdx.x) * kThreadsL + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * kThreadsL) {
+    const int b = static_cast<int>(i / HW2);
+    const int64_t p2 = i - static_cast<long long>(b) * HW2;
+    const float2* zs = reinterpret_cast<const float2*>(a.z + static_cast<size_t>(b) * C * a.HW) + p2;
+    float z[kPxL][C], t[kPxL][C], g[kPxL][C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float2 q = __ldcs(zs + static_cast<size_t>(c) * HW2);
+      z[0][c] = q.x; z[1][c] = q.y;
+    }
+    if (need_t) {
+      const float2* ts = reinterpret_cast<const float2*>(a.t + static_cast<size_t>(b) * C * a.HW) + p2;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const float2 q = __ldcs(ts + static_cast<size_t>(c) * HW2);
+        t[0][c] = q.x; t[1][c] = q.y;
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < C; ++c) t[0][c] = t[1][c] = 0.f;
+    }
+    const size_t lp = static_cast<size_t>(b) * a.HW + p2 * kPxL;
+#pragma unroll
+    for (int j = 0; j < kPxL; ++j)
+      pixel_backward<C>(z[j], t[j], load_label(a.plbl, a.plbl_bytes, lp + j), a.region, a.terms, sc, g[j]);
+    float2* gs = reinterpret_cast<float2*>(grad + static_cast<size_t>(b) * C * a.HW) + p2;
+#pragma unroll
+    for (int c = 0; c < C; ++c) __stcs(gs + static_cast<size_t>(c) * HW2, make_float2(g[0][c] + poison, g[1][c] + poison));
+  }
+}
+
+// Generic path: runtime C <= 255, any HW; channel column re-read through L1.
+constexpr int kMaxCGeneric = 255;
+
+__device__ __forceinline__ void generic_ls(const float* __restrict__ zp, int64_t cs, int C, float& m, float& logs, float& inv_s) {
+  m = zp[0];
+  for (int c = 1; c < C; ++c) m = fmaxf(m, zp[c * cs]);
+  float s = 0.f;
+  for (int c = 0; c < C; ++c) s += expf(zp[c * cs] - m);
+  logs = logf(s);
+  inv_s = 1.0f / s;
+}
+
+__global__ void __launch_bounds__(kThreadsL) k_loss_fwd_generic(LossArgs a, Partial* __restrict__ partials) {
+  const long long total = static_cast<long long>(a.B) * a.HW;
+  PixelSums acc = {0.0, 0.0, 0.0, 0.0, 0, 0, 0};
+  const int C = a.C;
+  for (long long i = static_cast<long long>(blockIdx.x) * kThreadsL + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * kThreadsL) {
+    const int b = static_cast<int>(i / a.HW);
+    const int64_t p = i - static_cast<long long>(b) * a.HW;
+    const float* zp = a.z + static_cast<size_t>(b) * C * a.HW + p;
+    const float* tp = a.t ? a.t + static_cast<size_t>(b) * C * a.HW + p : nullptr;
+    float m, logs, inv_s;
+    generic_ls(zp, a.HW, C, m, logs, inv_s);
+    const int y = load_label(a.plbl, a.plbl_bytes, static_cast<size_t>(i));
+    const bool ignored = (y == HIAST_IGNORE_LABEL);
+    if (ignored) acc.n_ign += 1; else acc.n_conf += 1;
+    if (!ignored) {
+      if ((a.terms & HIAST_TERM_CE) && y < C) acc.ce += static_cast<double>(-((zp[y * a.HW] - m) - logs));
+      if (a.terms & HIAST_TERM_KLD) {
+        float sl = 0.f;
+        for (int c = 0; c < C; ++c) sl += (zp[c * a.HW] - m) - logs;
+        acc.kld += static_cast<double>(-sl * (1.0f / C));
+      }
+    } else if (a.terms & HIAST_TERM_ENT) {
+      float h = 0.f;
+      for (int c = 0; c < C; ++c) {
+        const float zc = zp[c * a.HW];
+        h += (expf(zc - m) * inv_s) * ((zc - m) - logs);
+      }
+      acc.ent += static_cast<double>(-h);
+    }
+    if ((a.terms & HIAST_TERM_CST) && in_region(a.region, ignored)) {
+      float sc = 0.f;
+      int nz = 0;
+      for (int c = 0; c < C; ++c) {
+        const float prod = __fmul_rn(-((zp[c * a.HW] - m) - logs), tp[c * a.HW]);
+        nz += (prod != 0.f);
+        sc += prod;
+      }
+      acc.cst += static_cast<double>(sc);
+      acc.n_nz += nz;
+    }
+  }
+  block_reduce_store(acc, partials);
+}
+
+__global__ void __launch_bounds__(kThreadsL) k_loss_bwd_generic(LossArgs a, const float* __restrict__ scales,
+                                                                float* __restrict__ grad) {
+  const long long total = static_cast<long long>(a.B) * a.HW;
+  const int C = a.C;
+  const float s_ce = (a.terms & HIAST_TERM_CE) ? scales[0] : 0.f;
+  const float s_kld = (a.terms & HIAST_TERM_KLD) ? scales[1] : 0.f;
+  const float s_ent = (a.terms & HIAST_TERM_ENT) ? scales[2] : 0.f;
+  const float s_cst = (a.terms & HIAST_TERM_CST) ? scales[3] : 0.f;
+  const float poison = 0.f * s_ce + 0.f * s_kld + 0.f * s_ent + 0.f * s_cst;  // NaN iff an enabled scale is non-finite
+  for (long long i = static_cast<long long>(blockIdx.x) * kThreadsL + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * kThreadsL) {
+    const int b = static_cast<int>(i / a.HW);
+    const int64_t p = i - static_cast<long long>(b) * a.HW;
+    const size_t off = static_cast<size_t>(b) * C * a.HW + p;
+    const float* zp = a.z + off;
+    const float* tp = a.t ? a.t + off : nullptr;
+    float* gp = grad + off;
+    float m, logs, inv_s;
+    generic_ls(zp, a.HW, C, m, logs, inv_s);
+    const int y = load_label(a.plbl, a.plbl_bytes, static_cast<size_t>(i));
+    const bool ignored = (y == HIAST_IGNORE_LABEL);
+    const bool cst = (a.terms & HIAST_TERM_CST) && in_region(a.region, ignored);
+    float T = 0.f, h = 0.f;
+    if (cst) for (int c = 0; c < C; ++c) T += tp[c * a.HW];
+    if (ignored && (a.terms & HIAST_TERM_ENT))
+      for (int c = 0; c < C; ++c) {
+        const float zc = zp[c * a.HW];
+        h += (expf(zc - m) * inv_s) * ((zc - m) - logs);
+      }
+    for (int c = 0; c < C; ++c) {
+      const float zc = zp[c * a.HW];
+      const float pc = expf(zc - m) * inv_s;
+      float g = 0.f;
+      if (!ignored) g = (s_ce + s_kld) * pc - s_kld * (1.0f / C) - ((c == y) ? s_ce : 0.f);
+      else if (a.terms & HIAST_TERM_ENT) g = -s_ent * pc * (((zc - m) - logs) - h);
+      if (cst) g += s_cst * (pc * T - tp[c * a.HW]);
+      gp[c * a.HW] = g + poison;
+    }
+  }
+}
+
+// Final deterministic reduction of the per-CTA partials (one CTA, fixed order).
+__global__ void k_loss_finalize(const Partial* __restrict__ partials, int n, double* __restrict__ sums,
+                                long long* __restrict__ counts) {
+  __shared__ Partial s_part[kThreadsL / 32];
+  PixelSums acc = {0.0, 0.0, 0.0, 0.0, 0, 0, 0};
+  for (int i = threadIdx.x; i < n; i += kThreadsL) {
+    const Partial p = partials[i];
+    acc.ce += p.s[0]; acc.kld += p.s[1]; acc.ent += p.s[2]; acc.cst += p.s[3];
+    acc.n_conf += p.n[0]; acc.n_ign += p.n[1]; acc.n_nz += p.n[2];
+  }
+  double s0 = warp_sum(acc.ce), s1 = warp_sum(acc.kld), s2 = warp_sum(acc.ent), s3 = warp_sum(acc.cst);
+  long long n0 = warp_sum(acc.n_conf), n1 = warp_sum(acc.n_ign), n2 = warp_sum(acc.n_nz);
+  if (lane_id() == 0) {
+    Partial& p = s_part[threadIdx.x >> 5];
+    p.s[0] = s0; p.s[1] = s1; p.s[2] = s2; p.s[3] = s3;
+    p.n[0] = n0; p.n[1] = n1; p.n[2] = n2;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    Partial r = s_part[0];
+    for (int w = 1; w < kThreadsL / 32; ++w) {
+      for (int k = 0; k < 4; ++k) r.s[k] += s_part[w].s[k];
+      for (int k = 0; k < 3; ++k) r.n[k] += s_part[w].n[k];
+    }
+    for (int k = 0; k < 4; ++k) sums[k] = r.s[k];
+    for (int k = 0; k < 3; ++k) counts[k] = r.n[k];
+  }
+}
+
+int loss_grid(long long work_items) {
+  const long long want = (work_items + kThreadsL - 1) / kThreadsL;
+  const long long cap = static_cast<long long>(sm_count()) * 2 * 4;  // 2 resident CTAs/SM, 4 waves of work each
+  return static_cast<int>(std::max<long long>(1, std::min(want, cap)));
+}
+
+bool loss_vector_ok(const LossArgs& a, const void* extra) {
+  return (a.C == 19 || a.C == 16) && (a.HW % kPxL == 0) && (reinterpret_cast<uintptr_t>(a.z) % 8 == 0) &&
+         (!a.t || reinterpret_cast<uintptr_t>(a.t) % 8 == 0) && (reinterpret_cast<uintptr_t>(extra) % 8 == 0);
+}
+
+}  // namespace hiast
+
+using namespace hiast;
+
+extern "C" size_t hiast_st_loss_workspace_bytes(int B, int C, int64_t HW) {
+  (void)C;
+  if (B < 0 || HW < 0) return 0;
+  return static_cast<size_t>(loss_grid(static_cast<long long>(B) * HW)) * sizeof(Partial);
+}
+
+static int check_loss_args(const float* z, const float* t, const void* plbl, int plbl_bytes, int B, int C, int64_t HW,
+                           int region, int terms) {
+  if (!z || !plbl) return HIAST_ERR_INVALID_ARG;
+  if (plbl_bytes != 1 && plbl_bytes != 8) return HIAST_ERR_INVALID_ARG;
+  if (B < 0 || C < 1 || C > kMaxCGeneric || HW < 1) return HIAST_ERR_INVALID_ARG;
+  if (region < HIAST_REGION_IGNORED || region > HIAST_REGION_ALL) return HIAST_ERR_INVALID_ARG;
+  if (terms < 0 || terms > 15) return HIAST_ERR_INVALID_ARG;
+  if ((terms & HIAST_TERM_CST) && !t) return HIAST_ERR_INVALID_ARG;
+  return HIAST_OK;
+}
+
+extern "C" int hiast_st_loss_fwd(const float* z, const float* t, const void* plbl, int plbl_bytes, int B, int C,
+                                 int64_t HW, int region, int terms, double* sums, int64_t* counts, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
+  const int rc = check_loss_args(z, t, plbl, plbl_bytes, B, C, HW, region, terms);
+  if (rc != HIAST_OK) return rc;
+  if (!sums || !counts || !workspace) return HIAST_ERR_INVALID_ARG;
+  if (workspace_bytes < hiast_st_loss_workspace_bytes(B, C, HW)) return HIAST_ERR_WORKSPACE;
+  cudaStream_t st = as_stream(stream);
+  LossArgs a = {z, t, plbl, plbl_bytes, B, C, HW, region, terms};
+  Partial* parts = static_cast<Partial*>(workspace);
+  const int grid = loss_grid(static_cast<long long>(B) * HW);
+  if (loss_vector_ok(a, nullptr)) {
+    if (C == 19) k_loss_fwd<19><<<grid, kThreadsL, 0, st>>>(a, parts);
+    else k_loss_fwd<16><<<grid, kThreadsL, 0, st>>>(a, parts);
+  } else {
+    k_loss_fwd_generic<<<grid, kThreadsL, 0, st>>>(a, parts);
+  }
+  HIAST_CHECK_LAUNCH();
+  k_loss_finalize<<<1, kThreadsL, 0, st>>>(parts, grid, sums, reinterpret_cast<long long*>(counts));
+  HIAST_CHECK_LAUNCH();
+  return HIAST_OK;
+}
+
+extern "C" int hiast_st_loss_bwd(const float* z, const float* t, const void* plbl, int plbl_bytes, int B, int C,
+                                 int64_t HW, int region, int terms, const float* scales, float* grad_z, void* stream) {
+  const int rc = check_loss_args(z, t, plbl, plbl_bytes, B, C, HW, region, terms);
+  if (rc != HIAST_OK) return rc;
+  if (!scales || !grad_z) return HIAST_ERR_INVALID_ARG;
+  if (B == 0) return HIAST_OK;
+  cudaStream_t st = as_stream(stream);
+  LossArgs a = {z, t, plbl, plbl_bytes, B, C, HW, region, terms};
+  const int grid = loss_grid(static_cast<long long>(B) * HW);
+  if (loss_vector_ok(a, grad_z)) {
+    if (C == 19) k_loss_bwd<19><<<grid, kThreadsL, 0, st>>>(a, scales, grad_z);
+    else k_loss_bwd<16><<<grid, kThreadsL, 0, st>>>(a, scales, grad_z);
+  } else {
+    k_loss_bwd_generic<<<grid, kThreadsL, 0, st>>>(a, scales, grad_z);
+  }
+  HIAST_CHECK_LAUNCH();
+  return HIAST_OK;
+}

@@ -1,0 +1,114 @@
+"""LOSS registry entries backed by the fused CUDA loss kernels.
+
+Mirrors ``sseg/models/modules/losses.py`` (reference, /root/reference/code): ``ce`` :32-36,
+``soft_ce`` :39-41 (+ ``SoftCELoss`` :44-65, ``compute_loss_by_selected_pixel`` :75-89).  Same
+signatures ``LOSS[name](logits, labels, weights=None, ignore_index=255, refer_labels=None, region=...)``
+returning a 0-d float32 tensor with autograd; the whole chain of log_softmax / mask / product / sum /
+count kernels is one forward kernel + one backward kernel (hiast_b200/csrc/loss.cu).
+
+Not ported (raise NotImplementedError): class ``weights`` for CE, ``refer_labels`` for CE, and the
+``MSE`` / ``KLDIV`` consistency variants; ``BCEWithLogits`` is the adversarial
+warm-up loss and out of scope.
+"""
+
+from __future__ import annotations
+
+import torch
+
+from . import ops
+from ._lib import TERM_CE, TERM_CST, TERM_ENT, TERM_KLD, HiastError
+from .registry import LOSS
+
+IGNORE = 255
+
+
+class FusedSelfTrainingLoss(torch.autograd.Function):
+    """out[4] = (CE, KLD, ENT, CST) unweighted; entries of disabled terms are 0.
+
+    Denominators follow the reference: CE / n_conf; KLD / (C*n_conf); ENT / (C*n_ign);
+    CST / #non-zero masked products (or / numel when ``cst_mean_all``).  Empty regions give NaN
+    (0/0) exactly like the reference.  No host synchronisation anywhere.
+    """
+
+    @staticmethod
+    def forward(ctx, z, t, plbl, region, terms, cst_mean_all):
+        c = z.shape[1]
+        sums, counts = ops.st_loss_fwd(z, t, plbl, region, terms)
+        cnt = counts.to(torch.float64)
+        cst_div = torch.full((), float(z.numel()), dtype=torch.float64, device=z.device) if cst_mean_all else cnt[2]
+        denom = torch.stack([cnt[0], c * cnt[0], c * cnt[1], cst_div])
+        enabled = torch.tensor([bool(terms & TERM_CE), bool(terms & TERM_KLD), bool(terms & TERM_ENT),
+                                bool(terms & TERM_CST)], device=z.device)
+        out = torch.where(enabled, sums / denom, torch.zeros_like(sums)).to(torch.float32)
+        ctx.save_for_backward(z, t, plbl, denom, enabled)
+        ctx.region, ctx.terms = region, terms
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        z, t, plbl, denom, enabled = ctx.saved_tensors
+        scales = torch.where(enabled, gout.to(torch.float64) / denom, torch.zeros_like(denom)).to(torch.float32)
+        grad = ops.st_loss_bwd(z, t, plbl, scales.contiguous(), ctx.region, ctx.terms)
+        return grad, None, None, None, None, None
+
+
+def _prep_logits(logits):
+    if not logits.is_cuda:
+        raise HiastError('hiast_b200 losses need CUDA tensors (there is no CPU path)')
+    if logits.dtype != torch.float32:
+        logits = logits.float()
+    return logits.contiguous()
+
+
+def _prep_labels(labels):
+    if labels.dtype not in (torch.uint8, torch.int64):
+        labels = labels.long()
+    return labels.contiguous()
+
+
+def fused_terms(logits, plbl, target=None, region='ignored', terms=TERM_CE | TERM_KLD | TERM_ENT, cst_mean_all=False):
+    z = _prep_logits(logits)
+    t = None
+    if terms & TERM_CST:
+        t = _prep_logits(target)
+        assert t.shape == z.shape                                     # losses.py:50
+    return FusedSelfTrainingLoss.apply(z, t, _prep_labels(plbl), region, terms, cst_mean_all)
+
+
+@LOSS.register('CE')
+def ce(logits, labels, weights=None, ignore_index=IGNORE, refer_labels=None, region='confident'):
+    """losses.py:32-36 with refer_labels=None: nn.CrossEntropyLoss(ignore_index=255), mean over kept pixels."""
+    if weights is not None or refer_labels is not None:
+        raise NotImplementedError('CE with class weights / refer_labels is not ported (SURVEY.md 8f rank 3)')
+    if ignore_index != IGNORE:
+        raise NotImplementedError('only ignore_index=255 is supported')
+    return fused_terms(logits, labels, terms=TERM_CE)[0]
+
+
+@LOSS.register('SoftCE')
+def soft_ce(logits, labels, weights=None, ignore_index=IGNORE, refer_labels=None, region='confident'):
+    """losses.py:39-41.  ``labels`` are soft targets [B,C,H,W] in [0,1] (the reference asserts the range with
+    two host syncs, :52; here that check is skipped to stay asynchronous)."""
+    if ignore_index != IGNORE:
+        raise NotImplementedError('only ignore_index=255 is supported')
+    if region not in ('ignored', 'confident', 'all'):
+        raise ValueError('{} is not a valid region'.format(region))      # losses.py:84
+    if weights is not None:
+        assert len(weights) == labels.shape[1]                           # :56
+        for c in range(labels.shape[1]):                                 # in-place on the caller's target, like :57-58
+            labels[:, c, :, :] *= weights[c]
+    if refer_labels is None:
+        b, _, h, w = logits.shape
+        dummy = torch.zeros((b, h, w), dtype=torch.uint8, device=logits.device)
+        return fused_terms(logits, dummy, labels, region='all', terms=TERM_CST, cst_mean_all=True)[3]
+    return fused_terms(logits, refer_labels, labels, region=region, terms=TERM_CST)[3]
+
+
+@LOSS.register('MSE')
+def mse(*args, **kwargs):
+    raise NotImplementedError('MSE consistency loss is not ported (SURVEY.md 8f rank 3)')
+
+
+@LOSS.register('KLDIV')
+def kl_div(*args, **kwargs):
+    raise NotImplementedError('KLDIV consistency loss is not ported (SURVEY.md 8f rank 3)')

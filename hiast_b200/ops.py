@@ -1,0 +1,254 @@
+"""Functional wrappers over the C ABI: torch CUDA tensors in, torch CUDA tensors out.
+
+Every function launches asynchronously on torch's current stream and never syncs with the host.
+Shapes / dtypes follow include/hiast_b200.h.  No CPU path exists: CPU tensors raise.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import IGNORE, KEY_ONE, REGION, TERM_CE, TERM_CST, TERM_ENT, TERM_KLD, check, lib, ptr, require_cuda, stream_ptr
+
+__all__ = [
+    'ias_key_lo', 'ias_num_bins', 'ias_new_hist', 'ias_softmax_hist', 'ias_conf_hist', 'ias_threshold_scan',
+    'ias_select', 'ias_meanprob_scan', 'copy_paste', 'hard_lut', 'st_loss_fwd', 'st_loss_bwd',
+    'confusion_matrix', 'confusion_from_logits', 'iou_from_confusion',
+]
+
+
+# ----------------------------------------------------------------------------- IAS
+def ias_key_lo(num_classes):
+    """Smallest fp16 key a softmax max-probability over C classes can take: fp16(1/C)."""
+    k = lib().hiast_ias_key_lo(int(num_classes))
+    check(min(k, 0), 'hiast_ias_key_lo')
+    return k
+
+
+def ias_num_bins(key_lo):
+    return KEY_ONE - key_lo + 1
+
+
+def ias_new_hist(n_groups, num_classes, key_lo, device):
+    return torch.empty((n_groups, num_classes, ias_num_bins(key_lo)), dtype=torch.int32, device=device)
+
+
+def _n_groups(n_images, group_size):
+    return (n_images + group_size - 1) // group_size
+
+
+def ias_softmax_hist(logits, group_size, key_lo=None, conf=None, label=None, hist=None, accumulate=False,
+                     hist_mode=0):
+    """Phase A.  logits f32 [N,C,H,W] -> (conf f32 [N,H,W], label u8 [N,H,W], hist i32 [G,C,nb])."""
+    require_cuda(logits, torch.float32, 'logits')
+    n, c, h, w = logits.shape
+    if key_lo is None:
+        key_lo = ias_key_lo(c)
+    g = _n_groups(n, group_size)
+    dev = logits.device
+    conf = torch.empty((n, h, w), dtype=torch.float32, device=dev) if conf is None else require_cuda(conf, torch.float32, 'conf')
+    label = torch.empty((n, h, w), dtype=torch.uint8, device=dev) if label is None else require_cuda(label, torch.uint8, 'label')
+    if hist is None:
+        hist = ias_new_hist(g, c, key_lo, dev)
+        accumulate = False
+    else:
+        require_cuda(hist, torch.int32, 'hist')
+        assert hist.numel() >= g * c * ias_num_bins(key_lo)
+    check(lib().hiast_ias_softmax_hist(ptr(logits), n, c, h, w, int(group_size), int(key_lo), int(bool(accumulate)),
+                                       int(hist_mode), ptr(conf), ptr(label), ptr(hist), stream_ptr(dev)),
+          'hiast_ias_softmax_hist')
+    return conf, label, hist
+
+
+def ias_conf_hist(conf, label, num_classes, group_size, key_lo=0, hist=None, accumulate=False, want_u8=True):
+    """Histogram from caller-provided conf f32 [N,H,W] and label (u8 or i64) [N,H,W]."""
+    require_cuda(conf, torch.float32, 'conf')
+    require_cuda(label, (torch.uint8, torch.int64), 'label')
+    assert conf.shape == label.shape
+    n = conf.shape[0]
+    hw = conf[0].numel() if n else 1
+    g = _n_groups(n, group_size)
+    dev = conf.device
+    if hist is None:
+        hist = ias_new_hist(g, num_classes, key_lo, dev)
+        accumulate = False
+    label_u8 = None
+    if want_u8:
+        label_u8 = label if label.dtype == torch.uint8 else torch.empty(label.shape, dtype=torch.uint8, device=dev)
+    out_ptr = ptr(label_u8) if (label_u8 is not None and label_u8 is not label) else None
+    check(lib().hiast_ias_conf_hist(ptr(conf), ptr(label), label.element_size(), n, hw, int(num_classes),
+                                    int(group_size), int(key_lo), int(bool(accumulate)), out_ptr, ptr(hist),
+                                    stream_ptr(dev)), 'hiast_ias_conf_hist')
+    return hist, label_u8
+
+
+def ias_threshold_scan(hist, n_groups, num_classes, key_lo, alpha, beta, gamma, thr_state, thr_groups=None,
+                       temp_groups=None, error_flag=None):
+    """Phase B.  hist becomes prefix sums in place; thr_state f64[C] is updated in place.
+
+    Returns (thr_groups f64 [G,C], temp_groups f32 [G,C])."""
+    require_cuda(hist, torch.int32, 'hist')
+    require_cuda(thr_state, torch.float64, 'thr_state')
+    dev = hist.device
+    if thr_groups is None:
+        thr_groups = torch.empty((n_groups, num_classes), dtype=torch.float64, device=dev)
+    if temp_groups is None:
+        temp_groups = torch.empty((n_groups, num_classes), dtype=torch.float32, device=dev)
+    check(lib().hiast_ias_threshold_scan(ptr(hist), int(n_groups), int(num_classes), int(key_lo), float(alpha),
+                                         float(beta), float(gamma), ptr(thr_state), ptr(thr_groups), ptr(temp_groups),
+                                         ptr(error_flag), stream_ptr(dev)), 'hiast_ias_threshold_scan')
+    return thr_groups, temp_groups
+
+
+def ias_select(conf, label, thr_groups, num_classes, group_size, plbl=None, counts=None, confsum=None):
+    """Phase C.  Returns (plbl u8 [N,H,W], counts i64 [N,C], confsum i64(u64 bits) [G,C])."""
+    require_cuda(conf, torch.float32, 'conf')
+    require_cuda(label, torch.uint8, 'label')
+    require_cuda(thr_groups, torch.float64, 'thr_groups')
+    n = conf.shape[0]
+    hw = conf[0].numel() if n else 1
+    g = _n_groups(n, group_size)
+    dev = conf.device
+    if plbl is None:
+        plbl = torch.empty(conf.shape, dtype=torch.uint8, device=dev)
+    if counts is None:
+        counts = torch.zeros((n, num_classes), dtype=torch.int64, device=dev)
+    if confsum is None:
+        confsum = torch.zeros((g, num_classes), dtype=torch.int64, device=dev)
+    check(lib().hiast_ias_select(ptr(conf), ptr(label), ptr(thr_groups), n, hw, int(num_classes), int(group_size),
+                                 ptr(plbl), ptr(counts), ptr(confsum), stream_ptr(dev)), 'hiast_ias_select')
+    return plbl, counts, confsum
+
+
+def ias_meanprob_scan(confsum, counts, group_size, num_classes, cp_gamma, mean_state):
+    require_cuda(confsum, torch.int64, 'confsum')
+    require_cuda(counts, torch.int64, 'counts')
+    require_cuda(mean_state, torch.float64, 'mean_state')
+    n = counts.shape[0]
+    g = confsum.shape[0]
+    check(lib().hiast_ias_meanprob_scan(ptr(confsum), ptr(counts), n, int(group_size), g, int(num_classes),
+                                        float(cp_gamma), ptr(mean_state), stream_ptr(counts.device)),
+          'hiast_ias_meanprob_scan')
+    return mean_state
+
+
+# ---------------------------------------------------------------------- copy-paste
+def hard_lut(hard_classes):
+    """256-bit set of class ids as 8 uint32 words (host)."""
+    words = (C.c_uint32 * 8)()
+    for c in hard_classes:
+        c = int(c)
+        if not 0 <= c < 256:
+            raise ValueError('class id out of range: %r' % (c,))
+        words[c >> 5] |= (1 << (c & 31))
+    return words
+
+
+def copy_paste(img, lbl, cp_mask, donor_img, donor_lbl, hard_classes, donor_index=None):
+    """In place on img u8 [N,H,W,3], lbl u8 [N,H,W], cp_mask u8 [N,H,W]; donors indexed by donor_index (i32 [N])."""
+    for t, name in ((img, 'img'), (lbl, 'lbl'), (cp_mask, 'cp_mask'), (donor_img, 'donor_img'), (donor_lbl, 'donor_lbl')):
+        require_cuda(t, torch.uint8, name)
+    n = lbl.shape[0]
+    hw = lbl[0].numel() if n else 1
+    assert img.numel() == n * hw * 3 and cp_mask.numel() == n * hw
+    if donor_index is not None:
+        require_cuda(donor_index, torch.int32, 'donor_index')
+        assert donor_index.numel() == n
+    else:
+        assert donor_lbl.shape[0] >= n
+    lut = hard_lut(hard_classes)
+    check(lib().hiast_copy_paste(ptr(img), ptr(lbl), ptr(cp_mask), ptr(donor_img), ptr(donor_lbl), ptr(donor_index), n,
+                                 hw, C.cast(lut, C.c_void_p), stream_ptr(lbl.device)), 'hiast_copy_paste')
+    return img, lbl, cp_mask
+
+
+# ---------------------------------------------------------------------------- loss
+_ws_cache = {}
+
+
+def _loss_workspace(b, c, hw, device):
+    need = lib().hiast_st_loss_workspace_bytes(b, c, hw)
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(max(need, 1 << 16), dtype=torch.uint8, device=device)
+        _ws_cache[key] = ws
+    return ws
+
+
+def _plbl_arg(plbl):
+    require_cuda(plbl, (torch.uint8, torch.int64), 'plbl')
+    return plbl
+
+
+def st_loss_fwd(z, t, plbl, region='ignored', terms=TERM_CE | TERM_KLD | TERM_ENT | TERM_CST):
+    """Returns (sums f64[4], counts i64[3]) on the device; see include/hiast_b200.h."""
+    require_cuda(z, torch.float32, 'logits')
+    b, c = z.shape[0], z.shape[1]
+    hw = z[0, 0].numel() if b else 1
+    if t is not None:
+        require_cuda(t, torch.float32, 'target')
+        assert t.shape == z.shape
+    _plbl_arg(plbl)
+    assert plbl.numel() == b * hw
+    dev = z.device
+    sums = torch.empty(4, dtype=torch.float64, device=dev)
+    counts = torch.empty(3, dtype=torch.int64, device=dev)
+    ws = _loss_workspace(b, c, hw, dev)
+    check(lib().hiast_st_loss_fwd(ptr(z), ptr(t), ptr(plbl), plbl.element_size(), b, c, hw, REGION[region], int(terms),
+                                  ptr(sums), ptr(counts), ptr(ws), ws.numel(), stream_ptr(dev)), 'hiast_st_loss_fwd')
+    return sums, counts
+
+
+def st_loss_bwd(z, t, plbl, scales, region='ignored', terms=TERM_CE | TERM_KLD | TERM_ENT | TERM_CST, grad=None):
+    require_cuda(z, torch.float32, 'logits')
+    require_cuda(scales, torch.float32, 'scales')
+    b, c = z.shape[0], z.shape[1]
+    hw = z[0, 0].numel() if b else 1
+    if grad is None:
+        grad = torch.empty_like(z)
+    check(lib().hiast_st_loss_bwd(ptr(z), ptr(t), ptr(plbl), plbl.element_size(), b, c, hw, REGION[region], int(terms),
+                                  ptr(scales), ptr(grad), stream_ptr(z.device)), 'hiast_st_loss_bwd')
+    return grad
+
+
+# ----------------------------------------------------------------------- confusion
+def confusion_matrix(pred, target, K, ignore_index=IGNORE, cm=None, mutate_pred=False):
+    """cm i64 [K+1,K+1] accumulated; rows = target, cols = pred, index K = out of range."""
+    require_cuda(pred, (torch.uint8, torch.int64), 'pred')
+    require_cuda(target, (torch.uint8, torch.int64), 'target')
+    assert pred.dtype == target.dtype and pred.numel() == target.numel()
+    dev = pred.device
+    if cm is None:
+        cm = torch.zeros((K + 1, K + 1), dtype=torch.int64, device=dev)
+    check(lib().hiast_confusion_matrix(ptr(pred), ptr(target), pred.element_size(), pred.numel(), int(K),
+                                       int(ignore_index), ptr(pred) if mutate_pred else None, ptr(cm), stream_ptr(dev)),
+          'hiast_confusion_matrix')
+    return cm
+
+
+def confusion_from_logits(logits, target, K, ignore_index=IGNORE, cm=None):
+    require_cuda(logits, torch.float32, 'logits')
+    require_cuda(target, (torch.uint8, torch.int64), 'target')
+    b, c = logits.shape[0], logits.shape[1]
+    hw = logits[0, 0].numel() if b else 1
+    assert target.numel() == b * hw
+    dev = logits.device
+    if cm is None:
+        cm = torch.zeros((K + 1, K + 1), dtype=torch.int64, device=dev)
+    check(lib().hiast_confusion_from_logits(ptr(logits), ptr(target), target.element_size(), b, c, hw, int(K),
+                                            int(ignore_index), ptr(cm), stream_ptr(dev)), 'hiast_confusion_from_logits')
+    return cm
+
+
+def iou_from_confusion(cm, K):
+    require_cuda(cm, torch.int64, 'cm')
+    inter = torch.empty(K, dtype=torch.float32, device=cm.device)
+    union = torch.empty(K, dtype=torch.float32, device=cm.device)
+    check(lib().hiast_iou_from_confusion(ptr(cm), int(K), ptr(inter), ptr(union), stream_ptr(cm.device)),
+          'hiast_iou_from_confusion')
+    return inter, union

@@ -1,0 +1,179 @@
+/*
+ * hiast_b200 -- C ABI of the B200-native (sm_100a) post-logit self-training hot path of HIAST.
+ *
+ * The reference (bupt-ai-cz/HIAST) is pure Python and has no FFI; its extension point is the
+ * string-keyed registry (code/utils/registry/registry.py:6-43).  Each entry point below replaces
+ * the torch/numpy op chain of one reference function (cited per function, paths relative to
+ * /root/reference/code) and is what a ctypes / cffi binding on the reference side calls
+ * (see INTEGRATION.md).  The Python classes in hiast_b200/ mirror the reference's interface
+ * on top of these calls.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host; buffers are caller-owned;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); every call is
+ *     asynchronous on that stream and re-entrant per stream; nothing is allocated internally
+ *     (workspace sizes come from the *_bytes query functions);
+ *   - return value: HIAST_OK or a negative HIAST_ERR_* code, never an exception;
+ *   - tensors are dense, row-major, in the reference's layouts (logits NCHW float32);
+ *   - labels written by the library are uint8 with 255 = ignore (the PNG payload of
+ *     pseudo_label_generator.py:46); label inputs may be uint8 or int64 (`*_bytes` = 1 or 8).
+ */
+#ifndef HIAST_B200_H_
+#define HIAST_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define HIAST_API __attribute__((visibility("default")))
+#else
+#define HIAST_API
+#endif
+
+#define HIAST_OK                 0
+#define HIAST_ERR_INVALID_ARG   -1
+#define HIAST_ERR_UNSUPPORTED   -2
+#define HIAST_ERR_CUDA          -3
+#define HIAST_ERR_WORKSPACE     -4
+
+#define HIAST_IGNORE_LABEL      255
+#define HIAST_KEY_ONE           0x3C00  /* fp16 bit pattern of 1.0: the largest histogram key      */
+#define HIAST_MAX_CLASSES       255
+
+/* region selector of the consistency loss (losses.py:75-84) */
+#define HIAST_REGION_IGNORED    0
+#define HIAST_REGION_CONFIDENT  1
+#define HIAST_REGION_ALL        2
+
+/* loss term bit mask */
+#define HIAST_TERM_CE           1
+#define HIAST_TERM_KLD          2
+#define HIAST_TERM_ENT          4
+#define HIAST_TERM_CST          8
+
+/* ---- library ---------------------------------------------------------------------------- */
+HIAST_API int         hiast_version(void);                 /* 1000*major + minor                          */
+HIAST_API const char* hiast_status_string(int status);
+HIAST_API int         hiast_last_cuda_error(void);         /* cudaError_t of the last HIAST_ERR_CUDA      */
+HIAST_API int         hiast_device_sm_count(void);         /* SMs of the current device (0 if no device)  */
+
+/* ---- (1) instance-adaptive selector ----------------------------------------------------- */
+
+/* Smallest fp16 key a confidence 1/sum(exp) can round to with C classes: fp16_rn(1.0f/C).  */
+HIAST_API int    hiast_ias_key_lo(int C);
+/* Bytes of a histogram buffer uint32 [n_groups][C][HIAST_KEY_ONE - key_lo + 1].            */
+HIAST_API size_t hiast_ias_hist_bytes(int n_groups, int C, int key_lo);
+
+/* a1+a2  workflows/pseudo_label_generator.py:192-193,198-201
+ * softmax over C + first-index max (bit-exact with ATen's CUDA softmax -> max(dim=1)), fused
+ * with the per-(group, class) histogram of fp16_rn(conf) bit patterns.  Image i belongs to
+ * group i / group_size (the reference's DataLoader batch).  `accumulate` = 0 zeroes `hist`
+ * first.  `hist_mode` selects the histogram strategy (0 = library default).
+ *   logits f32 [n_images,C,H,W];  conf f32 [n_images,H,W];  label u8 [n_images,H,W]          */
+HIAST_API int hiast_ias_softmax_hist(const float* logits, int n_images, int C, int H, int W,
+                           int group_size, int key_lo, int accumulate, int hist_mode,
+                           float* conf, uint8_t* label, uint32_t* hist, void* stream);
+
+/* a2 alone, for callers that already hold conf/label (the signature of
+ * select_and_save_confident_label / get_ias_threshold takes them, :67,:171).
+ * label_bytes = 1 (uint8) or 8 (int64); label_u8_out (nullable) receives the uint8 copy.     */
+HIAST_API int hiast_ias_conf_hist(const float* conf, const void* label, int label_bytes,
+                        int n_images, int64_t HW, int C, int group_size, int key_lo,
+                        int accumulate, uint8_t* label_u8_out, uint32_t* hist, void* stream);
+
+/* a3+a4  :171-179, :207-209
+ * Sequential per-class EMA threshold scan over groups.  Step g, class c:
+ *   q = 1 - alpha * thr^gamma;  temp = float32(quantile_linear({keys of (g,c)} U {thr}, q));
+ *   thr = beta*thr + double(float(1-beta) * temp);  thr >= 1 -> 0.999
+ * `hist` is converted IN PLACE to inclusive prefix sums.  thr_state f64[C] is read and
+ * updated; thr_groups f64 [n_groups,C] receives the threshold in force for each group (the
+ * post-update value, which is the one the reference masks that same batch with, :211);
+ * temp_groups f32 [n_groups,C] (nullable) receives the quantiles.  *error_flag (device int,
+ * nullable) is OR-ed with: 1 if some q left [0,1] (numpy raises ValueError there); 2 if some
+ * float32 quantile is not certified independent of the last-bit rounding of the host libm's
+ * pow() (see hiast_b200/csrc/scan_math.h; bit-exactness versus numpy is certified when 0).   */
+HIAST_API int hiast_ias_threshold_scan(uint32_t* hist, int n_groups, int C, int key_lo,
+                             double alpha, double beta, double gamma,
+                             double* thr_state, double* thr_groups, float* temp_groups,
+                             int* error_flag, void* stream);
+
+/* a5+a6+a7(sums)  :71-89, :96-99
+ * plbl = conf < thr[group][label] ? 255 : label (float32 conf compared with the float64
+ * threshold); per-image counts of the kept labels; per-group fixed-point (2^-32) sums of the
+ * kept confidences per class.  counts / confsum are ACCUMULATED into (zero them first).
+ *   thr_groups f64 [n_groups,C]; plbl u8 [n_images,HW]; counts i64 [n_images,C];
+ *   confsum u64 [n_groups,C]                                                                  */
+HIAST_API int hiast_ias_select(const float* conf, const uint8_t* label, const double* thr_groups,
+                     int n_images, int64_t HW, int C, int group_size,
+                     uint8_t* plbl, int64_t* counts, uint64_t* confsum, void* stream);
+
+/* a7  :95-105   class_mean_probs EMA over groups (first touch initialises):
+ *   m = float32(sum/count);  cmp = (cmp == 0) ? m : cmp*g + double(m * float(1-g))           */
+HIAST_API int hiast_ias_meanprob_scan(const uint64_t* confsum, const int64_t* counts,
+                            int n_images, int group_size, int n_groups, int C, double cp_gamma,
+                            double* mean_state, void* stream);
+
+/* ---- (2) hard-aware copy-paste  sseg/datasets/preprocessor.py:102-112 ------------------- */
+/* For image i with donor d = donor_index ? donor_index[i] : i, per pixel:
+ *   M = hard[donor_lbl]; img = M ? donor_img : img; lbl = M ? donor_lbl : lbl;
+ *   cp_mask = M ? donor_lbl : cp_mask.   hard_lut_host: 256-bit set (8 x uint32, HOST memory).
+ *   img u8 [n,HW,3] (HWC); lbl, cp_mask u8 [n,HW]; donors likewise, indexed by d.            */
+HIAST_API int hiast_copy_paste(uint8_t* img, uint8_t* lbl, uint8_t* cp_mask,
+                     const uint8_t* donor_img, const uint8_t* donor_lbl,
+                     const int32_t* donor_index, int n_images, int64_t HW,
+                     const uint32_t* hard_lut_host, void* stream);
+
+/* ---- (3) region-adaptive regularisation + consistency losses ---------------------------- */
+/* a10-a15  sseg/models/segmentors/self_training_segmentor.py:30-53,128-163; losses.py:32-89
+ * One pass over (z, t, plbl): log-softmax once per pixel, then the four masked reductions
+ *   sums[0] = sum_conf -logp[y]            (CE,  / n_conf)
+ *   sums[1] = sum_conf sum_c -logp_c / C   (KLD, / (C*n_conf))
+ *   sums[2] = sum_ign  -sum_c p_c logp_c   (ENT, / (C*n_ign))
+ *   sums[3] = sum_region sum_c -logp_c t_c (CST, / counts[2])
+ *   counts  = { n_conf, n_ign, #nonzero fp32 products in the CST region }
+ * `terms` = mask of HIAST_TERM_*; t may be NULL without HIAST_TERM_CST.  Deterministic
+ * (two-stage reduction through `workspace`).                                                 */
+HIAST_API size_t hiast_st_loss_workspace_bytes(int B, int C, int64_t HW);
+HIAST_API int hiast_st_loss_fwd(const float* z, const float* t, const void* plbl, int plbl_bytes,
+                      int B, int C, int64_t HW, int region, int terms,
+                      double* sums, int64_t* counts,
+                      void* workspace, size_t workspace_bytes, void* stream);
+/* grad_z of  sum_k scales[k] * (unnormalised term k), scales f32[4] on the DEVICE
+ * (weight * upstream grad / denominator, computed by the caller without a host sync).       */
+HIAST_API int hiast_st_loss_bwd(const float* z, const float* t, const void* plbl, int plbl_bytes,
+                      int B, int C, int64_t HW, int region, int terms,
+                      const float* scales, float* grad_z, void* stream);
+
+/* ---- (4) confusion matrix / mIoU  utils/metrics.py:6-19 --------------------------------- */
+/* cm i64 [(K+1),(K+1)] (rows = target, cols = pred, index K = value outside [0,K)),
+ * ACCUMULATED over the pixels whose target != ignore_index.  If pred_masked_out != NULL it
+ * receives pred with the ignored pixels overwritten (the reference's in-place side effect,
+ * metrics.py:12); it may alias pred.  elem_bytes = 1 or 8 for both arrays.                   */
+HIAST_API int hiast_confusion_matrix(const void* pred, const void* target, int elem_bytes, int64_t n,
+                           int K, int ignore_index, void* pred_masked_out,
+                           int64_t* cm, void* stream);
+/* Same with pred = first-index argmax over C of logits [B,C,HW] (base_trainer.py:173).       */
+HIAST_API int hiast_confusion_from_logits(const float* logits, const void* target, int target_bytes,
+                                int B, int C, int64_t HW, int K, int ignore_index,
+                                int64_t* cm, void* stream);
+/* area_intersection, area_union f32 [K] from cm (diag; row+col-diag).                        */
+HIAST_API int hiast_iou_from_confusion(const int64_t* cm, int K, float* intersection, float* area_union,
+                             void* stream);
+
+/* ---- host-side test hooks (no GPU needed; used by tests only) --------------------------- */
+/* x^n by double-double repeated squaring, the integer-gamma power used by the scan.          */
+HIAST_API double hiast_testhook_powi(double x, int n);
+/* One class, one group of hiast_ias_threshold_scan on the HOST from an inclusive-prefix
+ * histogram row; returns the new threshold, *temp_out = the float32 quantile.               */
+HIAST_API double hiast_testhook_threshold_step(const uint32_t* prefix_row_host, int key_lo,
+                                     double thr, double alpha, double beta, double gamma,
+                                     float* temp_out, int* error_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HIAST_B200_H_ */

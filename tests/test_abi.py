@@ -1,0 +1,69 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/hiast_b200.h declares."""
+
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, 'include', 'hiast_b200.h')
+
+
+@pytest.fixture(scope='module')
+def built_lib():
+    from hiast_b200 import build
+    path = build.build()
+    assert os.path.exists(path)
+    return path
+
+
+def declared_functions():
+    text = open(HEADER).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    names = re.findall(r'\b(hiast_[a-z0-9_]+)\s*\(', text)
+    return sorted(set(names))
+
+
+def test_header_declares_the_expected_surface():
+    names = declared_functions()
+    for must in ['hiast_ias_softmax_hist', 'hiast_ias_threshold_scan', 'hiast_ias_select', 'hiast_ias_meanprob_scan',
+                 'hiast_copy_paste', 'hiast_st_loss_fwd', 'hiast_st_loss_bwd', 'hiast_confusion_matrix']:
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    handle = ctypes.CDLL(built_lib)
+    missing = [n for n in declared_functions() if not hasattr(handle, n)]
+    assert not missing, missing
+
+
+def test_python_binding_covers_the_header(built_lib):
+    from hiast_b200 import _lib
+    assert sorted(_lib.exported_symbols()) == declared_functions()
+    l = _lib.lib()
+    assert l.hiast_version() >= 1
+    assert l.hiast_status_string(0) == b'ok'
+    assert l.hiast_status_string(-1) == b'invalid argument'
+
+
+def test_argument_validation_without_gpu(built_lib):
+    """Invalid-argument paths return before touching CUDA."""
+    from hiast_b200 import _lib
+    l = _lib.lib()
+    assert l.hiast_ias_key_lo(19) == 0x2ABD
+    assert l.hiast_ias_key_lo(0) == -1
+    assert l.hiast_ias_hist_bytes(3, 19, 0x2ABD) == 3 * 19 * (0x3C00 - 0x2ABD + 1) * 4
+    assert l.hiast_ias_softmax_hist(None, 1, 19, 4, 4, 2, 0, 0, 0, None, None, None, None) == -1
+    assert l.hiast_st_loss_fwd(None, None, None, 8, 1, 19, 4, 0, 15, None, None, None, 0, None) == -1
+    assert l.hiast_confusion_matrix(None, None, 8, 4, 19, 255, None, None, None) == -1
+    assert l.hiast_copy_paste(None, None, None, None, None, None, 1, 4, None, None) == -1
+
+
+def test_product_path_has_no_cpu_fallback(built_lib):
+    import torch
+    from hiast_b200 import _lib, ops
+    with pytest.raises(_lib.HiastError):
+        ops.ias_softmax_hist(torch.zeros(1, 19, 4, 4), 2)
+    with pytest.raises(_lib.HiastError):
+        ops.confusion_matrix(torch.zeros(4, dtype=torch.int64), torch.zeros(4, dtype=torch.int64), 19)

@@ -1,0 +1,200 @@
+"""GPU parity of the IAS kernels (through the C ABI) against the oracle and the golden fixtures."""
+
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import golden_inputs as gi
+from oracle import ias as oias
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), 'golden')
+
+
+def load(name):
+    return np.load(os.path.join(GOLD, name + '.npz'), allow_pickle=False)
+
+
+def ops():
+    from hiast_b200 import ops as o
+    return o
+
+
+def torch_softmax_max(logits):
+    """The reference's own CUDA path for a1 (pseudo_label_generator.py:192-193)."""
+    probs = torch.softmax(logits, dim=1)
+    return probs.max(dim=1)
+
+
+@pytest.mark.parametrize('shape', [(2, 19, 64, 128), (3, 19, 33, 52), (1, 16, 40, 64), (2, 7, 31, 51), (1, 40, 9, 13)])
+@pytest.mark.parametrize('mode', [1, 2, 3])
+def test_phase_a_bit_exact_vs_torch_cuda(shape, mode):
+    o = ops()
+    g = torch.Generator().manual_seed(sum(shape) + mode)
+    n, c, h, w = shape
+    logits = torch.cat([gi.diffuse_logits(g, 1, c, h, w), gi.peaked_logits(g, n - 1, c, h, w)] if n > 1
+                       else [gi.peaked_logits(g, 1, c, h, w)]).cuda()
+    conf, label, hist = o.ias_softmax_hist(logits, group_size=2, hist_mode=mode)
+    want_conf, want_label = torch_softmax_max(logits)
+    assert torch.equal(conf, want_conf)
+    assert torch.equal(label.long(), want_label)
+    key_lo = o.ias_key_lo(c)
+    G = (n + 1) // 2
+    want_hist = np.stack([oias.class_key_histogram(want_conf[2 * k:2 * k + 2].cpu().numpy(),
+                                                   want_label[2 * k:2 * k + 2].cpu().numpy(), c, key_lo)
+                          for k in range(G)])
+    assert np.array_equal(hist.cpu().numpy().astype(np.uint32), want_hist)
+
+
+def test_phase_a_ties_and_near_ties():
+    """Exact logit ties, channels a hair below the max (expf -> 1.0f), constant maps, huge gaps."""
+    o = ops()
+    c, h, w = 19, 16, 64
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(4, c, h, w, generator=g) * 2
+    x[0, 7] = x[0, 3]                                       # exact ties, first index must win
+    x[0, 11] = torch.maximum(x[0, 11], x[0, 3])
+    top = x[1].max(dim=0).values
+    for k, eps in enumerate([1e-8, 3e-8, 6e-8, 1.2e-7, 2.4e-7, 5e-7]):
+        x[1, k] = top * (1 - eps) - eps                     # a hair below the max, earlier channels
+    x[2] = 0.0                                              # all equal -> conf = 1/19, label 0
+    x[3, 5] += 40.0                                         # saturated: conf == 1.0
+    x = x.cuda()
+    conf, label, _ = o.ias_softmax_hist(x, group_size=2)
+    want_conf, want_label = torch_softmax_max(x)
+    assert torch.equal(conf, want_conf)
+    assert torch.equal(label.long(), want_label)
+    assert (label[2] == 0).all() and (conf[3] == 1.0).any()
+
+
+@pytest.mark.parametrize('name', ['ias_small', 'ias_c7', 'ias_g25'])
+def test_post_softmax_stages_vs_reference_fixture(name):
+    """conf/label of the reference's own run -> conf_hist -> scan -> select -> meanprob == fixture."""
+    o = ops()
+    spec = gi.IAS_SPECS[name]
+    gold = load(name)
+    C, B, N = spec['C'], spec['B'], spec['N']
+    conf = torch.from_numpy(gold['conf']).cuda()
+    label = torch.from_numpy(gold['label'].astype(np.int64)).cuda()    # int64 like probs.max(1)
+    for key_lo in (0, o.ias_key_lo(C)):
+        hist, label_u8 = o.ias_conf_hist(conf, label, C, B, key_lo=key_lo)
+        G = (N + B - 1) // B
+        thr_state = torch.full((C,), 0.9, dtype=torch.float64, device='cuda')
+        flag = torch.zeros(1, dtype=torch.int32, device='cuda')
+        thr_groups, _ = o.ias_threshold_scan(hist, G, C, key_lo, spec['alpha'], spec['beta'], spec['gamma'],
+                                             thr_state, error_flag=flag)
+        assert flag.item() == 0
+        assert np.array_equal(thr_groups.cpu().numpy(), gold['thr_trace'])
+        assert np.array_equal(thr_state.cpu().numpy(), gold['class_threshold'])
+        plbl, counts, confsum = o.ias_select(conf, label_u8, thr_groups, C, B)
+        assert np.array_equal(plbl.cpu().numpy(), gold['plbl'])
+        assert np.array_equal(counts.cpu().numpy(), gold['counts'])
+        mean_state = torch.zeros(C, dtype=torch.float64, device='cuda')
+        o.ias_meanprob_scan(confsum, counts, B, C, spec['cp_gamma'], mean_state)
+        np.testing.assert_allclose(mean_state.cpu().numpy(), gold['class_mean_probs'], rtol=1e-6)
+
+
+@pytest.mark.parametrize('name', ['ias_small', 'ias_c7', 'ias_g25'])
+def test_full_pipeline_vs_oracle_on_cuda_softmax(name):
+    """logits -> labels/thresholds, oracle fed by torch's CUDA softmax exactly like the reference."""
+    o = ops()
+    spec = gi.IAS_SPECS[name]
+    C, B = spec['C'], spec['B']
+    batches = gi.ias_batches(spec)
+    oracle = oias.IASOracle(C, spec['alpha'], spec['beta'], spec['gamma'], spec['cp_gamma'])
+    oracle.run([(lg.cuda(), p) for lg, p in batches])
+    logits = torch.cat([lg for lg, _ in batches]).cuda()
+    conf, label, hist = o.ias_softmax_hist(logits, group_size=B)
+    G = len(batches)
+    thr_state = torch.full((C,), 0.9, dtype=torch.float64, device='cuda')
+    thr_groups, _ = o.ias_threshold_scan(hist, G, C, o.ias_key_lo(C), spec['alpha'], spec['beta'], spec['gamma'], thr_state)
+    plbl, counts, confsum = o.ias_select(conf, label, thr_groups, C, B)
+    mean_state = torch.zeros(C, dtype=torch.float64, device='cuda')
+    o.ias_meanprob_scan(confsum, counts, B, C, spec['cp_gamma'], mean_state)
+    assert np.array_equal(thr_groups.cpu().numpy(), np.stack(oracle.threshold_trace))
+    assert np.array_equal(plbl.cpu().numpy(), np.stack(oracle.labels))
+    assert np.array_equal(counts.sum(0).cpu().numpy(), oracle.statics_class)
+    np.testing.assert_allclose(mean_state.cpu().numpy(), oracle.class_mean_probs, rtol=1e-6)
+
+
+def test_config0_vs_oracle():
+    """BASELINE.json configs[0] (8 x 19x512x1024, batch 2) bit-exact against the oracle on CUDA softmax,
+    and within a hair of the CPU-generated fixture (CPU and CUDA softmax differ in the last ulp)."""
+    o = ops()
+    spec = gi.IAS_SPECS['ias_config0']
+    gold = load('ias_config0')
+    C, B = spec['C'], spec['B']
+    batches = gi.ias_batches(spec)
+    logits = torch.cat([lg for lg, _ in batches]).cuda()
+    oracle = oias.IASOracle(C, spec['alpha'], spec['beta'], spec['gamma'], spec['cp_gamma'])
+    oracle.run([(lg.cuda(), p) for lg, p in batches])
+    for mode in (1, 2, 3):
+        conf, label, hist = o.ias_softmax_hist(logits, group_size=B, hist_mode=mode)
+        thr_state = torch.full((C,), 0.9, dtype=torch.float64, device='cuda')
+        flag = torch.zeros(1, dtype=torch.int32, device='cuda')
+        thr_groups, _ = o.ias_threshold_scan(hist, len(batches), C, o.ias_key_lo(C), spec['alpha'], spec['beta'],
+                                             spec['gamma'], thr_state, error_flag=flag)
+        plbl, counts, _ = o.ias_select(conf, label, thr_groups, C, B)
+        assert flag.item() == 0
+        assert np.array_equal(thr_groups.cpu().numpy(), np.stack(oracle.threshold_trace))
+        assert np.array_equal(plbl.cpu().numpy(), np.stack(oracle.labels))
+        assert np.array_equal(counts.sum(0).cpu().numpy(), oracle.statics_class)
+    np.testing.assert_allclose(thr_groups.cpu().numpy(), gold['thr_trace'], rtol=1e-4)
+    rel = np.abs(counts.sum(0).cpu().numpy() - gold['statics_class']) / np.maximum(gold['statics_class'], 1)
+    assert rel.max() < 1e-2
+
+
+def test_full_resolution_properties():
+    """19x1024x2048 (BASELINE.json configs[1] shape), 4 images: size-independent properties."""
+    o = ops()
+    C, H, W, B = 19, 1024, 2048, 2
+    g = torch.Generator(device='cuda').manual_seed(1234)
+    logits = torch.randn(4, C, H, W, generator=g, device='cuda') * 3
+    logits[2:] = torch.nn.functional.interpolate(torch.randn(2, C, 32, 64, generator=g, device='cuda') * 4,
+                                                 size=(H, W), mode='bilinear', align_corners=True) + logits[2:] / 6
+    conf, label, hist = o.ias_softmax_hist(logits, group_size=B)
+    want_conf, want_label = torch_softmax_max(logits)
+    assert torch.equal(conf, want_conf) and torch.equal(label.long(), want_label)
+    # the histogram of each group is a partition of its pixels: checksum of checksums
+    assert hist.sum(dim=(1, 2)).tolist() == [B * H * W, B * H * W]
+    per_class = hist.sum(dim=2).cpu()
+    want = torch.stack([torch.bincount(want_label[2 * k:2 * k + 2].flatten(), minlength=C) for k in range(2)]).cpu()
+    assert torch.equal(per_class.long(), want)
+    thr_state = torch.full((C,), 0.9, dtype=torch.float64, device='cuda')
+    hist_raw = hist.clone()     # the scan turns `hist` into prefix sums in place
+    thr_groups, _ = o.ias_threshold_scan(hist, 2, C, o.ias_key_lo(C), 0.5, 0.9, 8.0, thr_state)
+    assert torch.equal(hist[:, :, -1].long(), want)          # last prefix = class total
+    plbl, counts, confsum = o.ias_select(conf, label, thr_groups, C, B)
+    # mask property: kept pixels keep their label and have conf >= thr; ignored have conf < thr
+    thr_px = thr_groups[torch.arange(4, device='cuda') // B][:, :, None, None].expand(4, C, H, W).gather(
+        1, label.long()[:, None]).squeeze(1)
+    kept = plbl != 255
+    assert torch.equal(kept, conf.double() >= thr_px)
+    assert torch.equal(plbl[kept], label[kept])
+    assert torch.equal(counts, torch.stack([torch.bincount(plbl[i][kept[i]].long(), minlength=C) for i in range(4)]))
+    # idempotence: same inputs, same outputs (atomics must not make anything order dependent)
+    conf2, label2, hist2 = o.ias_softmax_hist(logits, group_size=B)
+    assert torch.equal(hist2, hist_raw) and torch.equal(conf2, conf) and torch.equal(label2, label)
+
+
+def test_empty_and_single_image():
+    o = ops()
+    logits = torch.randn(1, 19, 8, 16, device='cuda')
+    conf, label, hist = o.ias_softmax_hist(logits, group_size=2)
+    assert hist.shape[0] == 1 and int(hist.sum()) == 128
+    empty = torch.empty(0, 19, 8, 16, device='cuda')
+    conf, label, hist = o.ias_softmax_hist(empty, group_size=2)
+    assert conf.numel() == 0 and hist.shape[0] == 0
+
+
+def test_scan_error_flag_mirrors_numpy_valueerror():
+    o = ops()
+    conf = torch.full((2, 4, 4), 0.5, device='cuda')
+    label = torch.zeros((2, 4, 4), dtype=torch.uint8, device='cuda')
+    hist, _ = o.ias_conf_hist(conf, label, 3, 2)
+    thr_state = torch.full((3,), 0.999, dtype=torch.float64, device='cuda')
+    flag = torch.zeros(1, dtype=torch.int32, device='cuda')
+    o.ias_threshold_scan(hist, 1, 3, 0, 1.5, 0.9, 1.0, thr_state, error_flag=flag)   # q = 1 - 1.5*0.999 < 0
+    assert flag.item() & 1

@@ -1,0 +1,146 @@
+#!/usr/bin/env python
+"""Kernel micro-benchmarks (CUDA events, L2-exceeding inputs).  Development tool, not bench.py.
+
+    python tools/bench_kernels.py [--images 16] [--out gpurun_out/kernels.json]
+"""
+
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from hiast_b200 import ops  # noqa: E402
+
+PEAK = 6459.3e9
+try:
+    PEAK = json.load(open(os.path.join(os.path.dirname(__file__), '..', 'MEASURED_PEAKS.json')))['hbm_gbs'] * 1e9
+except Exception:
+    pass
+
+
+def timeit(fn, iters=5, warmup=2):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    evs = []
+    for _ in range(iters):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    ts = sorted(a.elapsed_time(b) for a, b in evs)
+    return ts[len(ts) // 2]
+
+
+def make_logits(n, dist, C=19, H=1024, W=2048):
+    g = torch.Generator(device='cuda').manual_seed(1234)
+    out = torch.empty(n, C, H, W, device='cuda')
+    for i in range(n):
+        if dist == 'diffuse':
+            out[i] = torch.randn(C, H, W, generator=g, device='cuda') * 3
+        else:
+            low = torch.randn(1, C, 32, 64, generator=g, device='cuda') * 4
+            out[i] = torch.nn.functional.interpolate(low, size=(H, W), mode='bilinear', align_corners=True)[0]
+            out[i] += torch.randn(C, H, W, generator=g, device='cuda') * 0.5
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--images', type=int, default=16)
+    ap.add_argument('--out', default='gpurun_out/kernels.json')
+    args = ap.parse_args()
+    n, C, H, W, B = args.images, 19, 1024, 2048, 2
+    res = {'peak_gbs': PEAK / 1e9, 'images': n}
+    key_lo = ops.ias_key_lo(C)
+    G = (n + B - 1) // B
+    # plain copy of the same bytes for reference
+    src = torch.empty(n * C * H * W, device='cuda')
+    dst = torch.empty_like(src)
+    ms = timeit(lambda: dst.copy_(src))
+    res['copy_gbs'] = 2 * src.numel() * 4 / ms / 1e6
+    del src, dst
+    for dist in ('diffuse', 'peaked'):
+        logits = make_logits(n, dist)
+        conf = torch.empty(n, H, W, device='cuda')
+        label = torch.empty(n, H, W, dtype=torch.uint8, device='cuda')
+        hist = ops.ias_new_hist(G, C, key_lo, 'cuda')
+        alg_a = n * H * W * (4 * C + 1)
+        for mode in (1, 2, 3):
+            ms = timeit(lambda: ops.ias_softmax_hist(logits, B, key_lo, conf, label, hist, hist_mode=mode))
+            res['A_%s_mode%d' % (dist, mode)] = dict(ms=ms, img_s=n / ms * 1e3, alg_gbs=alg_a / ms / 1e6,
+                                                     frac=alg_a / ms / 1e6 / (PEAK / 1e9))
+        ops.ias_softmax_hist(logits, B, key_lo, conf, label, hist)
+        thr_state = torch.full((C,), 0.9, dtype=torch.float64, device='cuda')
+        hist_keep = hist.clone()
+
+        def scan():
+            hist.copy_(hist_keep)
+            ops.ias_threshold_scan(hist, G, C, key_lo, 0.5, 0.9, 8.0, thr_state)
+        ms_scan = timeit(scan)
+        ms_copy = timeit(lambda: hist.copy_(hist_keep))
+        res['B_%s' % dist] = dict(ms=ms_scan - ms_copy, us_per_group=(ms_scan - ms_copy) * 1e3 / G)
+        thr_groups, _ = ops.ias_threshold_scan(hist, G, C, key_lo, 0.5, 0.9, 8.0, thr_state)
+        plbl = torch.empty_like(label)
+        counts = torch.zeros(n, C, dtype=torch.int64, device='cuda')
+        confsum = torch.zeros(G, C, dtype=torch.int64, device='cuda')
+        ms = timeit(lambda: ops.ias_select(conf, label, thr_groups, C, B, plbl, counts, confsum))
+        res['C_%s' % dist] = dict(ms=ms, gbs=n * H * W * 6 / ms / 1e6, kept=float((plbl != 255).float().mean()))
+        tot = res['A_%s_mode3' % dist]['ms'] + res['B_%s' % dist]['ms'] + res['C_%s' % dist]['ms']
+        res['pipeline_%s' % dist] = dict(ms=tot, img_s=n / tot * 1e3, frac=alg_a / tot / 1e6 / (PEAK / 1e9))
+        # torch reference chain for context (what the reference launches on the GPU for a1 only)
+        def torch_a1():
+            p = torch.softmax(logits[:4], dim=1)
+            return p.max(dim=1)
+        ms = timeit(torch_a1)
+        res['torch_a1_%s' % dist] = dict(ms=ms, img_s=4 / ms * 1e3)
+        del logits
+    # loss fwd/bwd, config 3
+    z = torch.randn(2, 19, 512, 1024, device='cuda') * 3
+    t = torch.softmax(torch.randn(2, 19, 512, 1024, device='cuda') * 3, dim=1)
+    plbl = torch.randint(0, 19, (2, 512, 1024), device='cuda')
+    plbl[torch.rand(2, 512, 1024, device='cuda') < 0.5] = 255
+    scales = torch.full((4,), 1e-6, device='cuda')
+    grad = torch.empty_like(z)
+    flush = torch.empty(64 * 1024 * 1024, device='cuda')
+
+    def loss_step():
+        flush.zero_()
+        ops.st_loss_fwd(z, t, plbl, 'ignored')
+        ops.st_loss_bwd(z, t, plbl, scales, 'ignored', grad=grad)
+    ms_all = timeit(loss_step, iters=10)
+    ms_flush = timeit(lambda: flush.zero_(), iters=10)
+    px = 2 * 512 * 1024
+    ms_f = timeit(lambda: ops.st_loss_fwd(z, t, plbl, 'ignored'), iters=10)
+    ms_b = timeit(lambda: ops.st_loss_bwd(z, t, plbl, scales, 'ignored', grad=grad), iters=10)
+    res['loss'] = dict(ms_fwd_bwd_cold=ms_all - ms_flush, ms_fwd_warm=ms_f, ms_bwd_warm=ms_b,
+                       gbs_cold=px * (160 + 236) / (ms_all - ms_flush) / 1e6)
+    # confusion, int64 2x1024x2048
+    pred = torch.randint(0, 19, (8, 1024, 2048), device='cuda')
+    tgt = torch.randint(0, 19, (8, 1024, 2048), device='cuda')
+    cm = torch.zeros(20, 20, dtype=torch.int64, device='cuda')
+    ms = timeit(lambda: ops.confusion_matrix(pred, tgt, 19, cm=cm), iters=10)
+    res['confusion_random'] = dict(ms=ms, gbs=pred.numel() * 16 / ms / 1e6)
+    pred2 = (torch.arange(8 * 1024 * 2048, device='cuda') // 100000 % 19).view(8, 1024, 2048)
+    ms = timeit(lambda: ops.confusion_matrix(pred2, pred2, 19, cm=cm), iters=10)
+    res['confusion_coherent'] = dict(ms=ms, gbs=pred.numel() * 16 / ms / 1e6)
+    # copy-paste, uint8 1024x2048x3, 16 images
+    img = torch.randint(0, 256, (16, 1024, 2048, 3), dtype=torch.uint8, device='cuda')
+    lbl = torch.randint(0, 19, (16, 1024, 2048), dtype=torch.uint8, device='cuda')
+    mask = torch.full((16, 1024, 2048), 255, dtype=torch.uint8, device='cuda')
+    dimg = torch.randint(0, 256, (16, 1024, 2048, 3), dtype=torch.uint8, device='cuda')
+    dlbl = (torch.arange(16 * 1024 * 2048, device='cuda') // 5000 % 19).to(torch.uint8).view(16, 1024, 2048)
+    ms = timeit(lambda: ops.copy_paste(img, lbl, mask, dimg, dlbl, list(range(14))), iters=10)
+    res['copy_paste'] = dict(ms=ms, img_s=16 / ms * 1e3, gbs=16 * 1024 * 2048 * 13 / ms / 1e6)
+    os.makedirs(os.path.dirname(args.out) or '.', exist_ok=True)
+    json.dump(res, open(args.out, 'w'), indent=1)
+    print(json.dumps(res, indent=1))
+
+
+if __name__ == '__main__':
+    main()
