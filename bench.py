@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""Benchmark of the IAS pseudo-labelling hot path (BASELINE.json metric) -- one JSON line on stdout.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]): instance-adaptive pseudo-labelling of 19x1024x2048 float32 logit
+maps, batch (group) size 2, alpha .5 / beta .9 / gamma 8.  A *step* is one window of 64 images
+(32 groups) per GPU through phase A (softmax + arg-max + confidence + key histograms), phase B (the
+sequential threshold scan), phase C (threshold-and-mask, counts) and the mean-prob EMA; the threshold
+state carries over from step to step, so K steps are one K*64-image job (46 steps ~ the 2975-image
+Cityscapes train set).  474 GB of logits do not fit a GPU, so the maps cycle through a resident pool
+of 64 synthetic maps (10.2 GB: every step streams 80x the L2, no flush needed).
+
+* ``value``     images/s, whole job over all N GPUs, inputs resident in HBM, CUDA-event timed, max over ranks.
+* ``e2e``       same metric through the reference-facing API (``PSEUDO_POLICY['IAS'](cfg).run()``) with HOST
+                (pinned) logits: H2D of every batch and D2H of every label map inside the timed region.
+* ``roofline``  phase A (the dominant kernel): algorithmic bytes (77 B/px) / its mean launch time, measured
+                with CUDA events inside the timed steps, against MEASURED_PEAKS.json's HBM copy bandwidth.
+* ``cpu_baseline`` / ``--impl reference``: the oracle port of the reference's CPU path (faithful op sequence,
+                oracle/ias.py) on the host cores, on a bounded sample of the same workload.
+
+Multi-GPU (torchrun, one rank per GPU): windows are striped over ranks and the 19-double threshold state is
+handed rank to rank with NCCL send/recv (hiast_b200/sharded.py); weak scaling, per-GPU work fixed.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+C, H, W, GROUP = 19, 1024, 2048, 2
+ALPHA, BETA, GAMMA, CP_GAMMA = 0.5, 0.9, 8.0, 0.99
+WINDOW = 64                      # images per step per GPU
+ALG_BYTES_PER_IMAGE = H * W * (4 * C + 1)     # read logits + write uint8 label = 161 480 704 B
+METRIC = 'pseudo-labelled 19x1024x2048 images/s'
+UNIT = 'images/s'
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=46)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--dist', default='mixed', choices=['mixed', 'diffuse', 'peaked'])
+    ap.add_argument('--e2e-steps', type=int, default=4)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--cpu-images', type=int, default=8)
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    except Exception:
+        return 6650.0, 'fallback (B200_PROFILING.md, 6.65 TB/s)'
+
+
+def ncu_traffic():
+    """dram bytes per phase-A launch from the committed ncu capture, scaled to this window; else None."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'roofline_phase_a.json')) as f:
+            d = json.load(f)
+        return float(d['dram_bytes_per_image']) * WINDOW
+    except Exception:
+        return None
+
+
+# ------------------------------------------------------------------------- CPU arm
+def synth_logits_cpu(n, seed=1234):
+    """The bench distributions on the host (diffuse / peaked alternating), float32 [n,C,H,W]."""
+    import torch
+    from torch.nn import functional as F
+    g = torch.Generator().manual_seed(seed)
+    out = torch.empty(n, C, H, W)
+    for i in range(n):
+        if i % 2 == 0:
+            out[i] = torch.randn(C, H, W, generator=g) * 3
+        else:
+            low = torch.randn(1, C, 32, 64, generator=g) * 4
+            out[i] = F.interpolate(low, size=(H, W), mode='bilinear', align_corners=True)[0]
+            out[i] += torch.randn(C, H, W, generator=g) * 0.5
+    return out
+
+
+def run_cpu_port(n_images, steps=1, warmup=0):
+    """The reference's CPU path (oracle port, faithful op sequence) on a bounded sample.  images/s."""
+    import torch
+    from oracle import ias as oias
+    logits = synth_logits_cpu(n_images)
+    batches = [(logits[i:i + GROUP], ['img_%05d.png' % (i + j) for j in range(min(GROUP, n_images - i))])
+               for i in range(0, n_images, GROUP)]
+    best = None
+    for it in range(warmup + steps):
+        o = oias.IASOracle(C, ALPHA, BETA, GAMMA, CP_GAMMA, faithful=True, keep_labels=False)
+        t0 = time.perf_counter()
+        o.run(batches)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            best = dt if best is None else min(best, dt)
+    return n_images / best, best, torch.get_num_threads()
+
+
+def reference_arm(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    n = args.cpu_images
+    steps = max(1, min(args.steps, 2))
+    value, secs, threads = run_cpu_port(n, steps=steps, warmup=0)
+    sample = '%d maps of 19x1024x2048, batch 2 (%d groups), per step; PNG write excluded' % (n, (n + 1) // 2)
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': steps,
+        'warmup': 0, 'ms_per_step': secs * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'GTA5->Cityscapes IAS pseudo-labelling, 19x1024x2048 logit maps, batch 2 (configs[1])',
+                   'note': 'reference is pure Python/numpy and cannot travel to the GPU box; this is the oracle port '
+                           '(oracle/ias.py, faithful op sequence) on the host cores'},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample,
+                         'host_cpus': os.cpu_count(),
+                         'note': 'only softmax/max use all torch threads; the numpy/Python part is single-threaded '
+                                 'by construction, as in the reference'},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        self.index, self.samples, self.proc, self.thread = index, [], None, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for s in self.samples:
+            parts = [p.strip() for p in s.split(',')]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = float(parts[1])
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[2:6]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        sm.sort()
+        busy = [x for x in sm if mx and x > 0.5 * mx] or sm
+        return {'sm_mhz': busy[len(busy) // 2] if busy else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+# ------------------------------------------------------------------------- GPU arm
+def make_pool(device, dist_name, n):
+    import torch
+    from torch.nn import functional as F
+    g = torch.Generator(device=device).manual_seed(1234)
+    pool = torch.empty(n, C, H, W, device=device)
+    for i in range(n):
+        diffuse = dist_name == 'diffuse' or (dist_name == 'mixed' and i % 2 == 0)
+        if diffuse:
+            pool[i] = torch.randn(C, H, W, generator=g, device=device) * 3
+        else:
+            low = torch.randn(1, C, 32, 64, generator=g, device=device) * 4
+            pool[i] = F.interpolate(low, size=(H, W), mode='bilinear', align_corners=True)[0]
+            pool[i] += torch.randn(C, H, W, generator=g, device=device) * 0.5
+    return pool
+
+
+def gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    from types import SimpleNamespace
+    from hiast_b200.ias_engine import IASEngine
+    from hiast_b200.sharded import ShardedIAS
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device (there is no CPU path); use --impl reference for the CPU arm')
+    torch.cuda.set_device(local)
+    device = torch.device('cuda', local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=device)
+    if args.gpus != world and rank == 0 and world > 1:
+        print('warning: --gpus %d but WORLD_SIZE %d' % (args.gpus, world), file=sys.stderr)
+
+    K, Wm = args.steps, max(args.warmup, 3)
+    pool = make_pool(device, args.dist, WINDOW)
+    engine = IASEngine(C, H, W, GROUP, ALPHA, BETA, GAMMA, CP_GAMMA, 2 * WINDOW, device=device)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    a_events = []
+
+    class TimedEngine:
+        """Forwards to the engine; brackets every phase-A launch with CUDA events on the launching stream."""
+        def __getattr__(self, name):
+            return getattr(engine, name)
+
+        def phase_a(self, logits, first_image=0):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            engine.phase_a(logits, first_image)
+            e1.record()
+            a_events.append((e0, e1))
+
+    def run_job(n_steps, timed):
+        total_windows = n_steps * world
+        drv = ShardedIAS(TimedEngine() if timed else engine, WINDOW, total_windows * WINDOW, rank, world)
+        return drv.run(lambda w: pool)
+
+    # warm-up (also creates the NCCL p2p communicators)
+    run_job(Wm, timed=False)
+    engine.thr_state.fill_(0.9)
+    engine.mean_state.zero_()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0.record()
+    run_job(K, timed=True)
+    t1.record()
+    barrier()
+    ms = t0.elapsed_time(t1)
+    clocks = sampler.stop() if rank == 0 else None
+    certified = engine.check_errors()
+    a_ms = sum(e0.elapsed_time(e1) for e0, e1 in a_events) / max(len(a_events), 1)
+    if world > 1:
+        t = torch.tensor([ms, a_ms], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, a_ms = float(t[0]), float(t[1])
+    images = K * WINDOW * world
+    value = images / (ms / 1e3)
+
+    # ---- e2e through the reference-facing API with host buffers (every rank its own replica of the call)
+    e2e = measure_e2e(args, device, rank, world, barrier)
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        achieved = ALG_BYTES_PER_IMAGE * WINDOW / (a_ms / 1e3) / 1e9
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': Wm,
+            'ms_per_step': ms / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': 'GTA5->Cityscapes IAS pseudo-labelling, 19x1024x2048 logit maps, batch 2 (configs[1])',
+                       'images_per_step_per_gpu': WINDOW, 'images_total': images, 'alpha': ALPHA, 'beta': BETA,
+                       'gamma': GAMMA, 'distribution': args.dist, 'resident_pool_maps': WINDOW,
+                       'l2': 'inputs exceed L2 (10.2 GB streamed per step)',
+                       'parallelism': 'windows striped over %d rank(s); 19-double threshold state via NCCL send/recv' % world},
+            'hbm_frac_of_peak': ALG_BYTES_PER_IMAGE * value / world / 1e9 / peak,
+            'roofline': {'kernel': 'k_softmax_hist (phase A)', 'bound': 'hbm', 'achieved': achieved, 'peak': peak,
+                         'unit': 'GB/s', 'frac': achieved / peak, 'traffic': ncu_traffic(), 'peak_source': peak_src,
+                         'algorithmic_bytes_per_launch': ALG_BYTES_PER_IMAGE * WINDOW, 'launch_ms': a_ms,
+                         'share_of_step': a_ms / (ms / K)},
+            'e2e': e2e,
+            'gpu_launches': 5 * K,
+            'clocks': clocks,
+            'pow_rounding_certified': bool(certified),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            v, secs, threads = run_cpu_port(args.cpu_images)
+            line['cpu_baseline'] = {
+                'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'host_cpus': os.cpu_count(),
+                'sample': '%d maps of 19x1024x2048, batch 2 (%.1f s of host work); PNG write excluded' % (args.cpu_images, secs)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def measure_e2e(args, device, rank, world, barrier):
+    """IASPseudoGenerator.run() on pinned host logits: H2D per batch + D2H per label map inside the timed region."""
+    import torch
+    from types import SimpleNamespace
+    from hiast_b200.pseudo_label_generator import IASPseudoGenerator
+    import tempfile
+
+    n_host = 8                                     # pinned host pool: 8 maps = 1.3 GB
+    steps = max(1, args.e2e_steps)
+    host = torch.empty((n_host, C, H, W), dtype=torch.float32).pin_memory()
+    host.copy_(synth_logits_cpu(2).repeat(n_host // 2, 1, 1, 1))
+
+    class Identity:
+        def eval(self):
+            return self
+
+        def __call__(self, x):
+            return {'logits': x}
+
+    def loader(n_images):
+        for i in range(0, n_images, GROUP):
+            j = i % n_host
+            yield {'images': host[j:j + GROUP], 'image_paths': ['img_%06d.png' % (i + k) for k in range(GROUP)]}
+
+    cfg = SimpleNamespace(
+        dataset=SimpleNamespace(num_classes=C),
+        pseudo_policy=SimpleNamespace(type='IAS', batch_size=GROUP, ias=SimpleNamespace(alpha=ALPHA, beta=BETA, gamma=GAMMA)),
+        preprocessor=SimpleNamespace(copy_paste=SimpleNamespace(gamma=CP_GAMMA)))
+
+    class Gen(IASPseudoGenerator):
+        def save_pseudo_label(self, plbl, img_path):      # PNG encode/write excluded, as in the CPU baseline
+            self.last = plbl
+
+        def save_data(self):
+            pass
+
+    def run(n_images):
+        gen = Gen(cfg, model=Identity(), loader=loader(n_images), dataset_len=None, save_dir=tempfile.mkdtemp(),
+                  window_batches=WINDOW // GROUP, device=device)
+        gen.run()
+        return gen
+
+    run(WINDOW)                                    # warm-up
+    barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    run(steps * WINDOW)
+    e1.record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    secs = max(wall, e0.elapsed_time(e1) / 1e3)
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([secs], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        secs = float(t[0])
+    return {'value': steps * WINDOW * world / secs, 'unit': UNIT, 'steps': steps,
+            'h2d_bytes_per_step': WINDOW * C * H * W * 4,
+            'd2h_bytes_per_step': WINDOW * (H * W + C * 8) + (WINDOW // GROUP) * C * 8,
+            'api': "PSEUDO_POLICY['IAS'](cfg).run() on pinned host logits, identity model, PNG write stubbed; "
+                   "N>1: independent replicas of the call, one per GPU"}
+
+
+def main():
+    args = parse_args()
+    if args.impl == 'reference':
+        reference_arm(args)
+    else:
+        gpu_arm(args)
+
+
+if __name__ == '__main__':
+    main()

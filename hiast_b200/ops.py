@@ -64,8 +64,11 @@ def ias_softmax_hist(logits, group_size, key_lo=None, conf=None, label=None, his
     return conf, label, hist
 
 
-def ias_conf_hist(conf, label, num_classes, group_size, key_lo=0, hist=None, accumulate=False, want_u8=True):
-    """Histogram from caller-provided conf f32 [N,H,W] and label (u8 or i64) [N,H,W]."""
+def ias_conf_hist(conf, label, num_classes, group_size, key_lo=0, hist=None, accumulate=False, label_u8_out=None):
+    """Histogram from caller-provided conf f32 [N,H,W] and label (u8 or i64) [N,H,W].
+
+    Returns (hist, label_u8): label_u8 is ``label`` itself when it already is uint8, else a uint8 copy
+    (written into ``label_u8_out`` when given)."""
     require_cuda(conf, torch.float32, 'conf')
     require_cuda(label, (torch.uint8, torch.int64), 'label')
     assert conf.shape == label.shape
@@ -76,10 +79,15 @@ def ias_conf_hist(conf, label, num_classes, group_size, key_lo=0, hist=None, acc
     if hist is None:
         hist = ias_new_hist(g, num_classes, key_lo, dev)
         accumulate = False
-    label_u8 = None
-    if want_u8:
-        label_u8 = label if label.dtype == torch.uint8 else torch.empty(label.shape, dtype=torch.uint8, device=dev)
-    out_ptr = ptr(label_u8) if (label_u8 is not None and label_u8 is not label) else None
+    if label.dtype == torch.uint8:
+        label_u8, out_ptr = label, None
+        if label_u8_out is not None:
+            label_u8_out.copy_(label)
+            label_u8 = label_u8_out
+    else:
+        label_u8 = label_u8_out if label_u8_out is not None else torch.empty(label.shape, dtype=torch.uint8, device=dev)
+        require_cuda(label_u8, torch.uint8, 'label_u8_out')
+        out_ptr = ptr(label_u8)
     check(lib().hiast_ias_conf_hist(ptr(conf), ptr(label), label.element_size(), n, hw, int(num_classes),
                                     int(group_size), int(key_lo), int(bool(accumulate)), out_ptr, ptr(hist),
                                     stream_ptr(dev)), 'hiast_ias_conf_hist')

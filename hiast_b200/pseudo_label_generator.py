@@ -1,0 +1,325 @@
+"""Pseudo-label policies on the CUDA IAS pipeline, behind the reference's ``PSEUDO_POLICY`` interface.
+
+Mirrors ``workflows/pseudo_label_generator.py`` (reference, /root/reference/code):
+``BasePseudoGenerator`` :14-106, ``ConstantThresholdPseudoGenerator`` ('CT') :109-132,
+``NoThresholdPseudoGenerator`` ('NT') :135-139, ``IASPseudoGenerator`` ('IAS') :168-213.  Same
+constructor (``PSEUDO_POLICY[type](cfg)``), same attributes (``class_threshold``, ``class_mean_probs``,
+``statics_class``, ``sample_stats``, ``samples_class``), same methods and the same files written by
+``save_pseudo_label`` / ``save_data``.
+
+What changes is where the work happens.  The reference copies conf (f32) + label (int64) of every
+batch to the host (12 B/px) and runs numpy / Python loops there; here logits never leave the GPU:
+each batch goes through phase A as it arrives, a window of batches is then scanned (phase B) and
+masked (phase C) on the device, and only the uint8 pseudo-labels (1 B/px), the per-image class
+counts and the thresholds come back.  PNG encoding stays on the host (thread pool).
+
+The backbone and the datasets are outside this package: ``initialize`` takes an
+injected ``model`` / ``loader`` (any callable returning ``{'logits': [B,C,H,W]}``; any iterable of
+``{'images', 'image_paths'}``).  Inside a reference checkout, bind the reference's own
+``initialize`` instead.
+
+CBST (:142-165) is not ported yet.
+"""
+
+from __future__ import annotations
+
+import json
+import os
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+import torch
+
+from . import ops
+from .ias_engine import IASEngine
+from .registry import PSEUDO_POLICY
+
+
+def _cfg_get(node, path, default=None):
+    for part in path.split('.'):
+        if node is None or not hasattr(node, part):
+            return default
+        node = getattr(node, part)
+    return node
+
+
+class BasePseudoGenerator:
+
+    def __init__(self, cfg, model=None, loader=None, dataset_len=None, save_dir=None, window_batches=8,
+                 device='cuda', png_workers=4):
+        self.cfg = cfg
+        self.statics_class = np.array([0] * self.cfg.dataset.num_classes)                # :18
+        self.sample_stats = []                                                           # :19
+        self.samples_class = {i: [] for i in range(self.cfg.dataset.num_classes)}        # :20
+        self.class_mean_probs = np.zeros(self.cfg.dataset.num_classes)                   # :21
+        self.class_threshold = None
+        self.device = torch.device(device)
+        self.window_batches = int(window_batches)
+        self._model_arg, self._loader_arg, self._len_arg, self._save_dir_arg = model, loader, dataset_len, save_dir
+        self._png_pool = ThreadPoolExecutor(max_workers=png_workers) if png_workers > 0 else None
+        self._png_jobs = []
+        self._engine = None
+        self.pow_rounding_certified = True
+        self.initialize()
+
+    # ------------------------------------------------------------------ set-up
+    def initialize(self):
+        """:25-41.  The reference builds the segmentation model and the target DataLoader from cfg; both are
+        outside this package, so they are injected.  The save-dir contract (:38-41) is kept."""
+        if self._model_arg is None or self._loader_arg is None:
+            raise RuntimeError('hiast_b200 pseudo-label generators need model= and loader= (the DeepLabv2 backbone and '
+                               'the dataset loaders are not part of this package; see INTEGRATION.md)')
+        self.model = self._model_arg
+        self.t_loader = self._loader_arg
+        n = self._len_arg
+        if n is None:
+            ds = getattr(self.t_loader, 'dataset', None)
+            n = len(ds) if ds is not None else None
+        self.t_dataset = range(n) if n is not None else None
+        self.pseudo_label_save_dir = self._save_dir_arg or _cfg_get(self.cfg, 'pseudo_policy.save_dir')
+        assert self.pseudo_label_save_dir is not None and \
+            (not os.path.exists(self.pseudo_label_save_dir) or len(os.listdir(self.pseudo_label_save_dir)) == 0)
+        os.makedirs(self.pseudo_label_save_dir, exist_ok=True)
+
+    # ------------------------------------------------------------------ outputs
+    def save_pseudo_label(self, plbl, img_path):
+        """:43-46  uint8 gray PNG '{stem}_pseudo_label.png'."""
+        import cv2
+        img_name = os.path.splitext(os.path.basename(img_path))[0]
+        plbl_save_path = os.path.join(self.pseudo_label_save_dir, '{}_pseudo_label.png'.format(img_name))
+        cv2.imwrite(plbl_save_path, plbl.astype(np.uint8))
+
+    def _save_async(self, plbl, img_path):
+        if self._png_pool is None or type(self).save_pseudo_label is not BasePseudoGenerator.save_pseudo_label:
+            self.save_pseudo_label(plbl, img_path)       # overridden hooks are called inline, in order
+        else:
+            self._png_jobs.append(self._png_pool.submit(self.save_pseudo_label, plbl, img_path))
+
+    def _wait_png(self):
+        for job in self._png_jobs:
+            job.result()
+        self._png_jobs = []
+
+    def save_data(self):
+        """:48-62  same file names, formats and locations (one level above the PNG directory)."""
+        root = os.path.join(self.pseudo_label_save_dir, '..')
+        if self.class_threshold is not None:
+            print('class threshold: {}'.format(self.class_threshold))
+            np.save(os.path.join(root, 'class_threshold.npy'), self.class_threshold)
+        print('class statics number: {}'.format(self.statics_class))
+        np.save(os.path.join(root, 'statics_class.npy'), self.statics_class)
+        print('class mean probabilities: {}'.format(self.class_mean_probs))
+        np.save(os.path.join(root, 'class_mean_probabilities.npy'), self.class_mean_probs)
+        with open(os.path.join(root, 'sample_class_stats.json'), 'a') as f:
+            f.write(json.dumps(self.sample_stats))
+        with open(os.path.join(root, 'samples_with_class.json'), 'a') as f:
+            f.write(json.dumps(self.samples_class))
+
+    def run(self):
+        raise NotImplementedError
+
+    # ------------------------------------------------------- host bookkeeping
+    def _record_image(self, counts_row, img_path):
+        """:82-89 from the per-image class counts computed on the device."""
+        current_stats = {}
+        for i in range(self.cfg.dataset.num_classes):
+            pix_num = int(counts_row[i])
+            if pix_num != 0:
+                current_stats[i] = pix_num
+                self.samples_class[i].append([img_path, pix_num])
+                self.statics_class[i] += pix_num
+        current_stats['file'] = img_path
+        self.sample_stats.append(current_stats)
+
+    def _cp_gamma(self):
+        return float(_cfg_get(self.cfg, 'preprocessor.copy_paste.gamma', 0.99))
+
+    def select_and_save_confident_label(self, probs_pred, lbls_pred, img_paths):
+        """:67-106 for host (numpy) or device conf [B,H,W] / labels [B,H,W]; uses ``self.class_threshold``
+        (None = keep everything), records the per-image statistics, saves the PNGs and updates
+        ``class_mean_probs``.  Returns the last image's pseudo-label like the reference (:106)."""
+        C = self.cfg.dataset.num_classes
+        conf = torch.as_tensor(probs_pred).to(self.device, torch.float32).contiguous()
+        label = torch.as_tensor(lbls_pred).to(self.device)
+        label = label.contiguous() if label.dtype == torch.uint8 else label.to(torch.uint8).contiguous()
+        b = conf.shape[0]
+        thr = np.zeros(C) if self.class_threshold is None else np.asarray(self.class_threshold, dtype=np.float64)
+        thr_groups = torch.from_numpy(thr.reshape(1, C).copy()).to(self.device)
+        plbl, counts, confsum = ops.ias_select(conf, label, thr_groups, C, b)
+        mean_state = torch.from_numpy(np.asarray(self.class_mean_probs, dtype=np.float64).copy()).to(self.device)
+        ops.ias_meanprob_scan(confsum, counts, b, C, self._cp_gamma(), mean_state)
+        plbl_h, counts_h = plbl.cpu().numpy(), counts.cpu().numpy()
+        self.class_mean_probs = mean_state.cpu().numpy()
+        for i, img_path in enumerate(img_paths):
+            self._record_image(counts_h[i], img_path)
+            self._save_async(plbl_h[i], img_path)
+        self._wait_png()
+        return plbl_h[-1].astype(np.int64)
+
+    # ------------------------------------------------------------ device loop
+    def _make_engine(self, logits, alpha=0.0, beta=0.0, gamma=1.0):
+        b, c, h, w = logits.shape
+        group = int(_cfg_get(self.cfg, 'pseudo_policy.batch_size', b) or b)
+        group = max(group, b)
+        return IASEngine(c, h, w, group, alpha, beta, gamma, self._cp_gamma(), group * self.window_batches,
+                         device=self.device)
+
+    def _iterate_logits(self):
+        """Yields (logits [B,C,H,W] on the device, image_paths) exactly as :189-192 produces them."""
+        self.model.eval() if hasattr(self.model, 'eval') else None
+        with torch.no_grad():
+            for data in self.t_loader:
+                imgs = data['images'].to(self.device, non_blocking=True)
+                logits = self.model(imgs)['logits']
+                if logits.dtype != torch.float32:
+                    logits = logits.float()
+                yield logits.contiguous(), list(data['image_paths'])
+
+    def _already_done(self):
+        return self.t_dataset is not None and len(os.listdir(self.pseudo_label_save_dir)) >= len(self.t_dataset)
+
+
+def _flush_window(gen, engine, paths, n_images, scan):
+    """Phases B/C for the images in the window, then D2H of labels + counts (pinned buffers, one sync per
+    window) and the host bookkeeping."""
+    if n_images == 0:
+        return
+    if scan:
+        engine.phase_b(0, n_images)
+    engine.phase_c(0, n_images)
+    engine.mean_prob(0, n_images)
+    pins = getattr(gen, '_pinned', None)
+    if pins is None or pins[0].shape[0] < engine.max_images or pins[0].shape[1:] != engine.plbl.shape[1:]:
+        pins = gen._pinned = (torch.empty(engine.plbl.shape, dtype=torch.uint8).pin_memory(),
+                              torch.empty(engine.counts.shape, dtype=torch.int64).pin_memory())
+    pins[0][:n_images].copy_(engine.plbl[:n_images], non_blocking=True)   # the only per-pixel traffic back: 1 B/px
+    pins[1][:n_images].copy_(engine.counts[:n_images], non_blocking=True)
+    torch.cuda.current_stream(engine.device).synchronize()
+    gen._wait_png()                                   # the previous window's encoders still read the pinned buffer
+    plbl_h, counts_h = pins[0].numpy(), pins[1].numpy()
+    for i in range(n_images):
+        gen._record_image(counts_h[i], paths[i])
+        gen._save_async(plbl_h[i], paths[i])
+    gen._wait_png()
+
+
+@PSEUDO_POLICY.register('CT')
+class ConstantThresholdPseudoGenerator(BasePseudoGenerator):
+
+    def get_constant_threshold(self):
+        """:112-113"""
+        return self.cfg.pseudo_policy.ct.threshold * np.ones(self.cfg.dataset.num_classes)
+
+    def run(self):
+        """:115-132"""
+        if self._already_done():
+            print('%% pseudo labels have existed')
+            return
+        self.class_threshold = self.get_constant_threshold()
+        C = self.cfg.dataset.num_classes
+        thr = np.zeros(C) if self.class_threshold is None else np.asarray(self.class_threshold, dtype=np.float64)
+        engine, paths, n = None, [], 0
+        for logits, img_paths in self._iterate_logits():
+            if engine is None:
+                engine = self._engine = self._make_engine(logits)
+                engine.thr_groups.copy_(torch.from_numpy(np.tile(thr, (engine.max_groups, 1))))
+            b = logits.shape[0]
+            engine.phase_a(logits, n)
+            paths += img_paths
+            n += b
+            if n + engine.B > engine.max_images or b != engine.B:
+                _flush_window(self, engine, paths, n, scan=False)
+                paths, n = [], 0
+        if engine is not None:
+            _flush_window(self, engine, paths, n, scan=False)
+            self.class_mean_probs = engine.mean_state.cpu().numpy()
+        self._wait_png()
+        self.save_data()
+
+
+@PSEUDO_POLICY.register('NT')
+class NoThresholdPseudoGenerator(ConstantThresholdPseudoGenerator):
+
+    def get_constant_threshold(self):
+        """:138-139  no threshold: every arg-max label is kept."""
+        return None
+
+
+@PSEUDO_POLICY.register('CBST')
+class CBSTPseudoGenerator(ConstantThresholdPseudoGenerator):
+
+    def get_constant_threshold(self):
+        raise NotImplementedError('CBST (pseudo_label_generator.py:142-165) is not ported yet (SURVEY.md 8f rank 3)')
+
+
+@PSEUDO_POLICY.register('IAS')
+class IASPseudoGenerator(BasePseudoGenerator):
+
+    def get_ias_threshold(self, class_probs_dict, num_classes, alpha, old_thresholds=None, gamma=1.0):
+        """:171-179 on the device.  ``class_probs_dict[c]`` is the reference's sample list for class c: the
+        previous threshold followed by the fp16 confidences of the batch (:198-201); None skips the class.
+        Returns float32[num_classes] like the reference."""
+        if old_thresholds is None:
+            old_thresholds = np.ones(num_classes)
+        out = np.ones(num_classes, dtype=np.float32)
+        for c in range(num_classes):
+            samples = class_probs_dict[c]
+            if samples is None:
+                continue
+            head = np.float64(samples[0])
+            if head != np.float64(old_thresholds[c]):
+                raise ValueError('class_probs_dict[c][0] must be old_thresholds[c] (the reference prepends the '
+                                 'previous threshold to the sample list, pseudo_label_generator.py:198)')
+            vals = np.asarray(samples[1:], dtype=np.float32)
+            if not np.array_equal(vals.astype(np.float16).astype(np.float32), vals):
+                raise ValueError('samples must be fp16-representable confidences (pseudo_label_generator.py:201)')
+            conf = torch.from_numpy(vals.reshape(1, 1, -1)).to(self.device) if vals.size else \
+                torch.zeros((1, 1, 1), device=self.device)
+            label = torch.zeros(conf.shape, dtype=torch.uint8, device=self.device)
+            if vals.size == 0:
+                label.fill_(255)
+            hist, _ = ops.ias_conf_hist(conf, label, 1, 1, key_lo=0)
+            state = torch.tensor([float(old_thresholds[c])], dtype=torch.float64, device=self.device)
+            flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+            _, temp = ops.ias_threshold_scan(hist, 1, 1, 0, alpha, 0.0, gamma, state, error_flag=flag)
+            if int(flag.item()) & 1:
+                raise ValueError('Quantiles must be in the range [0, 1]')
+            out[c] = temp.item()
+        return out
+
+    def run(self):
+        """:181-213"""
+        if self._already_done():
+            print('%% pseudo labels have existed')
+            return
+        C = self.cfg.dataset.num_classes
+        ias = self.cfg.pseudo_policy.ias
+        self.class_threshold = 0.9 * np.ones(C)                                            # :185
+        self.threshold_trace = []
+        engine, paths, n = None, [], 0
+        for logits, img_paths in self._iterate_logits():
+            if engine is None:
+                engine = self._engine = self._make_engine(logits, ias.alpha, ias.beta, ias.gamma)
+                engine.thr_state.copy_(torch.from_numpy(self.class_threshold))
+                engine.mean_state.copy_(torch.from_numpy(self.class_mean_probs))
+            b = logits.shape[0]
+            engine.phase_a(logits, n)                     # asynchronous; overlaps the next forward pass
+            paths += img_paths
+            n += b
+            if n + engine.B > engine.max_images or b != engine.B:
+                self._finish_window(engine, paths, n)
+                paths, n = [], 0
+        if engine is not None:
+            self._finish_window(engine, paths, n)
+            self.pow_rounding_certified = engine.check_errors()
+        self._wait_png()
+        self.save_data()
+
+    def _finish_window(self, engine, paths, n):
+        if n == 0:
+            return
+        _flush_window(self, engine, paths, n, scan=True)
+        g = engine._groups(n)
+        self.threshold_trace.append(engine.thr_groups[:g].cpu().numpy().copy())
+        self.class_threshold = engine.thr_state.cpu().numpy()
+        self.class_mean_probs = engine.mean_state.cpu().numpy()

@@ -1,0 +1,155 @@
+"""The reference-facing generator API (PSEUDO_POLICY[...](cfg).run()) and the sharded driver on the GPU."""
+
+import json
+import os
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+import golden_inputs as gi
+from oracle import ias as oias
+
+pytestmark = pytest.mark.gpu
+
+
+class Identity:
+    def eval(self):
+        return self
+
+    def __call__(self, x):
+        return {'logits': x}
+
+
+def make_cfg(spec, ptype='IAS'):
+    return SimpleNamespace(
+        dataset=SimpleNamespace(num_classes=spec['C']),
+        pseudo_policy=SimpleNamespace(type=ptype, batch_size=spec['B'], ct=SimpleNamespace(threshold=0.6),
+                                      ias=SimpleNamespace(alpha=spec['alpha'], beta=spec['beta'], gamma=spec['gamma'])),
+        preprocessor=SimpleNamespace(copy_paste=SimpleNamespace(gamma=spec['cp_gamma'])))
+
+
+def loader_of(batches):
+    return [{'images': lg, 'image_paths': p} for lg, p in batches]
+
+
+@pytest.mark.parametrize('name', ['ias_small', 'ias_c7'])
+@pytest.mark.parametrize('window_batches', [1, 3, 8])
+def test_ias_generator_run_matches_oracle_and_writes_reference_files(name, window_batches, tmp_path):
+    import cv2
+    import hiast_b200
+    hiast_b200.register_all()
+    from hiast_b200 import PSEUDO_POLICY
+    spec = gi.IAS_SPECS[name]
+    batches = gi.ias_batches(spec)
+    save_dir = str(tmp_path / 'run' / 'pseudo_labels')
+    gen = PSEUDO_POLICY['IAS'](make_cfg(spec), model=Identity(), loader=loader_of(batches), dataset_len=spec['N'],
+                               save_dir=save_dir, window_batches=window_batches)
+    gen.run()
+    oracle = oias.IASOracle(spec['C'], spec['alpha'], spec['beta'], spec['gamma'], spec['cp_gamma'])
+    oracle.run([(lg.cuda(), p) for lg, p in batches])
+    assert np.array_equal(gen.class_threshold, oracle.class_threshold)
+    assert np.array_equal(np.concatenate(gen.threshold_trace), np.stack(oracle.threshold_trace))
+    assert np.array_equal(gen.statics_class, oracle.statics_class)
+    np.testing.assert_allclose(gen.class_mean_probs, oracle.class_mean_probs, rtol=1e-6)
+    assert gen.sample_stats == oracle.sample_stats
+    assert gen.samples_class == oracle.samples_class
+    assert gen.pow_rounding_certified
+    paths = [p for _, ps in batches for p in ps]
+    for i, p in enumerate(paths):                                     # PNG payload == oracle label map
+        png = cv2.imread(os.path.join(save_dir, os.path.splitext(p)[0] + '_pseudo_label.png'), cv2.IMREAD_UNCHANGED)
+        assert np.array_equal(png, oracle.labels[i])
+    root = os.path.join(save_dir, '..')                               # save_data: same files as the reference
+    assert np.array_equal(np.load(os.path.join(root, 'class_threshold.npy')), oracle.class_threshold)
+    assert np.array_equal(np.load(os.path.join(root, 'statics_class.npy')), oracle.statics_class)
+    assert json.load(open(os.path.join(root, 'sample_class_stats.json'))) == \
+        json.loads(json.dumps(oracle.sample_stats))
+    assert json.load(open(os.path.join(root, 'samples_with_class.json'))) == \
+        json.loads(json.dumps(oracle.samples_class))
+    # second run() is a no-op once the directory is full (:182-183)
+    gen2 = PSEUDO_POLICY['IAS'].__new__(PSEUDO_POLICY['IAS'])
+    assert len(os.listdir(save_dir)) == spec['N']
+
+
+@pytest.mark.parametrize('ptype', ['CT', 'NT'])
+def test_constant_and_no_threshold_policies(ptype, tmp_path):
+    import hiast_b200
+    hiast_b200.register_all()
+    from hiast_b200 import PSEUDO_POLICY
+    spec = gi.IAS_SPECS['ias_small']
+    batches = gi.ias_batches(spec)
+    captured = {}
+
+    class Gen(PSEUDO_POLICY[ptype]):
+        def save_pseudo_label(self, plbl, img_path):
+            captured[img_path] = plbl.copy()
+
+        def save_data(self):
+            pass
+
+    gen = Gen(make_cfg(spec, ptype), model=Identity(), loader=loader_of(batches), dataset_len=spec['N'],
+              save_dir=str(tmp_path / 'p'), window_batches=2)
+    gen.run()
+    thr = None if ptype == 'NT' else 0.6 * np.ones(spec['C'])
+    stats = np.zeros(spec['C'], dtype=np.int64)
+    for lg, paths in batches:
+        conf, label = oias.softmax_max(lg.cuda())
+        for k, p in enumerate(paths):
+            want = label[k] if thr is None else oias.select_confident(conf[k], label[k], thr)
+            assert np.array_equal(captured[p], want.astype(np.uint8))
+            stats += np.bincount(want[want != 255], minlength=spec['C'])
+    assert np.array_equal(gen.statics_class, stats)
+
+
+def test_reference_method_surface(tmp_path):
+    """get_ias_threshold / select_and_save_confident_label keep the reference's signatures and results."""
+    import hiast_b200
+    hiast_b200.register_all()
+    from hiast_b200 import PSEUDO_POLICY
+    spec = gi.IAS_SPECS['ias_small']
+    gold = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'ias_small.npz'))
+    C = spec['C']
+    gen = PSEUDO_POLICY['IAS'](make_cfg(spec), model=Identity(), loader=[], dataset_len=0,
+                               save_dir=str(tmp_path / 'pl'), png_workers=0)
+    conf, label = gold['conf'][:2], gold['label'][:2].astype(np.int64)
+    thr = 0.9 * np.ones(C)
+    d = {c: [thr[c]] + list(conf[label == c].astype(np.float16)) for c in range(C)}     # the reference's dict (:198-201)
+    temp = gen.get_ias_threshold(d, C, spec['alpha'], thr, spec['gamma'])
+    want = oias.ias_quantile_thresholds(conf, label, thr, C, spec['alpha'], spec['gamma'])
+    assert temp.dtype == np.float32 and np.array_equal(temp, want)
+    gen.class_threshold = oias.ias_ema_update(thr, temp, spec['beta'])
+    assert np.array_equal(gen.class_threshold, gold['thr_trace'][0])
+    last = gen.select_and_save_confident_label(conf, label, ['a.png', 'b.png'])
+    assert np.array_equal(last.astype(np.uint8), gold['plbl'][1])
+    assert np.array_equal(gen.statics_class, gold['counts'][:2].sum(0))
+    assert sorted(os.listdir(str(tmp_path / 'pl'))) == ['a_pseudo_label.png', 'b_pseudo_label.png']
+
+
+def test_windowed_ring_driver_single_rank_equals_oracle():
+    """ShardedIAS with world_size 1 (the bench path): windows of 2 groups, double-buffered engine."""
+    from hiast_b200.ias_engine import IASEngine
+    from hiast_b200.sharded import ShardedIAS, window_images
+    spec = gi.IAS_SPECS['ias_small']
+    batches = gi.ias_batches(spec)
+    logits = torch.cat([lg for lg, _ in batches]).cuda()
+    window = 2 * spec['B']
+    eng = IASEngine(spec['C'], spec['H'], spec['W'], spec['B'], spec['alpha'], spec['beta'], spec['gamma'],
+                    spec['cp_gamma'], 2 * window)
+    got = {}
+
+    def on_window(w, plbl, counts, thr_groups):
+        got[w] = (plbl.cpu().numpy(), thr_groups.cpu().numpy())
+
+    def window_logits(w):
+        i0, n = window_images(w, window, spec['N'])
+        return logits[i0:i0 + n]
+
+    thr, mean, statics = ShardedIAS(eng, window, spec['N'], 0, 1).run(window_logits, on_window)
+    oracle = oias.IASOracle(spec['C'], spec['alpha'], spec['beta'], spec['gamma'], spec['cp_gamma'])
+    oracle.run([(lg.cuda(), p) for lg, p in batches])
+    assert np.array_equal(thr.cpu().numpy(), oracle.class_threshold)
+    assert np.array_equal(statics.cpu().numpy(), oracle.statics_class)
+    np.testing.assert_allclose(mean.cpu().numpy(), oracle.class_mean_probs, rtol=1e-6)
+    assert np.array_equal(np.concatenate([got[w][0] for w in sorted(got)]), np.stack(oracle.labels))
+    assert np.array_equal(np.concatenate([got[w][1] for w in sorted(got)]), np.stack(oracle.threshold_trace))

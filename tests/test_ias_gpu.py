@@ -165,7 +165,7 @@ def test_full_resolution_properties():
     thr_state = torch.full((C,), 0.9, dtype=torch.float64, device='cuda')
     hist_raw = hist.clone()     # the scan turns `hist` into prefix sums in place
     thr_groups, _ = o.ias_threshold_scan(hist, 2, C, o.ias_key_lo(C), 0.5, 0.9, 8.0, thr_state)
-    assert torch.equal(hist[:, :, -1].long(), want)          # last prefix = class total
+    assert torch.equal(hist[:, :, -1].long().cpu(), want)    # last prefix = class total
     plbl, counts, confsum = o.ias_select(conf, label, thr_groups, C, B)
     # mask property: kept pixels keep their label and have conf >= thr; ignored have conf < thr
     thr_px = thr_groups[torch.arange(4, device='cuda') // B][:, :, None, None].expand(4, C, H, W).gather(

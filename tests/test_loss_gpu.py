@@ -1,0 +1,150 @@
+"""GPU parity of the fused loss kernels and their reference-facing wrappers (1e-5 relative)."""
+
+import os
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+import golden_inputs as gi
+from oracle import losses as oloss
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), 'golden')
+RTOL = 1e-5      # BASELINE.json north_star: losses and gradients within 1e-5 relative
+
+
+def make_cfg(spec):
+    return SimpleNamespace(
+        model=SimpleNamespace(predictor=SimpleNamespace(
+            seg_loss=SimpleNamespace(type='CE', target_pseudo_weight=spec['w_seg']),
+            kld_loss=SimpleNamespace(weight=spec['w_kld']),
+            ent_loss=SimpleNamespace(weight=spec['w_ent']))),
+        cst_training=SimpleNamespace(is_enabled=True, cst_loss=SimpleNamespace(
+            type='SoftCE', weight=spec['w_cst'], region=spec['region'])))
+
+
+def grad_close(got, want):
+    got, want = got.double(), want.double()
+    scale = want.abs().max().item()
+    assert (got - want).abs().max().item() <= RTOL * scale + 1e-12
+
+
+@pytest.mark.parametrize('name', list(gi.LOSS_SPECS))
+def test_compute_loss_vs_reference_fixture(name):
+    """SelfTrainingSegmentor.compute_loss: same keys, values and gradient as the reference's own run."""
+    from hiast_b200.segmentor import SelfTrainingSegmentor
+    spec = gi.LOSS_SPECS[name]
+    gold = np.load(os.path.join(GOLD, name + '.npz'))
+    z = torch.from_numpy(gold['z']).cuda().requires_grad_(True)
+    t = torch.from_numpy(gold['t']).cuda()
+    plbl = torch.from_numpy(gold['plbl']).cuda()
+    s_z = s_lbl = None
+    if spec['source']:
+        s_z = torch.from_numpy(gold['s_z']).cuda().requires_grad_(True)
+        s_lbl = torch.from_numpy(gold['s_lbl']).cuda()
+    seg = SelfTrainingSegmentor(make_cfg(spec))
+    out = seg.compute_loss(z, plbl, t, s_z, s_lbl)
+    assert list(out.keys()) == list(gold['keys'])
+    for v in out.values():
+        assert v.dim() == 0 and v.dtype == torch.float32
+    np.testing.assert_allclose([v.item() for v in out.values()], gold['values'], rtol=RTOL)
+    sum(v.mean() for v in out.values()).backward()                  # base_trainer.py:129
+    grad_close(z.grad.cpu(), torch.from_numpy(gold['grad']))
+    if spec['source']:
+        grad_close(s_z.grad.cpu(), torch.from_numpy(gold['s_grad']))
+
+
+@pytest.mark.parametrize('region', ['ignored', 'confident', 'all'])
+@pytest.mark.parametrize('shape', [(2, 19, 64, 128), (1, 16, 33, 52), (2, 7, 15, 21)])
+def test_fused_terms_vs_oracle_on_cuda(shape, region):
+    """Vector (C=19/16) and generic (C=7, odd HW) kernels against the oracle's torch expressions on CUDA."""
+    from hiast_b200.losses import fused_terms
+    b, c, h, w = shape
+    g = torch.Generator().manual_seed(b * 1000 + c + h)
+    z = (torch.randn(b, c, h, w, generator=g) * 3).cuda().requires_grad_(True)
+    t = torch.softmax(torch.randn(b, c, h, w, generator=g) * 3, dim=1).cuda()
+    plbl = torch.randint(0, c, (b, h, w), generator=g)
+    plbl[torch.rand(b, h, w, generator=g) < 0.4] = 255
+    plbl = plbl.cuda()
+    wts = torch.tensor([1.0, 0.1, 1.0, 0.5], device='cuda')
+    for lbl in (plbl, plbl.to(torch.uint8)):                          # int64 and uint8 label inputs
+        z.grad = None
+        out = fused_terms(z, lbl, t, region=region, terms=15)
+        (out * wts).sum().backward()
+        z2 = z.detach().clone().requires_grad_(True)
+        ref = oloss.compute_loss(z2, plbl, t, cst_region=region)
+        sum(ref.values()).backward()
+        np.testing.assert_allclose((out * wts).tolist(), [v.item() for v in ref.values()], rtol=RTOL)
+        grad_close(z.grad, z2.grad)
+
+
+def test_config3_full_size():
+    """BASELINE.json configs[2]: 2x19x512x1024, 50 % ignored, CE 1.0 / KLD 0.1 / ENT 1.0 / SoftCE 0.5 'ignored'."""
+    from hiast_b200.segmentor import SelfTrainingSegmentor
+    spec = dict(w_seg=1.0, w_kld=0.1, w_ent=1.0, w_cst=0.5, region='ignored')
+    z = (torch.randn(2, 19, 512, 1024, generator=torch.Generator().manual_seed(0)) * 3).cuda().requires_grad_(True)
+    t = torch.softmax(torch.randn(2, 19, 512, 1024, generator=torch.Generator().manual_seed(1)) * 3, dim=1).cuda()
+    g2 = torch.Generator().manual_seed(2)
+    plbl = torch.randint(0, 19, (2, 512, 1024), generator=g2)
+    plbl[torch.rand(2, 512, 1024, generator=g2) < 0.5] = 255
+    plbl = plbl.cuda()
+    out = SelfTrainingSegmentor(make_cfg(spec)).compute_loss(z, plbl, t)
+    sum(v.mean() for v in out.values()).backward()
+    z2 = z.detach().clone().requires_grad_(True)
+    ref = oloss.compute_loss(z2, plbl, t)
+    sum(v.mean() for v in ref.values()).backward()
+    np.testing.assert_allclose([v.item() for v in out.values()], [v.item() for v in ref.values()], rtol=RTOL)
+    grad_close(z.grad, z2.grad)
+    # determinism of the two-stage reduction
+    out2 = SelfTrainingSegmentor(make_cfg(spec)).compute_loss(z.detach(), plbl, t)
+    assert [v.item() for v in out2.values()] == [v.item() for v in out.values()]
+
+
+def test_registry_losses():
+    """LOSS['CE'] / LOSS['SoftCE'] keep the reference signatures (losses.py:32-41)."""
+    import hiast_b200
+    hiast_b200.register_all()
+    from hiast_b200 import LOSS
+    g = torch.Generator().manual_seed(5)
+    z = (torch.randn(2, 19, 16, 32, generator=g) * 2).cuda().requires_grad_(True)
+    t = torch.softmax(torch.randn(2, 19, 16, 32, generator=g), dim=1).cuda()
+    y = torch.randint(0, 19, (2, 16, 32), generator=g)
+    y[torch.rand(2, 16, 32, generator=g) < 0.3] = 255
+    y = y.cuda()
+    np.testing.assert_allclose(LOSS['CE'](z, y).item(), oloss.ce(z, y).item(), rtol=RTOL)
+    for region in ('ignored', 'confident', 'all'):
+        got = LOSS['SoftCE'](z, t, refer_labels=y, region=region)
+        np.testing.assert_allclose(got.item(), oloss.soft_ce(z, t, refer_labels=y, region=region).item(), rtol=RTOL)
+    np.testing.assert_allclose(LOSS['SoftCE'](z, t).item(), oloss.soft_ce(z, t).item(), rtol=RTOL)   # refer_labels=None
+    with pytest.raises(ValueError):
+        LOSS['SoftCE'](z, t, refer_labels=y, region='bogus')
+
+
+def test_softce_divisor_counts_nonzero_products():
+    """losses.py:89 divides by the number of non-zero masked products: zero targets / exact log-softmax zeros
+    shrink the divisor."""
+    from hiast_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    z = (torch.randn(1, 19, 8, 16, generator=g) * 3)
+    z[0, 4, :, :8] += 60.0                      # log_softmax == 0 exactly for class 4 there
+    t = torch.softmax(torch.randn(1, 19, 8, 16, generator=g), dim=1)
+    t[0, 7] = 0.0                               # zero targets
+    y = torch.full((1, 8, 16), 255, dtype=torch.int64)
+    z, t, y = z.cuda(), t.cuda(), y.cuda()
+    sums, counts = ops.st_loss_fwd(z, t, y, 'ignored')
+    ref = (-torch.log_softmax(z, dim=1) * t)
+    assert counts[2].item() == int((ref != 0).sum().item()) < 19 * 8 * 16
+    np.testing.assert_allclose(sums[3].item() / counts[2].item(), oloss.soft_ce(z, t, refer_labels=y, region='ignored').item(),
+                               rtol=RTOL)
+
+
+def test_empty_regions_give_nan_like_the_reference():
+    from hiast_b200.losses import fused_terms
+    z = torch.randn(1, 19, 4, 8).cuda().requires_grad_(True)
+    y = torch.zeros((1, 4, 8), dtype=torch.int64).cuda()          # nothing ignored
+    out = fused_terms(z, y, None, terms=7)
+    assert torch.isfinite(out[0]) and torch.isfinite(out[1]) and torch.isnan(out[2])     # entropy: 0/0
+    out.sum().backward()
+    assert torch.isnan(z.grad).all()                                # inf * 0 in the reference's autograd

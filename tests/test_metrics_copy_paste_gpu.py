@@ -1,0 +1,154 @@
+"""GPU parity of the confusion-matrix / IoU kernels and the copy-paste kernel (bit-exact)."""
+
+import os
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+import golden_inputs as gi
+from oracle import copy_paste as ocp
+from oracle import metrics as omet
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), 'golden')
+
+
+@pytest.mark.parametrize('name', list(gi.METRIC_SPECS))
+def test_intersection_and_union_vs_reference_fixture(name):
+    from hiast_b200.metrics import confusion_matrix, intersectionAndUnionGPU
+    spec = gi.METRIC_SPECS[name]
+    gold = np.load(os.path.join(GOLD, name + '.npz'))
+    pred = torch.from_numpy(gold['pred']).cuda()
+    target = torch.from_numpy(gold['target']).cuda()
+    inter, union = intersectionAndUnionGPU(pred, target, spec['K'])
+    assert inter.dtype == torch.float32 and inter.is_cuda
+    assert np.array_equal(inter.cpu().numpy(), gold['intersection'])
+    assert np.array_equal(union.cpu().numpy(), gold['union'])
+    assert np.array_equal(pred.cpu().numpy(), gold['pred_after'])          # the reference's in-place side effect
+    cm = confusion_matrix(torch.from_numpy(gold['pred']).cuda(), target, spec['K'])
+    assert np.array_equal(cm.cpu().numpy(), omet.confusion_matrix(gold['pred'], gold['target'], spec['K']))
+
+
+@pytest.mark.parametrize('K', [19, 3, 120, 200])
+@pytest.mark.parametrize('dtype', [torch.int64, torch.uint8])
+def test_confusion_matrix_sizes_and_dtypes(K, dtype):
+    """shared-matrix path (K small), and the global-atomic path (K = 120, 200); ragged sizes."""
+    from hiast_b200 import ops
+    g = torch.Generator().manual_seed(K)
+    n = 100003
+    pred = torch.randint(0, K, (n,), generator=g)
+    tgt = torch.randint(0, K, (n,), generator=g)
+    tgt[torch.rand(n, generator=g) < 0.1] = 255
+    if K < 200:
+        pred[torch.rand(n, generator=g) < 0.02] = 250
+    pred, tgt = pred.to(dtype).cuda(), tgt.to(dtype).cuda()
+    cm = ops.confusion_matrix(pred, tgt, K)
+    want = omet.confusion_matrix(pred.cpu().numpy(), tgt.cpu().numpy(), K)
+    assert np.array_equal(cm.cpu().numpy(), want)
+    cm2 = ops.confusion_matrix(pred, tgt, K, cm=cm.clone())               # accumulates
+    assert np.array_equal(cm2.cpu().numpy(), 2 * want)
+
+
+def test_confusion_full_size_and_from_logits():
+    """int64 2x1024x2048 as the reference calls it + the fused argmax-from-logits form; row/col checksums."""
+    from hiast_b200 import ops
+    from hiast_b200.metrics import ConfusionMeter
+    g = torch.Generator(device='cuda').manual_seed(3)
+    logits = torch.randn(2, 19, 1024, 2048, generator=g, device='cuda')
+    logits[:, 3] += 1.0
+    target = torch.randint(0, 19, (2, 1024, 2048), generator=g, device='cuda')
+    target[torch.rand(2, 1024, 2048, generator=g, device='cuda') < 0.1] = 255
+    pred = logits.argmax(dim=1)
+    cm = ops.confusion_matrix(pred, target, 19)
+    valid = target != 255
+    want = torch.bincount(target[valid] * 20 + pred[valid], minlength=400).view(20, 20)
+    assert torch.equal(cm, want)
+    assert torch.equal(ops.confusion_from_logits(logits, target, 19), want)
+    assert int(cm.sum()) == int(valid.sum())
+    meter = ConfusionMeter(19)
+    meter.update(pred, target)
+    meter.update_from_logits(logits, target)
+    res = meter.result(exact=True)
+    inter = torch.diag(want)[:19].double()
+    union = (want.sum(0)[:19] + want.sum(1)[:19]).double() - inter
+    np.testing.assert_allclose(res['iou'], (inter / (union + 1e-10)).cpu().numpy(), rtol=1e-6)
+    ref = omet.iou_from_sums(meter.intersection_sum.cpu().numpy(), meter.union_sum.cpu().numpy(), synthia=True)
+    got = meter.result(synthia=True)
+    assert got['miou'] == ref['miou'] and got['miou_16'] == ref['miou_16'] and got['miou_13'] == ref['miou_13']
+
+
+def test_argmax_ties_take_first_index():
+    from hiast_b200 import ops
+    logits = torch.zeros(1, 5, 4, 4, device='cuda')
+    logits[0, 2] = 1.0
+    logits[0, 4] = 1.0
+    target = torch.full((1, 4, 4), 2, dtype=torch.int64, device='cuda')
+    cm = ops.confusion_from_logits(logits, target, 5)
+    assert cm[2, 2].item() == 16
+
+
+def cp_cfg(spec, source='GTAV'):
+    return SimpleNamespace(dataset=SimpleNamespace(source=SimpleNamespace(type=source), num_classes=spec['C']),
+                           preprocessor=SimpleNamespace(copy_paste=SimpleNamespace(
+                               selected_num_classes=spec['selected'], mode='original')))
+
+
+def test_copy_paste_vs_reference_fixture():
+    """PREPROCESSOR['CopyPaste'](cfg, dataset, class_value).run(img, lbl): same donors (seeded np.random), same
+    pixels as the reference's run."""
+    from hiast_b200.preprocessor import CopyPaste
+    spec = gi.COPY_PASTE_SPEC
+    gold = np.load(os.path.join(GOLD, 'copy_paste.npz'))
+    ds = gi.CopyPasteDataset(spec)
+    cp = CopyPaste(cp_cfg(spec), ds, gi.copy_paste_class_value(spec))
+    assert np.array_equal(cp.hard_classes, gold['hard'])
+    np.testing.assert_array_equal(cp.class_probs, gold['probs'])
+    np.random.seed(spec['seed'])
+    for i in range(spec['n_run']):
+        img, lbl, _ = ds.load_data(i)
+        o_img, o_lbl, o_mask = cp.run(img, lbl)
+        assert np.array_equal(o_img, gold['img_%d' % i])
+        assert np.array_equal(o_lbl, gold['lbl_%d' % i])
+        assert np.array_equal(o_mask, gold['mask_%d' % i])
+        assert o_img is img and o_lbl is lbl                                  # edited in place like the reference
+
+
+@pytest.mark.parametrize('hw', [(64, 96), (37, 53), (1024, 2048)])
+def test_copy_paste_batched_vs_oracle(hw):
+    """Batched kernel (vector and ragged paths, full size) with a donor index array against the oracle."""
+    from hiast_b200 import ops
+    h, w = hw
+    n = 3
+    rs = np.random.RandomState(h)
+    img = rs.randint(0, 256, size=(n, h, w, 3)).astype(np.uint8)
+    lbl = rs.randint(0, 19, size=(n, h, w)).astype(np.uint8)
+    d_img = rs.randint(0, 256, size=(n + 1, h, w, 3)).astype(np.uint8)
+    coarse = rs.randint(0, 19, size=(n + 1, (h + 7) // 8, (w + 7) // 8))
+    d_lbl = np.kron(coarse, np.ones((8, 8), dtype=np.int64))[:, :h, :w].astype(np.uint8)
+    d_lbl[rs.rand(n + 1, h, w) < 0.2] = 255
+    hard = [10, 8, 3, 16, 11, 6, 9, 14, 18, 1, 17, 0, 2, 5]
+    donor_index = np.array([3, 0, 2], dtype=np.int32)
+    want_img, want_lbl = img.copy(), lbl.copy()
+    want_mask = np.full_like(lbl, 255)
+    for i in range(n):
+        ocp.paste(want_img[i], want_lbl[i], want_mask[i], d_img[donor_index[i]], d_lbl[donor_index[i]], hard)
+    t = lambda a: torch.from_numpy(a).cuda()
+    g_img, g_lbl, g_mask = t(img), t(lbl), torch.full((n, h, w), 255, dtype=torch.uint8, device='cuda')
+    ops.copy_paste(g_img, g_lbl, g_mask, t(d_img), t(d_lbl), hard, t(donor_index))
+    assert np.array_equal(g_img.cpu().numpy(), want_img)
+    assert np.array_equal(g_lbl.cpu().numpy(), want_lbl)
+    assert np.array_equal(g_mask.cpu().numpy(), want_mask)
+
+
+def test_copy_paste_synthia_probabilities_are_defined():
+    """The reference crashes for SYNTHIA (NaN sampling probabilities); here ignored classes get p = 0."""
+    from hiast_b200.preprocessor import CopyPaste
+    spec = gi.COPY_PASTE_SPEC
+    ds = gi.CopyPasteDataset(spec)
+    cp = CopyPaste(cp_cfg(spec, 'SYNTHIA'), ds, gi.copy_paste_class_value(spec))
+    assert np.all(cp.class_probs[[9, 14, 16]] == 0) and np.isclose(cp.class_probs.sum(), 1.0)
+    assert not set(cp.hard_classes) & {9, 14, 16}
+    want = ocp.class_probs(cp.class_value, nan_to_zero=True)
+    np.testing.assert_array_equal(cp.class_probs, want)

@@ -1,0 +1,89 @@
+"""Host-side logic of the multi-GPU IAS path with world_size 2 and 3 over gloo on CPU: group partitioning,
+the rank-to-rank threshold hand-off order, the all-gather replay of the mean-prob EMA.  The kernels are
+replaced by a CPU stand-in engine (tests/host_engine.py); sharded == unsharded == oracle, bit for bit."""
+
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import golden_inputs as gi
+from hiast_b200.sharded import ShardedIAS, local_windows, window_images
+from oracle import ias as oias
+
+SPEC = dict(C=7, H=12, W=20, N=13, B=2, alpha=0.5, beta=0.9, gamma=8.0, cp_gamma=0.99, seed=31, dist='mixed', absent=())
+
+
+def test_window_striping():
+    assert local_windows(5, 0, 2) == [0, 2, 4] and local_windows(5, 1, 2) == [1, 3]
+    assert local_windows(2, 3, 4) == []
+    assert window_images(2, 4, 9) == (8, 1)            # last window holds one image
+    assert window_images(1, 4, 9) == (4, 4)
+    assert window_images(3, 4, 9) == (12, 0)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, out_dir):
+    import sys
+    sys.path.insert(0, os.path.dirname(__file__))
+    from host_engine import HostEngine
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        s = SPEC
+        logits = torch.cat([lg for lg, _ in gi.ias_batches(s)])
+        window = 2 * s['B']                               # 2 groups per window -> 4 windows for 13 images
+        eng = HostEngine(s['C'], s['H'], s['W'], s['B'], s['alpha'], s['beta'], s['gamma'], s['cp_gamma'], 2 * window)
+        drv = ShardedIAS(eng, window, s['N'])
+        got = {}
+
+        def on_window(w, plbl, counts, thr_groups):
+            got[w] = (np.array(plbl), np.array(thr_groups))
+
+        def window_logits(w):
+            i0, n = window_images(w, window, s['N'])
+            return logits[i0:i0 + n]
+
+        thr, mean, statics = drv.run(window_logits, on_window)
+        np.savez(os.path.join(out_dir, 'rank%d.npz' % rank), thr=thr.numpy(), mean=mean.numpy(),
+                 statics=statics.numpy(), windows=np.array(sorted(got)),
+                 **{'plbl_%d' % w: v[0] for w, v in got.items()}, **{'thr_%d' % w: v[1] for w, v in got.items()})
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world', [2, 3])
+def test_sharded_equals_unsharded_equals_oracle(world, tmp_path):
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    s = SPEC
+    oracle = oias.IASOracle(s['C'], s['alpha'], s['beta'], s['gamma'], s['cp_gamma'])
+    oracle.run(gi.ias_batches(s))
+    ranks = [np.load(os.path.join(str(tmp_path), 'rank%d.npz' % r)) for r in range(world)]
+    for r in ranks:                                         # every rank ends with the same global state
+        assert np.array_equal(r['thr'], oracle.class_threshold)
+        assert np.array_equal(r['statics'], oracle.statics_class)
+        np.testing.assert_allclose(r['mean'], oracle.class_mean_probs, rtol=1e-6)
+        assert np.array_equal(r['mean'], ranks[0]['mean'])
+    n_win = (s['N'] + 2 * s['B'] - 1) // (2 * s['B'])
+    by_window = {}
+    for r in ranks:
+        for w in r['windows']:
+            by_window[int(w)] = (r['plbl_%d' % w], r['thr_%d' % w])
+    assert sorted(by_window) == list(range(n_win))
+    plbl = np.concatenate([by_window[w][0] for w in range(n_win)])
+    assert np.array_equal(plbl, np.stack(oracle.labels))
+    thr_groups = np.concatenate([by_window[w][1] for w in range(n_win)])
+    assert np.array_equal(thr_groups, np.stack(oracle.threshold_trace))
