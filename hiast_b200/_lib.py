@@ -28,6 +28,7 @@ _SIGNATURES = {
     'hiast_last_cuda_error': (_i, []),
     'hiast_device_sm_count': (_i, []),
     'hiast_ias_key_lo': (_i, [_i]),
+    'hiast_ias_hist_row_stride': (_i, [_i]),
     'hiast_ias_hist_bytes': (_sz, [_i, _i, _i]),
     'hiast_ias_softmax_hist': (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     'hiast_ias_conf_hist': (_i, [_vp, _vp, _i, _i, _i64, _i, _i, _i, _i, _vp, _vp, _vp]),

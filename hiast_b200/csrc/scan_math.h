@@ -36,12 +36,20 @@
 
 namespace hiast {
 
-// Value of a non-negative fp16 bit pattern as a double (exact).
+// Value of a non-negative, finite fp16 bit pattern as a double (exact), by bit manipulation.
 HIAST_HD double half_bits_to_double(unsigned bits) {
-  const int e = static_cast<int>((bits >> 10) & 0x1f);
-  const int m = static_cast<int>(bits & 0x3ff);
-  if (e == 0) return ldexp(static_cast<double>(m), -24);
-  return ldexp(static_cast<double>(m | 0x400), e - 25);
+  const unsigned e = (bits >> 10) & 0x1fu;
+  const unsigned m = bits & 0x3ffu;
+  if (e == 0) return static_cast<double>(m) * 5.9604644775390625e-08;  // subnormal: m * 2^-24
+  const unsigned long long d = (static_cast<unsigned long long>(e + (1023 - 15)) << 52) |
+                               (static_cast<unsigned long long>(m) << 42);
+#if defined(__CUDA_ARCH__)
+  return __longlong_as_double(static_cast<long long>(d));
+#else
+  double r;
+  memcpy(&r, &d, sizeof(r));
+  return r;
+#endif
 }
 
 struct dd {
@@ -95,6 +103,14 @@ HIAST_HD int upper_bin(const P* prefix, int nb, long long j) {
   return lo;
 }
 
+// Serial searcher (host hook, single-thread device use).
+template <typename P>
+struct SerialSearch {
+  const P* prefix;
+  int nb;
+  HIAST_HD int operator()(long long j) const { return upper_bin(prefix, nb, j); }
+};
+
 // number of bins whose fp16 value is < thr
 HIAST_HD int bins_below(int key_lo, int nb, double thr) {
   int lo = 0, hi = nb;  // first bin with value >= thr
@@ -143,10 +159,10 @@ HIAST_HD double lerp_np(double a, double b, double g) {  // numpy >= 1.22 _lerp
 //              the result is not certified independent of the last-bit rounding of the host's pow()
 //              (glibc's pow is within 1 ulp but not always correctly rounded; this implementation
 //              is correctly rounded for integer gamma).  Never observed on real data; see DESIGN.md.
-template <typename P>
+template <typename P, typename Search>
 HIAST_HD double ias_threshold_step(const P* prefix, int nb, int key_lo, double thr,
                                    double alpha, double beta, double gamma,
-                                   float* temp_out, int* err) {
+                                   float* temp_out, int* err, const Search& search) {
   const long long m = static_cast<long long>(prefix[nb - 1]);
   const double p = ias_pow(thr, gamma);
   const double q = HIAST_DSUB(1.0, HIAST_DMUL(alpha, p));
@@ -169,10 +185,10 @@ HIAST_HD double ias_threshold_step(const P* prefix, int nb, int key_lo, double t
     const long long r = kb > 0 ? static_cast<long long>(prefix[kb - 1]) : 0;  // rank of thr in the merged list
     double a, b;
     if (lo_i == r) a = thr;
-    else a = half_bits_to_double(static_cast<unsigned>(key_lo + upper_bin(prefix, nb, lo_i < r ? lo_i : lo_i - 1)));
+    else a = half_bits_to_double(static_cast<unsigned>(key_lo + search(lo_i < r ? lo_i : lo_i - 1)));
     if (hi_i == lo_i) b = a;
     else if (hi_i == r) b = thr;
-    else b = half_bits_to_double(static_cast<unsigned>(key_lo + upper_bin(prefix, nb, hi_i < r ? hi_i : hi_i - 1)));
+    else b = half_bits_to_double(static_cast<unsigned>(key_lo + search(hi_i < r ? hi_i : hi_i - 1)));
     t64 = lerp_np(a, b, pos.g);
     if (p > 0.0 && alpha != 0.0 && gamma != 1.0) {
       // certificate: same order statistics and same float32 result for p -/+ 1 ulp
@@ -193,6 +209,14 @@ HIAST_HD double ias_threshold_step(const P* prefix, int nb, int key_lo, double t
   double nt = HIAST_DADD(HIAST_DMUL(beta, thr), static_cast<double>(prod));
   if (nt >= 1.0) nt = 0.999;
   return nt;
+}
+
+template <typename P>
+HIAST_HD double ias_threshold_step(const P* prefix, int nb, int key_lo, double thr,
+                                   double alpha, double beta, double gamma,
+                                   float* temp_out, int* err) {
+  const SerialSearch<P> search = {prefix, nb};
+  return ias_threshold_step(prefix, nb, key_lo, thr, alpha, beta, gamma, temp_out, err, search);
 }
 
 }  // namespace hiast

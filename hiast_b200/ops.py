@@ -15,7 +15,7 @@ from . import _lib
 from ._lib import IGNORE, KEY_ONE, REGION, TERM_CE, TERM_CST, TERM_ENT, TERM_KLD, check, lib, ptr, require_cuda, stream_ptr
 
 __all__ = [
-    'ias_key_lo', 'ias_num_bins', 'ias_new_hist', 'ias_softmax_hist', 'ias_conf_hist', 'ias_threshold_scan',
+    'ias_key_lo', 'ias_num_bins', 'ias_row_stride', 'ias_new_hist', 'ias_softmax_hist', 'ias_conf_hist', 'ias_threshold_scan',
     'ias_select', 'ias_meanprob_scan', 'copy_paste', 'hard_lut', 'st_loss_fwd', 'st_loss_bwd',
     'confusion_matrix', 'confusion_from_logits', 'iou_from_confusion',
 ]
@@ -33,8 +33,14 @@ def ias_num_bins(key_lo):
     return KEY_ONE - key_lo + 1
 
 
+def ias_row_stride(key_lo):
+    """Words per histogram row: the bins padded to a multiple of 4 (16-byte aligned rows)."""
+    return lib().hiast_ias_hist_row_stride(int(key_lo))
+
+
 def ias_new_hist(n_groups, num_classes, key_lo, device):
-    return torch.empty((n_groups, num_classes, ias_num_bins(key_lo)), dtype=torch.int32, device=device)
+    """uint32 (as int32) [G, C, row_stride]; the first ias_num_bins(key_lo) entries of a row are its bins."""
+    return torch.empty((n_groups, num_classes, ias_row_stride(key_lo)), dtype=torch.int32, device=device)
 
 
 def _n_groups(n_images, group_size):
@@ -57,7 +63,9 @@ def ias_softmax_hist(logits, group_size, key_lo=None, conf=None, label=None, his
         accumulate = False
     else:
         require_cuda(hist, torch.int32, 'hist')
-        assert hist.numel() >= g * c * ias_num_bins(key_lo)
+        assert hist.numel() >= g * c * ias_row_stride(key_lo)
+    if n == 0:
+        return conf, label, hist
     check(lib().hiast_ias_softmax_hist(ptr(logits), n, c, h, w, int(group_size), int(key_lo), int(bool(accumulate)),
                                        int(hist_mode), ptr(conf), ptr(label), ptr(hist), stream_ptr(dev)),
           'hiast_ias_softmax_hist')

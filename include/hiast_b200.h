@@ -65,7 +65,9 @@ HIAST_API int         hiast_device_sm_count(void);         /* SMs of the current
 
 /* Smallest fp16 key a confidence 1/sum(exp) can round to with C classes: fp16_rn(1.0f/C).  */
 HIAST_API int    hiast_ias_key_lo(int C);
-/* Bytes of a histogram buffer uint32 [n_groups][C][HIAST_KEY_ONE - key_lo + 1].            */
+/* Histogram buffers are uint32 [n_groups][C][row_stride]; a row holds the HIAST_KEY_ONE - key_lo + 1
+ * bins of one (group, class), padded to a multiple of 4 words so that rows are 16-byte aligned.  */
+HIAST_API int    hiast_ias_hist_row_stride(int key_lo);
 HIAST_API size_t hiast_ias_hist_bytes(int n_groups, int C, int key_lo);
 
 /* a1+a2  workflows/pseudo_label_generator.py:192-193,198-201

@@ -53,7 +53,8 @@ def test_argument_validation_without_gpu(built_lib):
     l = _lib.lib()
     assert l.hiast_ias_key_lo(19) == 0x2ABD
     assert l.hiast_ias_key_lo(0) == -1
-    assert l.hiast_ias_hist_bytes(3, 19, 0x2ABD) == 3 * 19 * (0x3C00 - 0x2ABD + 1) * 4
+    assert l.hiast_ias_hist_row_stride(0x2ABD) == 4420 and l.hiast_ias_hist_row_stride(0) == 15364
+    assert l.hiast_ias_hist_bytes(3, 19, 0x2ABD) == 3 * 19 * 4420 * 4
     assert l.hiast_ias_softmax_hist(None, 1, 19, 4, 4, 2, 0, 0, 0, None, None, None, None) == -1
     assert l.hiast_st_loss_fwd(None, None, None, 8, 1, 19, 4, 0, 15, None, None, None, 0, None) == -1
     assert l.hiast_confusion_matrix(None, None, 8, 4, 19, 255, None, None, None) == -1

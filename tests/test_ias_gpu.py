@@ -29,7 +29,7 @@ def torch_softmax_max(logits):
 
 
 @pytest.mark.parametrize('shape', [(2, 19, 64, 128), (3, 19, 33, 52), (1, 16, 40, 64), (2, 7, 31, 51), (1, 40, 9, 13)])
-@pytest.mark.parametrize('mode', [1, 2, 3])
+@pytest.mark.parametrize('mode', [1, 2, 3, 4, 5, 6, 11, 16, 21, 25, 26])
 def test_phase_a_bit_exact_vs_torch_cuda(shape, mode):
     o = ops()
     g = torch.Generator().manual_seed(sum(shape) + mode)
@@ -45,7 +45,9 @@ def test_phase_a_bit_exact_vs_torch_cuda(shape, mode):
     want_hist = np.stack([oias.class_key_histogram(want_conf[2 * k:2 * k + 2].cpu().numpy(),
                                                    want_label[2 * k:2 * k + 2].cpu().numpy(), c, key_lo)
                           for k in range(G)])
-    assert np.array_equal(hist.cpu().numpy().astype(np.uint32), want_hist)
+    nb = o.ias_num_bins(key_lo)
+    assert hist.shape[2] == o.ias_row_stride(key_lo) and int(hist[:, :, nb:].sum()) == 0
+    assert np.array_equal(hist[:, :, :nb].cpu().numpy().astype(np.uint32), want_hist)
 
 
 def test_phase_a_ties_and_near_ties():
@@ -130,7 +132,7 @@ def test_config0_vs_oracle():
     logits = torch.cat([lg for lg, _ in batches]).cuda()
     oracle = oias.IASOracle(C, spec['alpha'], spec['beta'], spec['gamma'], spec['cp_gamma'])
     oracle.run([(lg.cuda(), p) for lg, p in batches])
-    for mode in (1, 2, 3):
+    for mode in (1, 2, 3, 4, 5, 6, 11, 16, 21, 25, 26):
         conf, label, hist = o.ias_softmax_hist(logits, group_size=B, hist_mode=mode)
         thr_state = torch.full((C,), 0.9, dtype=torch.float64, device='cuda')
         flag = torch.zeros(1, dtype=torch.int32, device='cuda')
@@ -165,7 +167,8 @@ def test_full_resolution_properties():
     thr_state = torch.full((C,), 0.9, dtype=torch.float64, device='cuda')
     hist_raw = hist.clone()     # the scan turns `hist` into prefix sums in place
     thr_groups, _ = o.ias_threshold_scan(hist, 2, C, o.ias_key_lo(C), 0.5, 0.9, 8.0, thr_state)
-    assert torch.equal(hist[:, :, -1].long().cpu(), want)    # last prefix = class total
+    nb = o.ias_num_bins(o.ias_key_lo(C))
+    assert torch.equal(hist[:, :, nb - 1].long().cpu(), want)    # last prefix = class total
     plbl, counts, confsum = o.ias_select(conf, label, thr_groups, C, B)
     # mask property: kept pixels keep their label and have conf >= thr; ignored have conf < thr
     thr_px = thr_groups[torch.arange(4, device='cuda') // B][:, :, None, None].expand(4, C, H, W).gather(
