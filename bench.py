@@ -220,6 +220,7 @@ def gpu_arm(args):
     device = torch.device('cuda', local)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        os.environ.setdefault('TORCH_NCCL_SHOW_EAGER_INIT_P2P_SERIALIZATION_WARNING', 'false')
         dist.init_process_group('nccl', device_id=device)
     if args.gpus != world and rank == 0 and world > 1:
         print('warning: --gpus %d but WORLD_SIZE %d' % (args.gpus, world), file=sys.stderr)

@@ -85,7 +85,18 @@ HIAST_HD double powi_dd(double x, int n) {
   return HIAST_DADD(acc.hi, acc.lo);
 }
 
+// x^8 by three double-double squarings (gamma = 8 in every shipped config).
+HIAST_HD double pow8_dd(double x) {
+  dd a;
+  a.hi = HIAST_DMUL(x, x);
+  a.lo = HIAST_FMA(x, x, -a.hi);
+  a = dd_mul(a, a);
+  a = dd_mul(a, a);
+  return HIAST_DADD(a.hi, a.lo);
+}
+
 HIAST_HD double ias_pow(double thr, double gamma) {
+  if (gamma == 8.0) return pow8_dd(thr);
   const int gi = static_cast<int>(gamma);
   if (static_cast<double>(gi) == gamma && gi >= 1 && gi <= 64) return powi_dd(thr, gi);
   if (gamma == 0.0) return 1.0;
@@ -111,14 +122,29 @@ struct SerialSearch {
   HIAST_HD int operator()(long long j) const { return upper_bin(prefix, nb, j); }
 };
 
-// number of bins whose fp16 value is < thr
+// number of bins (keys key_lo + 0 .. key_lo + nb - 1) whose fp16 value is < thr: the smallest fp16 key whose
+// value is >= thr, found directly from the bits of thr (truncate to fp16, step up if that lost anything).
 HIAST_HD int bins_below(int key_lo, int nb, double thr) {
-  int lo = 0, hi = nb;  // first bin with value >= thr
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (half_bits_to_double(static_cast<unsigned>(key_lo + mid)) < thr) lo = mid + 1; else hi = mid;
+  if (!(thr > 0.0)) return 0;                       // every key >= 0 has value >= thr
+  if (thr > 65504.0) return nb;
+  long long db;
+#if defined(__CUDA_ARCH__)
+  db = __double_as_longlong(thr);
+#else
+  memcpy(&db, &thr, sizeof(db));
+#endif
+  const int e = static_cast<int>((db >> 52) & 0x7ff) - 1023;     // unbiased exponent of thr
+  int key;                                                       // largest key with value <= thr
+  if (e >= -14) {
+    key = ((e + 15) << 10) | static_cast<int>((db >> 42) & 0x3ff);
+  } else {
+    key = static_cast<int>(thr * 16777216.0);                   // subnormal half: floor(thr * 2^24), exact product
   }
-  return lo;
+  if (half_bits_to_double(static_cast<unsigned>(key)) < thr) key += 1;
+  int b = key - key_lo;
+  if (b < 0) b = 0;
+  if (b > nb) b = nb;
+  return b;
 }
 
 HIAST_HD double bits_step(double x, int dir) {  // next representable double above (dir>0) / below a positive x
@@ -184,11 +210,20 @@ HIAST_HD double ias_threshold_step(const P* prefix, int nb, int key_lo, double t
     const int kb = bins_below(key_lo, nb, thr);
     const long long r = kb > 0 ? static_cast<long long>(prefix[kb - 1]) : 0;  // rank of thr in the merged list
     double a, b;
+    int bin_a = -1;
     if (lo_i == r) a = thr;
-    else a = half_bits_to_double(static_cast<unsigned>(key_lo + search(lo_i < r ? lo_i : lo_i - 1)));
+    else {
+      bin_a = search(lo_i < r ? lo_i : lo_i - 1);
+      a = half_bits_to_double(static_cast<unsigned>(key_lo + bin_a));
+    }
     if (hi_i == lo_i) b = a;
     else if (hi_i == r) b = thr;
-    else b = half_bits_to_double(static_cast<unsigned>(key_lo + search(hi_i < r ? hi_i : hi_i - 1)));
+    else {
+      const long long j = hi_i < r ? hi_i : hi_i - 1;
+      // the next order statistic usually sits in the same bin as the previous one
+      if (bin_a >= 0 && static_cast<long long>(prefix[bin_a]) > j) b = a;
+      else b = half_bits_to_double(static_cast<unsigned>(key_lo + search(j)));
+    }
     t64 = lerp_np(a, b, pos.g);
     if (p > 0.0 && alpha != 0.0 && gamma != 1.0) {
       // certificate: same order statistics and same float32 result for p -/+ 1 ulp

@@ -29,7 +29,7 @@ def torch_softmax_max(logits):
 
 
 @pytest.mark.parametrize('shape', [(2, 19, 64, 128), (3, 19, 33, 52), (1, 16, 40, 64), (2, 7, 31, 51), (1, 40, 9, 13)])
-@pytest.mark.parametrize('mode', [1, 2, 3, 4, 5, 6, 11, 16, 21, 25, 26])
+@pytest.mark.parametrize('mode', [1, 2, 3, 4, 5, 6, 11, 16, 21, 25, 26, 31, 36, 41, 46])
 def test_phase_a_bit_exact_vs_torch_cuda(shape, mode):
     o = ops()
     g = torch.Generator().manual_seed(sum(shape) + mode)
@@ -64,11 +64,12 @@ def test_phase_a_ties_and_near_ties():
     x[2] = 0.0                                              # all equal -> conf = 1/19, label 0
     x[3, 5] += 40.0                                         # saturated: conf == 1.0
     x = x.cuda()
-    conf, label, _ = o.ias_softmax_hist(x, group_size=2)
     want_conf, want_label = torch_softmax_max(x)
-    assert torch.equal(conf, want_conf)
-    assert torch.equal(label.long(), want_label)
-    assert (label[2] == 0).all() and (conf[3] == 1.0).any()
+    for mode in (0, 1, 6, 16, 26, 36, 46):
+        conf, label, _ = o.ias_softmax_hist(x, group_size=2, hist_mode=mode)
+        assert torch.equal(conf, want_conf), mode
+        assert torch.equal(label.long(), want_label), mode
+        assert (label[2] == 0).all() and (conf[3] == 1.0).any()
 
 
 @pytest.mark.parametrize('name', ['ias_small', 'ias_c7', 'ias_g25'])
@@ -132,7 +133,7 @@ def test_config0_vs_oracle():
     logits = torch.cat([lg for lg, _ in batches]).cuda()
     oracle = oias.IASOracle(C, spec['alpha'], spec['beta'], spec['gamma'], spec['cp_gamma'])
     oracle.run([(lg.cuda(), p) for lg, p in batches])
-    for mode in (1, 2, 3, 4, 5, 6, 11, 16, 21, 25, 26):
+    for mode in (1, 2, 3, 4, 5, 6, 11, 16, 21, 25, 26, 31, 36, 41, 46):
         conf, label, hist = o.ias_softmax_hist(logits, group_size=B, hist_mode=mode)
         thr_state = torch.full((C,), 0.9, dtype=torch.float64, device='cuda')
         flag = torch.zeros(1, dtype=torch.int32, device='cuda')
