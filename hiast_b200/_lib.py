@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(_HERE, 'libhiast_b200.so')
 OK = 0
 REGION = {'ignored': 0, 'confident': 1, 'all': 2}
 TERM_CE, TERM_KLD, TERM_ENT, TERM_CST = 1, 2, 4, 8
+CST_SOFTCE, CST_KLDIV, CST_MSE = 0, 16, 32
 KEY_ONE = 0x3C00
 IGNORE = 255
 

@@ -35,8 +35,10 @@ struct LossArgs {
   int C;
   int64_t HW;
   int region;
-  int terms;
+  int terms;   // HIAST_TERM_* | HIAST_CST_* (kind of the consistency term)
 };
+
+__device__ __forceinline__ int cst_kind(int terms) { return terms & (HIAST_CST_KLDIV | HIAST_CST_MSE); }
 
 __device__ __forceinline__ int load_label(const void* p, int bytes, size_t i) {
   if (bytes == 1) return static_cast<const uint8_t*>(p)[i];
@@ -56,7 +58,7 @@ struct PixelSums {
 // log-softmax pieces of one pixel held in registers
 template <int C>
 struct PixelLS {
-  float m, logs, inv_s;
+  float m, logs, inv_s, sum;
   __device__ __forceinline__ void init(const float (&z)[C]) {
     m = z[0];
 #pragma unroll
@@ -66,7 +68,9 @@ struct PixelLS {
     for (int c = 0; c < C; ++c) s += expf(z[c] - m);
     logs = logf(s);
     inv_s = 1.0f / s;
+    sum = s;
   }
+  __device__ __forceinline__ float prob(float zc) const { return __fdiv_rn(expf(zc - m), sum); }  // ATen softmax
   __device__ __forceinline__ float logp(float zc) const { return (zc - m) - logs; }
   __device__ __forceinline__ float p(float zc) const { return expf(zc - m) * inv_s; }
 };
@@ -100,50 +104,91 @@ __device__ __forceinline__ void pixel_forward(const float (&z)[C], const float (
   if ((terms & HIAST_TERM_CST) && in_region(region, ignored)) {
     float sc = 0.f;
     int nz = 0;
+    const int kind = cst_kind(terms);
+    if (kind == HIAST_CST_KLDIV) {
+      // losses.py:16-23: KLDivLoss(reduction='none')(log_softmax(z), softmax(t)) = xlogy(tp,tp) - tp*logp
+      PixelLS<C> lt;
+      lt.init(t);
 #pragma unroll
-    for (int c = 0; c < C; ++c) {
-      const float prod = __fmul_rn(-ls.logp(z[c]), t[c]);
-      nz += (prod != 0.f);
-      sc += prod;
+      for (int c = 0; c < C; ++c) {
+        const float tp = lt.prob(t[c]);
+        const float elem = (tp == 0.f ? 0.f : __fmul_rn(tp, logf(tp))) - __fmul_rn(tp, ls.logp(z[c]));
+        nz += (elem != 0.f);
+        sc += elem;
+      }
+    } else if (kind == HIAST_CST_MSE) {
+#pragma unroll
+      for (int c = 0; c < C; ++c) {      // losses.py:9-13: (z - t)^2
+        const float d = z[c] - t[c];
+        const float elem = __fmul_rn(d, d);
+        nz += (elem != 0.f);
+        sc += elem;
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const float prod = __fmul_rn(-ls.logp(z[c]), t[c]);
+        nz += (prod != 0.f);
+        sc += prod;
+      }
     }
     acc.cst += static_cast<double>(sc);
     acc.n_nz += nz;
   }
 }
 
+// Backward of one pixel with a small register footprint: `z` is overwritten by its log-softmax (the gradient
+// only needs logp and p = exp(logp)), KLDIV targets are turned into probabilities in place, and the per-pixel
+// scalars are kept in this struct; grad(c) is then evaluated channel by channel right before the store.
 template <int C>
-__device__ __forceinline__ void pixel_backward(const float (&z)[C], const float (&t)[C], int y, int region, int terms,
-                                               const float (&sc)[4], float (&g)[C]) {
-  PixelLS<C> ls;
-  ls.init(z);
-  const bool ignored = (y == HIAST_IGNORE_LABEL);
-  float p[C];
+struct PixelBwd {
+  float a, kb, ce, ent, h, cst, T, mls;  // mls = max + log-sum (to rebuild z for MSE)
+  int y, kind;
+  bool ignored, has_cst;
+
+  __device__ __forceinline__ void init(float (&z)[C], float (&t)[C], int y_, int region, int terms, const float (&sc)[4]) {
+    PixelLS<C> ls;
+    ls.init(z);
 #pragma unroll
-  for (int c = 0; c < C; ++c) {
-    p[c] = ls.p(z[c]);
-    g[c] = 0.f;
+    for (int c = 0; c < C; ++c) z[c] = ls.logp(z[c]);
+    mls = ls.m + ls.logs;
+    y = y_;
+    ignored = (y == HIAST_IGNORE_LABEL);
+    kind = cst_kind(terms);
+    has_cst = (terms & HIAST_TERM_CST) && in_region(region, ignored);
+    ce = (!ignored && (terms & HIAST_TERM_CE)) ? sc[0] : 0.f;
+    const float kld = (!ignored && (terms & HIAST_TERM_KLD)) ? sc[1] : 0.f;
+    a = ce + kld;
+    kb = kld * (1.0f / C);
+    ent = (ignored && (terms & HIAST_TERM_ENT)) ? sc[2] : 0.f;
+    h = 0.f;
+    if (ent != 0.f || (ignored && (terms & HIAST_TERM_ENT))) {
+#pragma unroll
+      for (int c = 0; c < C; ++c) h += expf(z[c]) * z[c];  // = -H
+    }
+    cst = has_cst ? sc[3] : 0.f;
+    T = 0.f;
+    if (has_cst && kind != HIAST_CST_MSE) {
+      if (kind == HIAST_CST_KLDIV) {
+        PixelLS<C> lt;
+        lt.init(t);
+#pragma unroll
+        for (int c = 0; c < C; ++c) t[c] = lt.prob(t[c]);
+      }
+#pragma unroll
+      for (int c = 0; c < C; ++c) T += t[c];
+    }
   }
-  if (!ignored) {
-    const float a = ((terms & HIAST_TERM_CE) ? sc[0] : 0.f) + ((terms & HIAST_TERM_KLD) ? sc[1] : 0.f);
-    const float kb = (terms & HIAST_TERM_KLD) ? sc[1] * (1.0f / C) : 0.f;
-    const float ce = (terms & HIAST_TERM_CE) ? sc[0] : 0.f;
-#pragma unroll
-    for (int c = 0; c < C; ++c) g[c] = a * p[c] - kb - ((c == y) ? ce : 0.f);
-  } else if (terms & HIAST_TERM_ENT) {
-    float h = 0.f;
-#pragma unroll
-    for (int c = 0; c < C; ++c) h += p[c] * ls.logp(z[c]);  // = -H
-#pragma unroll
-    for (int c = 0; c < C; ++c) g[c] = -sc[2] * p[c] * (ls.logp(z[c]) - h);
+
+  __device__ __forceinline__ float grad(int c, float lp, float tc) const {
+    const float p = expf(lp);
+    float g;
+    if (!ignored) g = a * p - kb - ((c == y) ? ce : 0.f);
+    else g = -ent * p * (lp - h);
+    if (has_cst) g += (kind == HIAST_CST_MSE) ? cst * 2.0f * ((lp + mls) - tc) : cst * (p * T - tc);
+    return g;
   }
-  if ((terms & HIAST_TERM_CST) && in_region(region, ignored)) {
-    float T = 0.f;
-#pragma unroll
-    for (int c = 0; c < C; ++c) T += t[c];
-#pragma unroll
-    for (int c = 0; c < C; ++c) g[c] += sc[3] * (p[c] * T - t[c]);
-  }
-}
+};
 
 struct Partial {
   double s[4];
@@ -174,7 +219,7 @@ __device__ __forceinline__ void block_reduce_store(const PixelSums& acc, Partial
 
 // Vector path: HW even, C compile-time.  Grid-stride over pairs of pixels.
 template <int C>
-__global__ void __launch_bounds__(kThreadsL) k_loss_fwd(LossArgs a, Partial* __restrict__ partials) {
+__global__ void __launch_bounds__(kThreadsL, 2) k_loss_fwd(LossArgs a, Partial* __restrict__ partials) {
   const int64_t HW2 = a.HW / kPxL;
   const long long total = static_cast<long long>(a.B) * HW2;
   PixelSums acc = {0.0, 0.0, 0.0, 0.0, 0, 0, 0};
@@ -209,7 +254,7 @@ __global__ void __launch_bounds__(kThreadsL) k_loss_fwd(LossArgs a, Partial* __r
 }
 
 template <int C>
-__global__ void __launch_bounds__(kThreadsL) k_loss_bwd(LossArgs a, const float* __restrict__ scales,
+__global__ void __launch_bounds__(kThreadsL, 2) k_loss_bwd(LossArgs a, const float* __restrict__ scales,
                                                         float* __restrict__ grad) {
   const int64_t HW2 = a.HW / kPxL;
   const long long total = static_cast<long long>(a.B) * HW2;
@@ -227,7 +272,7 @@ __global__ void __launch_bounds__(kThreadsL) k_loss_bwd(LossArgs a, const float*
     const int b = static_cast<int>(i / HW2);
     const int64_t p2 = i - static_cast<long long>(b) * HW2;
     const float2* zs = reinterpret_cast<const float2*>(a.z + static_cast<size_t>(b) * C * a.HW) + p2;
-    float z[kPxL][C], t[kPxL][C], g[kPxL][C];
+    float z[kPxL][C], t[kPxL][C];
 #pragma unroll
     for (int c = 0; c < C; ++c) {
       const float2 q = __ldcs(zs + static_cast<size_t>(c) * HW2);
@@ -245,12 +290,14 @@ __global__ void __launch_bounds__(kThreadsL) k_loss_bwd(LossArgs a, const float*
       for (int c = 0; c < C; ++c) t[0][c] = t[1][c] = 0.f;
     }
     const size_t lp = static_cast<size_t>(b) * a.HW + p2 * kPxL;
-#pragma unroll
-    for (int j = 0; j < kPxL; ++j)
-      pixel_backward<C>(z[j], t[j], load_label(a.plbl, a.plbl_bytes, lp + j), a.region, a.terms, sc, g[j]);
+    PixelBwd<C> px0, px1;
+    px0.init(z[0], t[0], load_label(a.plbl, a.plbl_bytes, lp), a.region, a.terms, sc);
+    px1.init(z[1], t[1], load_label(a.plbl, a.plbl_bytes, lp + 1), a.region, a.terms, sc);
     float2* gs = reinterpret_cast<float2*>(grad + static_cast<size_t>(b) * C * a.HW) + p2;
 #pragma unroll
-    for (int c = 0; c < C; ++c) __stcs(gs + static_cast<size_t>(c) * HW2, make_float2(g[0][c] + poison, g[1][c] + poison));
+    for (int c = 0; c < C; ++c)
+      __stcs(gs + static_cast<size_t>(c) * HW2,
+             make_float2(px0.grad(c, z[0][c], t[0][c]) + poison, px1.grad(c, z[1][c], t[1][c]) + poison));
   }
 }
 
@@ -299,10 +346,27 @@ __global__ void __launch_bounds__(kThreadsL) k_loss_fwd_generic(LossArgs a, Part
     if ((a.terms & HIAST_TERM_CST) && in_region(a.region, ignored)) {
       float sc = 0.f;
       int nz = 0;
+      const int kind = cst_kind(a.terms);
+      float tm = 0.f, tlogs = 0.f, tinv = 0.f, tsum = 1.f;
+      if (kind == HIAST_CST_KLDIV) {
+        generic_ls(tp, a.HW, C, tm, tlogs, tinv);
+        tsum = 0.f;
+        for (int c = 0; c < C; ++c) tsum += expf(tp[c * a.HW] - tm);
+      }
       for (int c = 0; c < C; ++c) {
-        const float prod = __fmul_rn(-((zp[c * a.HW] - m) - logs), tp[c * a.HW]);
-        nz += (prod != 0.f);
-        sc += prod;
+        const float lp = (zp[c * a.HW] - m) - logs;
+        float elem;
+        if (kind == HIAST_CST_KLDIV) {
+          const float pr = __fdiv_rn(expf(tp[c * a.HW] - tm), tsum);
+          elem = (pr == 0.f ? 0.f : __fmul_rn(pr, logf(pr))) - __fmul_rn(pr, lp);
+        } else if (kind == HIAST_CST_MSE) {
+          const float d = zp[c * a.HW] - tp[c * a.HW];
+          elem = __fmul_rn(d, d);
+        } else {
+          elem = __fmul_rn(-lp, tp[c * a.HW]);
+        }
+        nz += (elem != 0.f);
+        sc += elem;
       }
       acc.cst += static_cast<double>(sc);
       acc.n_nz += nz;
@@ -334,7 +398,17 @@ __global__ void __launch_bounds__(kThreadsL) k_loss_bwd_generic(LossArgs a, cons
     const bool ignored = (y == HIAST_IGNORE_LABEL);
     const bool cst = (a.terms & HIAST_TERM_CST) && in_region(a.region, ignored);
     float T = 0.f, h = 0.f;
-    if (cst) for (int c = 0; c < C; ++c) T += tp[c * a.HW];
+    const int kind = cst_kind(a.terms);
+    float tm = 0.f, tlogs = 0.f, tinv = 0.f, tsum = 1.f;
+    if (cst && kind == HIAST_CST_KLDIV) {
+      generic_ls(tp, a.HW, C, tm, tlogs, tinv);
+      tsum = 0.f;
+      for (int c = 0; c < C; ++c) tsum += expf(tp[c * a.HW] - tm);
+    }
+    auto tval = [&](int c) {
+      return kind == HIAST_CST_KLDIV ? __fdiv_rn(expf(tp[c * a.HW] - tm), tsum) : tp[c * a.HW];
+    };
+    if (cst && kind != HIAST_CST_MSE) for (int c = 0; c < C; ++c) T += tval(c);
     if (ignored && (a.terms & HIAST_TERM_ENT))
       for (int c = 0; c < C; ++c) {
         const float zc = zp[c * a.HW];
@@ -346,7 +420,7 @@ __global__ void __launch_bounds__(kThreadsL) k_loss_bwd_generic(LossArgs a, cons
       float g = 0.f;
       if (!ignored) g = (s_ce + s_kld) * pc - s_kld * (1.0f / C) - ((c == y) ? s_ce : 0.f);
       else if (a.terms & HIAST_TERM_ENT) g = -s_ent * pc * (((zc - m) - logs) - h);
-      if (cst) g += s_cst * (pc * T - tp[c * a.HW]);
+      if (cst) g += (kind == HIAST_CST_MSE) ? s_cst * 2.0f * (zc - tp[c * a.HW]) : s_cst * (pc * T - tval(c));
       gp[c * a.HW] = g + poison;
     }
   }
@@ -408,7 +482,7 @@ static int check_loss_args(const float* z, const float* t, const void* plbl, int
   if (plbl_bytes != 1 && plbl_bytes != 8) return HIAST_ERR_INVALID_ARG;
   if (B < 0 || C < 1 || C > kMaxCGeneric || HW < 1) return HIAST_ERR_INVALID_ARG;
   if (region < HIAST_REGION_IGNORED || region > HIAST_REGION_ALL) return HIAST_ERR_INVALID_ARG;
-  if (terms < 0 || terms > 15) return HIAST_ERR_INVALID_ARG;
+  if (terms < 0 || terms > 63 || (terms & (HIAST_CST_KLDIV | HIAST_CST_MSE)) == (HIAST_CST_KLDIV | HIAST_CST_MSE)) return HIAST_ERR_INVALID_ARG;
   if ((terms & HIAST_TERM_CST) && !t) return HIAST_ERR_INVALID_ARG;
   return HIAST_OK;
 }

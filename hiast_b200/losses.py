@@ -6,9 +6,9 @@ signatures ``LOSS[name](logits, labels, weights=None, ignore_index=255, refer_la
 returning a 0-d float32 tensor with autograd; the whole chain of log_softmax / mask / product / sum /
 count kernels is one forward kernel + one backward kernel (hiast_b200/csrc/loss.cu).
 
-Not ported (raise NotImplementedError): class ``weights`` for CE, ``refer_labels`` for CE, and the
-``MSE`` / ``KLDIV`` consistency variants; ``BCEWithLogits`` is the adversarial
-warm-up loss and out of scope.
+``kl_div`` :16-23 and ``mse`` :9-13 (the other consistency-loss types) run on the
+same kernels with a different per-element term.  Not ported (raise NotImplementedError): class ``weights``
+for CE and ``refer_labels`` for CE; ``BCEWithLogits`` is the adversarial warm-up loss and out of scope.
 """
 
 from __future__ import annotations
@@ -16,7 +16,7 @@ from __future__ import annotations
 import torch
 
 from . import ops
-from ._lib import TERM_CE, TERM_CST, TERM_ENT, TERM_KLD, HiastError
+from ._lib import CST_KLDIV, CST_MSE, CST_SOFTCE, TERM_CE, TERM_CST, TERM_ENT, TERM_KLD, HiastError
 from .registry import LOSS
 
 IGNORE = 255
@@ -37,8 +37,7 @@ class FusedSelfTrainingLoss(torch.autograd.Function):
         cnt = counts.to(torch.float64)
         cst_div = torch.full((), float(z.numel()), dtype=torch.float64, device=z.device) if cst_mean_all else cnt[2]
         denom = torch.stack([cnt[0], c * cnt[0], c * cnt[1], cst_div])
-        enabled = torch.tensor([bool(terms & TERM_CE), bool(terms & TERM_KLD), bool(terms & TERM_ENT),
-                                bool(terms & TERM_CST)], device=z.device)
+        enabled = _enabled_mask(terms, z.device)
         out = torch.where(enabled, sums / denom, torch.zeros_like(sums)).to(torch.float32)
         ctx.save_for_backward(z, t, plbl, denom, enabled)
         ctx.region, ctx.terms = region, terms
@@ -50,6 +49,19 @@ class FusedSelfTrainingLoss(torch.autograd.Function):
         scales = torch.where(enabled, gout.to(torch.float64) / denom, torch.zeros_like(denom)).to(torch.float32)
         grad = ops.st_loss_bwd(z, t, plbl, scales.contiguous(), ctx.region, ctx.terms)
         return grad, None, None, None, None, None
+
+
+_enabled_cache = {}
+
+
+def _enabled_mask(terms, device):
+    key = (terms & 15, device)
+    m = _enabled_cache.get(key)
+    if m is None:
+        m = torch.tensor([bool(terms & TERM_CE), bool(terms & TERM_KLD), bool(terms & TERM_ENT), bool(terms & TERM_CST)],
+                         device=device)
+        _enabled_cache[key] = m
+    return m
 
 
 def _prep_logits(logits):
@@ -104,11 +116,29 @@ def soft_ce(logits, labels, weights=None, ignore_index=IGNORE, refer_labels=None
     return fused_terms(logits, refer_labels, labels, region=region, terms=TERM_CST)[3]
 
 
+def _consistency(kind, logits, labels, weights, ignore_index, refer_labels, region):
+    if weights is not None:
+        import warnings
+        warnings.warn('Weights is not available for this loss')              # losses.py:11-12 / :18-19
+    if ignore_index != IGNORE:
+        raise NotImplementedError('only ignore_index=255 is supported')
+    if refer_labels is None:                                                 # reduction='mean' over every element
+        b, _, h, w = logits.shape
+        dummy = torch.zeros((b, h, w), dtype=torch.uint8, device=logits.device)
+        return fused_terms(logits, dummy, labels, region='all', terms=TERM_CST | kind, cst_mean_all=True)[3]
+    if region not in ('ignored', 'confident', 'all'):
+        raise ValueError('{} is not a valid region'.format(region))
+    return fused_terms(logits, refer_labels, labels, region=region, terms=TERM_CST | kind)[3]
+
+
 @LOSS.register('MSE')
-def mse(*args, **kwargs):
-    raise NotImplementedError('MSE consistency loss is not ported (SURVEY.md 8f rank 3)')
+def mse(logits, labels, weights=None, ignore_index=IGNORE, refer_labels=None, region='ignore'):
+    """losses.py:9-13: (logits - labels)^2, mean over all elements or over the non-zero elements of a region."""
+    return _consistency(CST_MSE, logits, labels, weights, ignore_index, refer_labels, region)
 
 
 @LOSS.register('KLDIV')
-def kl_div(*args, **kwargs):
-    raise NotImplementedError('KLDIV consistency loss is not ported (SURVEY.md 8f rank 3)')
+def kl_div(input_logits, target_logits, weights=None, ignore_index=IGNORE, refer_labels=None, region='confident'):
+    """losses.py:16-23: KLDivLoss(log_softmax(input_logits), softmax(target_logits)); both soft-maxes are computed
+    inside the kernel.  No gradient flows to ``target_logits`` (the trainer produces them under no_grad)."""
+    return _consistency(CST_KLDIV, input_logits, target_logits, weights, ignore_index, refer_labels, region)

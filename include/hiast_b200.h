@@ -54,6 +54,10 @@ extern "C" {
 #define HIAST_TERM_KLD          2
 #define HIAST_TERM_ENT          4
 #define HIAST_TERM_CST          8
+/* kind of the consistency term, OR-ed into `terms` (default 0 = SoftCE, losses.py:39-61) */
+#define HIAST_CST_SOFTCE         0   /* -logp_c * t_c,            t = soft targets in [0,1]                           */
+#define HIAST_CST_KLDIV         16   /* xlogy(tp,tp) - tp*logp_c, t = target LOGITS, tp = softmax(t), losses.py:16-23 */
+#define HIAST_CST_MSE           32   /* (z_c - t_c)^2,                                                losses.py:9-13  */
 
 /* ---- library ---------------------------------------------------------------------------- */
 HIAST_API int         hiast_version(void);                 /* 1000*major + minor                          */

@@ -69,6 +69,26 @@ def soft_ce(logits, target, refer_labels=None, region='confident', ignore_index=
     return per_elem.sum() / (per_elem != 0).sum()
 
 
+def _by_region(per_elem, numel, refer_labels, region, ignore_index):
+    """losses.py:68-72 + :75-89 for a reduction='none' tensor."""
+    if refer_labels is None:
+        return per_elem.sum() / numel
+    per_elem = per_elem * _region_mask(refer_labels, ignore_index, region).unsqueeze(1)
+    return per_elem.sum() / (per_elem != 0).sum()
+
+
+def mse(logits, labels, refer_labels=None, region='ignore', ignore_index=IGNORE):
+    """losses.py:9-13 (nn.MSELoss / nn.MSELoss(reduction='none'))."""
+    return _by_region(F.mse_loss(logits, labels, reduction='none'), logits.numel(), refer_labels, region, ignore_index)
+
+
+def kl_div(input_logits, target_logits, refer_labels=None, region='confident', ignore_index=IGNORE):
+    """losses.py:16-23 (nn.KLDivLoss default 'mean' = mean over all elements / reduction='none')."""
+    inp = F.log_softmax(input_logits, dim=1)
+    tgt = F.softmax(target_logits, dim=1)
+    return _by_region(F.kl_div(inp, tgt, reduction='none'), inp.numel(), refer_labels, region, ignore_index)
+
+
 def compute_loss(t_logits, t_plbl, t_cst_lbl=None, s_logits=None, s_lbl=None, *,
                  w_seg=1.0, w_kld=0.1, w_ent=1.0, w_cst=0.5, cst_region='ignored',
                  cst_enabled=True):

@@ -9,6 +9,7 @@ none of the stubs touch the arithmetic of the hot path.  Every fixture is the
 output of the reference's own functions on seeded inputs:
 
 * ias_*.npz       IASPseudoGenerator.run        workflows/pseudo_label_generator.py:181-213
+* loss_cst_variants.npz  LOSS['KLDIV'], LOSS['MSE']      sseg/models/modules/losses.py:9-23
 * loss_*.npz      SelfTrainingSegmentor.compute_loss + autograd
                                                 sseg/models/segmentors/self_training_segmentor.py:30-53
 * metric_*.npz    intersectionAndUnionGPU       utils/metrics.py:6-19
@@ -167,6 +168,29 @@ def loss_fixture(name, spec):
     print(name, {k: float(v) for k, v in out.items()})
 
 
+def cst_variant_fixture(name, spec):
+    """LOSS['KLDIV'] / LOSS['MSE'] of the reference (losses.py:9-23) with and without refer_labels, + gradients."""
+    import warnings
+    from sseg.models.modules import losses
+    z, t, plbl, _, _ = gi.loss_inputs(spec)
+    tz = torch.log(t) * 1.7                      # teacher "logits" with a different temperature
+    res = dict(spec=np.array(repr(spec)), z=z.numpy(), t=t.numpy(), tz=tz.numpy(), plbl=plbl.numpy())
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        for kind, fn, tgt in (('kldiv', losses.kl_div, tz), ('mse', losses.mse, t)):
+            for region in ('none', 'ignored', 'confident', 'all'):
+                zz = z.clone().requires_grad_(True)
+                if region == 'none':
+                    val = fn(zz, tgt)
+                else:
+                    val = fn(zz, tgt, refer_labels=plbl, region=region)
+                val.backward()
+                res['%s_%s' % (kind, region)] = np.float64(val.item())
+                res['%s_%s_grad' % (kind, region)] = zz.grad.numpy()
+    np.savez_compressed(os.path.join(HERE, name + '.npz'), **res)
+    print(name, {k: float(v) for k, v in res.items() if k.endswith(('none', 'ignored', 'confident', 'all'))})
+
+
 # -------------------------------------------------------------------------- metric
 def metric_fixture(name, spec):
     from utils import metrics
@@ -210,6 +234,7 @@ def main():
         ias_fixture(name, spec, store_conf=spec.get('store_conf', True))
     for name, spec in gi.LOSS_SPECS.items():
         loss_fixture(name, spec)
+    cst_variant_fixture('loss_cst_variants', gi.CST_VARIANT_SPEC)
     for name, spec in gi.METRIC_SPECS.items():
         metric_fixture(name, spec)
     copy_paste_fixture('copy_paste', gi.COPY_PASTE_SPEC)

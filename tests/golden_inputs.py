@@ -37,6 +37,8 @@ LOSS_SPECS = {
                         w_seg=0.5, w_kld=0.2, w_ent=1.0, w_cst=1.0, source=False),
 }
 
+CST_VARIANT_SPEC = dict(B=2, C=19, H=12, W=20, seed=12, p_ignore=0.5, source=False)
+
 METRIC_SPECS = {
     'metric_k19': dict(B=2, H=64, W=96, K=19, seed=7, p_ignore=0.1, p_oor=0.0),
     'metric_k16_oor': dict(B=1, H=33, W=57, K=16, seed=8, p_ignore=0.2, p_oor=0.05),

@@ -153,3 +153,71 @@ def test_windowed_ring_driver_single_rank_equals_oracle():
     np.testing.assert_allclose(mean.cpu().numpy(), oracle.class_mean_probs, rtol=1e-6)
     assert np.array_equal(np.concatenate([got[w][0] for w in sorted(got)]), np.stack(oracle.labels))
     assert np.array_equal(np.concatenate([got[w][1] for w in sorted(got)]), np.stack(oracle.threshold_trace))
+
+
+def test_config4_synthia_16_class_ias_plus_copy_paste():
+    """BASELINE.json configs[3] on one GPU: 19-channel tensors whose classes {9,14,16} are never predicted, IAS through
+    the windowed driver, then hard-aware copy-paste on uint8 images with labels = IAS output and donor (i*7919+13) mod N."""
+    from hiast_b200.ias_engine import IASEngine
+    from hiast_b200.preprocessor import CopyPaste
+    from hiast_b200.sharded import ShardedIAS, window_images
+    from oracle import copy_paste as ocp
+    spec = dict(C=19, H=32, W=64, N=10, B=2, alpha=0.5, beta=0.9, gamma=8.0, cp_gamma=0.99, seed=77, dist='peaked',
+                absent=(9, 14, 16))
+    batches = gi.ias_batches(spec)
+    logits = torch.cat([lg for lg, _ in batches]).cuda()
+    window = 4
+    eng = IASEngine(19, 32, 64, 2, 0.5, 0.9, 8.0, 0.99, 2 * window)
+    labels = {}
+    def window_logits(w):
+        i0, n_w = window_images(w, window, spec['N'])
+        return logits[i0:i0 + n_w]
+
+    def on_window(w, plbl_w, counts, thr_groups):
+        labels[w] = plbl_w.clone()
+
+    thr, mean, statics = ShardedIAS(eng, window, spec['N'], 0, 1).run(window_logits, on_window)
+    oracle = oias.IASOracle(19, 0.5, 0.9, 8.0, 0.99)
+    oracle.run([(lg.cuda(), p) for lg, p in batches])
+    plbl = torch.cat([labels[w] for w in sorted(labels)])
+    assert np.array_equal(plbl.cpu().numpy(), np.stack(oracle.labels))
+    assert np.array_equal(thr.cpu().numpy(), oracle.class_threshold)
+    assert statics[[9, 14, 16]].sum().item() == 0 and (mean[[9, 14, 16]] == 0).all()
+    # copy-paste with the SYNTHIA class set: ignored classes get p = 0 and never enter the hard set
+    cfg = SimpleNamespace(dataset=SimpleNamespace(source=SimpleNamespace(type='SYNTHIA'), num_classes=19),
+                          preprocessor=SimpleNamespace(copy_paste=SimpleNamespace(selected_num_classes=10, mode='original')))
+
+    class DS:
+        def get_samples_with_class(self):
+            return {c: ['x'] for c in range(19)}
+
+    class_value = mean.cpu().numpy().copy()
+    class_value[class_value == 0] = 1.0
+    cp = CopyPaste(cfg, DS(), class_value)
+    assert not set(int(c) for c in cp.hard_classes) & {9, 14, 16}
+    n = spec['N']
+    rs = np.random.RandomState(1)
+    imgs = torch.from_numpy(rs.randint(0, 256, size=(n, 32, 64, 3)).astype(np.uint8)).cuda()
+    donor_imgs, donor_lbls = imgs.clone(), plbl.clone()
+    donor_index = torch.tensor([(i * 7919 + 13) % n for i in range(n)], dtype=torch.int32, device='cuda')
+    out_img, out_lbl, out_mask = cp.run_batch(imgs.clone(), plbl.clone(), donor_imgs, donor_lbls, donor_index)
+    for i in range(n):
+        d = int(donor_index[i])
+        w_img, w_lbl = imgs[i].cpu().numpy().copy(), plbl[i].cpu().numpy().copy()
+        w_mask = np.full_like(w_lbl, 255)
+        ocp.paste(w_img, w_lbl, w_mask, donor_imgs[d].cpu().numpy(), donor_lbls[d].cpu().numpy(), cp.hard_classes)
+        assert np.array_equal(out_img[i].cpu().numpy(), w_img)
+        assert np.array_equal(out_lbl[i].cpu().numpy(), w_lbl)
+        assert np.array_equal(out_mask[i].cpu().numpy(), w_mask)
+
+
+def test_config5_full_round_example_small():
+    """BASELINE.json configs[4] at toy size: DeepLabv2-ResNet101 forward -> IAS -> confusion matrix, via the example."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, 'examples', 'full_round.py'), '--images', '5', '--height', '65',
+                          '--width', '129', '--window', '2'], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    res = json.loads(out.stdout.strip().splitlines()[-1])
+    assert res['images'] == 5 and 0.0 <= res['miou'] <= 1.0 and res['pow_rounding_certified']

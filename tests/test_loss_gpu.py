@@ -148,3 +148,56 @@ def test_empty_regions_give_nan_like_the_reference():
     assert torch.isfinite(out[0]) and torch.isfinite(out[1]) and torch.isnan(out[2])     # entropy: 0/0
     out.sum().backward()
     assert torch.isnan(z.grad).all()                                # inf * 0 in the reference's autograd
+
+
+def test_kldiv_and_mse_consistency_variants_vs_reference_fixture():
+    """LOSS['KLDIV'] / LOSS['MSE'] (losses.py:9-23): values and gradients of the reference's own run, all regions,
+    vector (C=19) kernels; then the generic kernels (C=7, odd size) against the oracle on CUDA."""
+    import hiast_b200
+    hiast_b200.register_all()
+    from hiast_b200 import LOSS
+    gold = np.load(os.path.join(GOLD, 'loss_cst_variants.npz'))
+    z0, t, tz, plbl = (torch.from_numpy(gold[k]).cuda() for k in ('z', 't', 'tz', 'plbl'))
+    for kind, name, tgt in (('kldiv', 'KLDIV', tz), ('mse', 'MSE', t)):
+        for region in ('none', 'ignored', 'confident', 'all'):
+            z = z0.clone().requires_grad_(True)
+            val = LOSS[name](z, tgt) if region == 'none' else LOSS[name](z, tgt, refer_labels=plbl, region=region)
+            val.backward()
+            np.testing.assert_allclose(val.item(), gold['%s_%s' % (kind, region)], rtol=RTOL)
+            grad_close(z.grad.cpu(), torch.from_numpy(gold['%s_%s_grad' % (kind, region)]))
+    g = torch.Generator().manual_seed(21)
+    z0 = (torch.randn(2, 7, 9, 13, generator=g) * 2).cuda()
+    tz = (torch.randn(2, 7, 9, 13, generator=g) * 2).cuda()
+    y = torch.randint(0, 7, (2, 9, 13), generator=g)
+    y[torch.rand(2, 9, 13, generator=g) < 0.5] = 255
+    y = y.cuda()
+    for name, ofn in (('KLDIV', oloss.kl_div), ('MSE', oloss.mse)):
+        z = z0.clone().requires_grad_(True)
+        LOSS[name](z, tz, refer_labels=y, region='ignored').backward()
+        z2 = z0.clone().requires_grad_(True)
+        ofn(z2, tz, refer_labels=y, region='ignored').backward()
+        grad_close(z.grad, z2.grad)
+
+
+def test_segmentor_with_kldiv_consistency():
+    """cst_loss.type = KLDIV goes through the per-term composition of compute_loss (self_training_segmentor.py:49-51)."""
+    from hiast_b200.segmentor import SelfTrainingSegmentor
+    spec = dict(w_seg=1.0, w_kld=0.1, w_ent=1.0, w_cst=0.5, region='confident')
+    cfg = make_cfg(spec)
+    cfg.cst_training.cst_loss.type = 'KLDIV'
+    g = torch.Generator().manual_seed(33)
+    z = (torch.randn(2, 19, 16, 24, generator=g) * 3).cuda().requires_grad_(True)
+    tz = (torch.randn(2, 19, 16, 24, generator=g) * 3).cuda()
+    y = torch.randint(0, 19, (2, 16, 24), generator=g)
+    y[torch.rand(2, 16, 24, generator=g) < 0.5] = 255
+    y = y.cuda()
+    out = SelfTrainingSegmentor(cfg).compute_loss(z, y, tz)
+    assert list(out) == ['target_seg_loss', 'kld_confident_loss', 'ent_ignored_loss', 'cst_loss']
+    sum(v.mean() for v in out.values()).backward()
+    z2 = z.detach().clone().requires_grad_(True)
+    w_conf, w_ign = oloss.region_weights(z2, y)
+    ref = [oloss.ce(z2, y), 0.1 * oloss.kld_reg(z2, w_conf), oloss.entropy_reg(z2, w_ign),
+           0.5 * oloss.kl_div(z2, tz, refer_labels=y, region='confident')]
+    sum(ref).backward()
+    np.testing.assert_allclose([v.item() for v in out.values()], [v.item() for v in ref], rtol=RTOL)
+    grad_close(z.grad, z2.grad)

@@ -168,3 +168,16 @@ def test_copy_paste_oracle_matches_reference():
         assert np.array_equal(o_img, gold['img_%d' % i])
         assert np.array_equal(o_lbl, gold['lbl_%d' % i])
         assert np.array_equal(o_mask, gold['mask_%d' % i])
+
+
+def test_cst_variant_oracles_match_reference():
+    """LOSS['KLDIV'] / LOSS['MSE'] restatements against the reference's own values and gradients."""
+    gold = load('loss_cst_variants')
+    z0, t, tz, plbl = (torch.from_numpy(gold[k]) for k in ('z', 't', 'tz', 'plbl'))
+    for kind, fn, tgt in (('kldiv', oloss.kl_div, tz), ('mse', oloss.mse, t)):
+        for region in ('none', 'ignored', 'confident', 'all'):
+            z = z0.clone().requires_grad_(True)
+            val = fn(z, tgt) if region == 'none' else fn(z, tgt, refer_labels=plbl, region=region)
+            val.backward()
+            np.testing.assert_allclose(val.item(), gold['%s_%s' % (kind, region)], rtol=1e-6)
+            np.testing.assert_allclose(z.grad.numpy(), gold['%s_%s_grad' % (kind, region)], rtol=1e-5, atol=1e-10)
