@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, 'libhiast_b200.so')
 OK = 0
 REGION = {'ignored': 0, 'confident': 1, 'all': 2}
 TERM_CE, TERM_KLD, TERM_ENT, TERM_CST = 1, 2, 4, 8
-CST_SOFTCE, CST_KLDIV, CST_MSE = 0, 16, 32
+CST_SOFTCE, CST_KLDIV, CST_MSE, CST_SOFTCE_LOGITS = 0, 16, 32, 48
 KEY_ONE = 0x3C00
 IGNORE = 255
 
@@ -32,6 +32,7 @@ _SIGNATURES = {
     'hiast_ias_hist_row_stride': (_i, [_i]),
     'hiast_ias_hist_bytes': (_sz, [_i, _i, _i]),
     'hiast_ias_softmax_hist': (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    'hiast_ias_upsample_softmax_hist': (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     'hiast_ias_conf_hist': (_i, [_vp, _vp, _i, _i, _i64, _i, _i, _i, _i, _vp, _vp, _vp]),
     'hiast_ias_threshold_scan': (_i, [_vp, _i, _i, _i, _d, _d, _d, _vp, _vp, _vp, _vp, _vp]),
     'hiast_ias_select': (_i, [_vp, _vp, _vp, _i, _i64, _i, _i, _vp, _vp, _vp, _vp]),

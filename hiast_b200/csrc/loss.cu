@@ -38,7 +38,7 @@ struct LossArgs {
   int terms;   // HIAST_TERM_* | HIAST_CST_* (kind of the consistency term)
 };
 
-__device__ __forceinline__ int cst_kind(int terms) { return terms & (HIAST_CST_KLDIV | HIAST_CST_MSE); }
+__device__ __forceinline__ int cst_kind(int terms) { return terms & HIAST_CST_SOFTCE_LOGITS; }
 
 __device__ __forceinline__ int load_label(const void* p, int bytes, size_t i) {
   if (bytes == 1) return static_cast<const uint8_t*>(p)[i];
@@ -125,9 +125,12 @@ __device__ __forceinline__ void pixel_forward(const float (&z)[C], const float (
         sc += elem;
       }
     } else {
+      PixelLS<C> lt;
+      if (kind == HIAST_CST_SOFTCE_LOGITS) lt.init(t);   // teacher logits: softmax fused here (8f rank 4)
 #pragma unroll
       for (int c = 0; c < C; ++c) {
-        const float prod = __fmul_rn(-ls.logp(z[c]), t[c]);
+        const float tc = (kind == HIAST_CST_SOFTCE_LOGITS) ? lt.prob(t[c]) : t[c];
+        const float prod = __fmul_rn(-ls.logp(z[c]), tc);
         nz += (prod != 0.f);
         sc += prod;
       }
@@ -169,7 +172,7 @@ struct PixelBwd {
     cst = has_cst ? sc[3] : 0.f;
     T = 0.f;
     if (has_cst && kind != HIAST_CST_MSE) {
-      if (kind == HIAST_CST_KLDIV) {
+      if (kind == HIAST_CST_KLDIV || kind == HIAST_CST_SOFTCE_LOGITS) {   // targets arrive as logits
         PixelLS<C> lt;
         lt.init(t);
 #pragma unroll
@@ -348,7 +351,7 @@ __global__ void __launch_bounds__(kThreadsL) k_loss_fwd_generic(LossArgs a, Part
       int nz = 0;
       const int kind = cst_kind(a.terms);
       float tm = 0.f, tlogs = 0.f, tinv = 0.f, tsum = 1.f;
-      if (kind == HIAST_CST_KLDIV) {
+      if (kind == HIAST_CST_KLDIV || kind == HIAST_CST_SOFTCE_LOGITS) {
         generic_ls(tp, a.HW, C, tm, tlogs, tinv);
         tsum = 0.f;
         for (int c = 0; c < C; ++c) tsum += expf(tp[c * a.HW] - tm);
@@ -362,6 +365,8 @@ __global__ void __launch_bounds__(kThreadsL) k_loss_fwd_generic(LossArgs a, Part
         } else if (kind == HIAST_CST_MSE) {
           const float d = zp[c * a.HW] - tp[c * a.HW];
           elem = __fmul_rn(d, d);
+        } else if (kind == HIAST_CST_SOFTCE_LOGITS) {
+          elem = __fmul_rn(-lp, __fdiv_rn(expf(tp[c * a.HW] - tm), tsum));
         } else {
           elem = __fmul_rn(-lp, tp[c * a.HW]);
         }
@@ -400,13 +405,14 @@ __global__ void __launch_bounds__(kThreadsL) k_loss_bwd_generic(LossArgs a, cons
     float T = 0.f, h = 0.f;
     const int kind = cst_kind(a.terms);
     float tm = 0.f, tlogs = 0.f, tinv = 0.f, tsum = 1.f;
-    if (cst && kind == HIAST_CST_KLDIV) {
+    const bool t_is_logits = (kind == HIAST_CST_KLDIV || kind == HIAST_CST_SOFTCE_LOGITS);
+    if (cst && t_is_logits) {
       generic_ls(tp, a.HW, C, tm, tlogs, tinv);
       tsum = 0.f;
       for (int c = 0; c < C; ++c) tsum += expf(tp[c * a.HW] - tm);
     }
     auto tval = [&](int c) {
-      return kind == HIAST_CST_KLDIV ? __fdiv_rn(expf(tp[c * a.HW] - tm), tsum) : tp[c * a.HW];
+      return t_is_logits ? __fdiv_rn(expf(tp[c * a.HW] - tm), tsum) : tp[c * a.HW];
     };
     if (cst && kind != HIAST_CST_MSE) for (int c = 0; c < C; ++c) T += tval(c);
     if (ignored && (a.terms & HIAST_TERM_ENT))
@@ -482,7 +488,7 @@ static int check_loss_args(const float* z, const float* t, const void* plbl, int
   if (plbl_bytes != 1 && plbl_bytes != 8) return HIAST_ERR_INVALID_ARG;
   if (B < 0 || C < 1 || C > kMaxCGeneric || HW < 1) return HIAST_ERR_INVALID_ARG;
   if (region < HIAST_REGION_IGNORED || region > HIAST_REGION_ALL) return HIAST_ERR_INVALID_ARG;
-  if (terms < 0 || terms > 63 || (terms & (HIAST_CST_KLDIV | HIAST_CST_MSE)) == (HIAST_CST_KLDIV | HIAST_CST_MSE)) return HIAST_ERR_INVALID_ARG;
+  if (terms < 0 || terms > 63) return HIAST_ERR_INVALID_ARG;
   if ((terms & HIAST_TERM_CST) && !t) return HIAST_ERR_INVALID_ARG;
   return HIAST_OK;
 }

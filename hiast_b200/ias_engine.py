@@ -63,6 +63,17 @@ class IASEngine:
                              self.label[first_image:first_image + n], self.hist[g0:g0 + self._groups(n)],
                              accumulate=False, hist_mode=self.hist_mode)
 
+    def phase_a_lowres(self, logits_lr, first_image=0):
+        """Phase A from the network's LOW-RESOLUTION logits f32 [n,C,h,w]: the bilinear up-sampling to (H,W) of
+        self_training_segmentor.py:27 is fused into the kernel (bit-identical to interpolate -> softmax -> max)."""
+        n = logits_lr.shape[0]
+        if first_image % self.B or first_image + n > self.max_images:
+            raise ValueError('bad window')
+        g0 = first_image // self.B
+        ops.ias_upsample_softmax_hist(logits_lr, (self.H, self.W), self.B, self.key_lo,
+                                      self.conf[first_image:first_image + n], self.label[first_image:first_image + n],
+                                      self.hist[g0:g0 + self._groups(n)], accumulate=False)
+
     def phase_a_from_conf(self, conf, label, first_image=0):
         """Same, from caller-provided conf f32 [n,H,W] / label (u8|i64) [n,H,W]; the engine's key range must
         cover the confidences (key_lo=0 covers every value in [0,1])."""

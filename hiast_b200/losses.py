@@ -16,7 +16,7 @@ from __future__ import annotations
 import torch
 
 from . import ops
-from ._lib import CST_KLDIV, CST_MSE, CST_SOFTCE, TERM_CE, TERM_CST, TERM_ENT, TERM_KLD, HiastError
+from ._lib import CST_KLDIV, CST_MSE, CST_SOFTCE, CST_SOFTCE_LOGITS, TERM_CE, TERM_CST, TERM_ENT, TERM_KLD, HiastError
 from .registry import LOSS
 
 IGNORE = 255
@@ -129,6 +129,13 @@ def _consistency(kind, logits, labels, weights, ignore_index, refer_labels, regi
     if region not in ('ignored', 'confident', 'all'):
         raise ValueError('{} is not a valid region'.format(region))
     return fused_terms(logits, refer_labels, labels, region=region, terms=TERM_CST | kind)[3]
+
+
+@LOSS.register('SoftCE_from_logits')
+def soft_ce_from_logits(logits, teacher_logits, weights=None, ignore_index=IGNORE, refer_labels=None, region='confident'):
+    """SoftCE whose soft targets are softmax(teacher_logits), with that softmax computed inside the kernel (SURVEY.md
+    section 8f rank 4: drops the trainer's F.softmax pass, consistency_self_training_trainer.py:119, 152 B/px)."""
+    return _consistency(CST_SOFTCE_LOGITS, logits, teacher_logits, weights, ignore_index, refer_labels, region)
 
 
 @LOSS.register('MSE')

@@ -15,7 +15,7 @@ from . import _lib
 from ._lib import IGNORE, KEY_ONE, REGION, TERM_CE, TERM_CST, TERM_ENT, TERM_KLD, check, lib, ptr, require_cuda, stream_ptr
 
 __all__ = [
-    'ias_key_lo', 'ias_num_bins', 'ias_row_stride', 'ias_new_hist', 'ias_softmax_hist', 'ias_conf_hist', 'ias_threshold_scan',
+    'ias_key_lo', 'ias_num_bins', 'ias_row_stride', 'ias_new_hist', 'ias_softmax_hist', 'ias_upsample_softmax_hist', 'ias_conf_hist', 'ias_threshold_scan',
     'ias_select', 'ias_meanprob_scan', 'copy_paste', 'hard_lut', 'st_loss_fwd', 'st_loss_bwd',
     'confusion_matrix', 'confusion_from_logits', 'iou_from_confusion',
 ]
@@ -69,6 +69,30 @@ def ias_softmax_hist(logits, group_size, key_lo=None, conf=None, label=None, his
     check(lib().hiast_ias_softmax_hist(ptr(logits), n, c, h, w, int(group_size), int(key_lo), int(bool(accumulate)),
                                        int(hist_mode), ptr(conf), ptr(label), ptr(hist), stream_ptr(dev)),
           'hiast_ias_softmax_hist')
+    return conf, label, hist
+
+
+def ias_upsample_softmax_hist(logits_lr, out_hw, group_size, key_lo=None, conf=None, label=None, hist=None,
+                              accumulate=False):
+    """Phase A on LOW-RESOLUTION logits f32 [N,C,h,w]: bilinear (align_corners=True) up-sampling to out_hw fused in.
+    Returns (conf f32 [N,H,W], label u8 [N,H,W], hist)."""
+    require_cuda(logits_lr, torch.float32, 'logits_lr')
+    n, c, h, w = logits_lr.shape
+    H, W = int(out_hw[0]), int(out_hw[1])
+    if key_lo is None:
+        key_lo = ias_key_lo(c)
+    g = _n_groups(n, group_size)
+    dev = logits_lr.device
+    conf = torch.empty((n, H, W), dtype=torch.float32, device=dev) if conf is None else require_cuda(conf, torch.float32, 'conf')
+    label = torch.empty((n, H, W), dtype=torch.uint8, device=dev) if label is None else require_cuda(label, torch.uint8, 'label')
+    if hist is None:
+        hist = ias_new_hist(g, c, key_lo, dev)
+        accumulate = False
+    if n == 0:
+        return conf, label, hist
+    check(lib().hiast_ias_upsample_softmax_hist(ptr(logits_lr), n, c, h, w, H, W, int(group_size), int(key_lo),
+                                                int(bool(accumulate)), ptr(conf), ptr(label), ptr(hist), stream_ptr(dev)),
+          'hiast_ias_upsample_softmax_hist')
     return conf, label, hist
 
 

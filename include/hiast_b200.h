@@ -58,6 +58,7 @@ extern "C" {
 #define HIAST_CST_SOFTCE         0   /* -logp_c * t_c,            t = soft targets in [0,1]                           */
 #define HIAST_CST_KLDIV         16   /* xlogy(tp,tp) - tp*logp_c, t = target LOGITS, tp = softmax(t), losses.py:16-23 */
 #define HIAST_CST_MSE           32   /* (z_c - t_c)^2,                                                losses.py:9-13  */
+#define HIAST_CST_SOFTCE_LOGITS 48   /* SoftCE with t = teacher LOGITS: the trainer's F.softmax (consistency_self_training_trainer.py:119) fused in */
 
 /* ---- library ---------------------------------------------------------------------------- */
 HIAST_API int         hiast_version(void);                 /* 1000*major + minor                          */
@@ -83,6 +84,15 @@ HIAST_API size_t hiast_ias_hist_bytes(int n_groups, int C, int key_lo);
 HIAST_API int hiast_ias_softmax_hist(const float* logits, int n_images, int C, int H, int W,
                            int group_size, int key_lo, int accumulate, int hist_mode,
                            float* conf, uint8_t* label, uint32_t* hist, void* stream);
+
+/* a1+a2 with the bilinear up-sampling of the step before the path fused in (SURVEY.md 8f rank 1;
+ * sseg/models/segmentors/self_training_segmentor.py:27: F.interpolate(mode='bilinear', align_corners=True)).
+ * logits_lr f32 [n_images,C,h_in,w_in] is the network output at its own resolution; conf / label / hist are
+ * those of softmax(interpolate(logits_lr, (H,W))).max(1), bit-identical to ATen's CUDA path, without the
+ * full-resolution tensor ever existing.  C in {19,16}, W % 4 == 0, up-sampling only; else HIAST_ERR_UNSUPPORTED. */
+HIAST_API int hiast_ias_upsample_softmax_hist(const float* logits_lr, int n_images, int C, int h_in, int w_in,
+                                    int H, int W, int group_size, int key_lo, int accumulate,
+                                    float* conf, uint8_t* label, uint32_t* hist, void* stream);
 
 /* a2 alone, for callers that already hold conf/label (the signature of
  * select_and_save_confident_label / get_ias_threshold takes them, :67,:171).

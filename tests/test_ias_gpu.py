@@ -202,3 +202,39 @@ def test_scan_error_flag_mirrors_numpy_valueerror():
     flag = torch.zeros(1, dtype=torch.int32, device='cuda')
     o.ias_threshold_scan(hist, 1, 3, 0, 1.5, 0.9, 1.0, thr_state, error_flag=flag)   # q = 1 - 1.5*0.999 < 0
     assert flag.item() & 1
+
+
+@pytest.mark.parametrize('shape', [((17, 33), (128, 256)), ((9, 21), (64, 160)), ((13, 17), (100, 132)), ((129, 257), (1024, 2048)),
+                                   ((16, 16), (16, 16))])
+@pytest.mark.parametrize('C', [19, 16])
+def test_fused_bilinear_upsample_bit_exact_vs_torch(shape, C):
+    """phase A straight from the stride-8 logits == softmax(F.interpolate(x, align_corners=True)).max(1)
+    on CUDA, bit for bit (conf, label, histogram), without the full-resolution tensor."""
+    o = ops()
+    (h, w), (H, W) = shape
+    n = 3 if H * W < 1 << 20 else 2
+    g = torch.Generator().manual_seed(h * 1000 + W + C)
+    lr = (torch.randn(n, C, h, w, generator=g) * 4).cuda()
+    full = torch.nn.functional.interpolate(lr, size=(H, W), mode='bilinear', align_corners=True)
+    want_conf, want_label = torch_softmax_max(full)
+    conf, label, hist = o.ias_upsample_softmax_hist(lr, (H, W), group_size=2)
+    assert torch.equal(conf, want_conf)
+    assert torch.equal(label.long(), want_label)
+    conf2, label2, hist2 = o.ias_softmax_hist(full.contiguous(), group_size=2)
+    assert torch.equal(hist, hist2)
+
+
+def test_engine_from_lowres_logits_equals_full_resolution_path():
+    from hiast_b200.ias_engine import IASEngine
+    g = torch.Generator().manual_seed(3)
+    lr = (torch.randn(4, 19, 9, 17, generator=g) * 4).cuda()
+    full = torch.nn.functional.interpolate(lr, size=(64, 128), mode='bilinear', align_corners=True).contiguous()
+    a = IASEngine(19, 64, 128, 2, 0.5, 0.9, 8.0, 0.99, 4)
+    b = IASEngine(19, 64, 128, 2, 0.5, 0.9, 8.0, 0.99, 4)
+    a.phase_a_lowres(lr)
+    b.phase_a(full)
+    for e in (a, b):
+        e.phase_b(0, 4)
+        e.phase_c(0, 4)
+        e.mean_prob(0, 4)
+    assert torch.equal(a.plbl, b.plbl) and torch.equal(a.thr_groups, b.thr_groups) and torch.equal(a.mean_state, b.mean_state)

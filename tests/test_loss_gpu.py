@@ -201,3 +201,25 @@ def test_segmentor_with_kldiv_consistency():
     sum(ref).backward()
     np.testing.assert_allclose([v.item() for v in out.values()], [v.item() for v in ref], rtol=RTOL)
     grad_close(z.grad, z2.grad)
+
+
+def test_softce_from_teacher_logits_equals_softce_of_softmax():
+    """8f rank 4: the teacher softmax fused into the kernel gives the same loss / gradient as feeding probabilities."""
+    import hiast_b200
+    hiast_b200.register_all()
+    from hiast_b200 import LOSS
+    g = torch.Generator().manual_seed(44)
+    for shape in [(2, 19, 16, 24), (1, 7, 9, 11)]:
+        z0 = (torch.randn(*shape, generator=g) * 3).cuda()
+        tz = (torch.randn(*shape, generator=g) * 3).cuda()
+        y = torch.randint(0, shape[1], (shape[0],) + shape[2:], generator=g)
+        y[torch.rand(y.shape, generator=g) < 0.5] = 255
+        y = y.cuda()
+        z1 = z0.clone().requires_grad_(True)
+        a = LOSS['SoftCE_from_logits'](z1, tz, refer_labels=y, region='ignored')
+        a.backward()
+        z2 = z0.clone().requires_grad_(True)
+        b = oloss.soft_ce(z2, torch.softmax(tz, dim=1), refer_labels=y, region='ignored')
+        b.backward()
+        np.testing.assert_allclose(a.item(), b.item(), rtol=RTOL)
+        grad_close(z1.grad, z2.grad)

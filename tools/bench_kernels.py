@@ -127,6 +127,22 @@ def main():
         ms = timeit(torch_a1)
         res['torch_a1_%s' % dist] = dict(ms=ms, img_s=4 / ms * 1e3)
         del logits
+    # fused up-sampling: stride-8 logits [n,19,129,257] -> IAS phase A at 1024x2048, vs interpolate + phase A
+    lr = torch.randn(n, C, 129, 257, device='cuda') * 4
+    conf = torch.empty(n, H, W, device='cuda')
+    label = torch.empty(n, H, W, dtype=torch.uint8, device='cuda')
+    hist = ops.ias_new_hist(G, C, key_lo, 'cuda')
+    full = torch.empty(n, C, H, W, device='cuda')
+
+    def two_step():
+        torch.nn.functional.interpolate(lr, size=(H, W), mode='bilinear', align_corners=True, out=None)
+        ops.ias_softmax_hist(full, B, key_lo, conf, label, hist)
+    ms_fused = timeit(lambda: ops.ias_upsample_softmax_hist(lr, (H, W), B, key_lo, conf, label, hist), iters=5)
+    ms_interp = timeit(lambda: torch.nn.functional.interpolate(lr, size=(H, W), mode='bilinear', align_corners=True), iters=5)
+    ms_a = timeit(lambda: ops.ias_softmax_hist(full, B, key_lo, conf, label, hist), iters=5)
+    res['upsample_fused'] = dict(ms_fused=ms_fused, img_s_fused=n / ms_fused * 1e3, ms_interpolate=ms_interp, ms_phase_a=ms_a,
+                                 img_s_two_step=n / (ms_interp + ms_a) * 1e3)
+    del lr, full
     # loss fwd/bwd, config 3
     z = torch.randn(2, 19, 512, 1024, device='cuda') * 3
     t = torch.softmax(torch.randn(2, 19, 512, 1024, device='cuda') * 3, dim=1)
