@@ -37,6 +37,9 @@ _SIGNATURES = {
     'hiast_ias_threshold_scan': (_i, [_vp, _i, _i, _i, _d, _d, _d, _vp, _vp, _vp, _vp, _vp]),
     'hiast_ias_select': (_i, [_vp, _vp, _vp, _i, _i64, _i, _i, _vp, _vp, _vp, _vp]),
     'hiast_ias_meanprob_scan': (_i, [_vp, _vp, _i, _i, _i, _i, _d, _vp, _vp]),
+    'hiast_cbst_workspace_bytes': (_sz, [_i, _i64, _i]),
+    'hiast_cbst_sample_hist': (_i, [_vp, _vp, _i, _i64, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
+    'hiast_cbst_quantile': (_i, [_vp, _i, _i, _d, _vp, _vp, _vp]),
     'hiast_copy_paste': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _vp, _vp]),
     'hiast_st_loss_workspace_bytes': (_sz, [_i, _i, _i64]),
     'hiast_st_loss_fwd': (_i, [_vp, _vp, _vp, _i, _i, _i, _i64, _i, _i, _vp, _vp, _vp, _sz, _vp]),

@@ -48,20 +48,31 @@ __global__ void __launch_bounds__(kThreadsM) k_confusion(const T* __restrict__ p
   }
   CmSink sink = {use_shared ? s_cm : nullptr, cm};
   // per-CTA contiguous chunk, rounded so that every warp iteration is full except the last one
-  const long long per = ((n + gridDim.x - 1) / gridDim.x + kThreadsM - 1) / kThreadsM * kThreadsM;
+  const long long per = ((n + gridDim.x - 1) / gridDim.x + kThreadsM * 4 - 1) / (kThreadsM * 4) * (kThreadsM * 4);
   const long long i0 = per * blockIdx.x;
   const long long i1 = min(n, i0 + per);
-  for (long long base = i0; base < i1; base += kThreadsM) {
-    const long long i = base + threadIdx.x;
-    const bool in = i < i1;
-    long long p = 0, t = ignore_index;
-    if (in) {
-      p = static_cast<long long>(pred[i]);
-      t = static_cast<long long>(target[i]);
+  constexpr int kUnroll = 4;   // independent load pairs in flight per thread
+  for (long long base = i0; base < i1; base += kThreadsM * kUnroll) {
+    long long p[kUnroll], t[kUnroll];
+    bool in[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const long long i = base + u * kThreadsM + threadIdx.x;
+      in[u] = i < i1;
+      p[u] = 0;
+      t[u] = ignore_index;
+      if (in[u]) {
+        p[u] = static_cast<long long>(__ldcs(pred + i));
+        t[u] = static_cast<long long>(__ldcs(target + i));
+      }
     }
-    const bool keep = in && (t != ignore_index);
-    if (in && pred_out) pred_out[i] = keep ? static_cast<T>(p) : static_cast<T>(ignore_index);
-    sink.add(keep, clamp_class(t, K) * (K + 1) + clamp_class(p, K));
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const long long i = base + u * kThreadsM + threadIdx.x;
+      const bool keep = in[u] && (t[u] != ignore_index);
+      if (in[u] && pred_out) pred_out[i] = keep ? static_cast<T>(p[u]) : static_cast<T>(ignore_index);
+      sink.add(keep, clamp_class(t[u], K) * (K + 1) + clamp_class(p[u], K));
+    }
   }
   if (use_shared) {
     __syncthreads();

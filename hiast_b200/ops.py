@@ -16,7 +16,7 @@ from ._lib import IGNORE, KEY_ONE, REGION, TERM_CE, TERM_CST, TERM_ENT, TERM_KLD
 
 __all__ = [
     'ias_key_lo', 'ias_num_bins', 'ias_row_stride', 'ias_new_hist', 'ias_softmax_hist', 'ias_upsample_softmax_hist', 'ias_conf_hist', 'ias_threshold_scan',
-    'ias_select', 'ias_meanprob_scan', 'copy_paste', 'hard_lut', 'st_loss_fwd', 'st_loss_bwd',
+    'ias_select', 'ias_meanprob_scan', 'cbst_sample_hist', 'cbst_quantile', 'copy_paste', 'hard_lut', 'st_loss_fwd', 'st_loss_bwd',
     'confusion_matrix', 'confusion_from_logits', 'iou_from_confusion',
 ]
 
@@ -174,6 +174,30 @@ def ias_meanprob_scan(confsum, counts, group_size, num_classes, cp_gamma, mean_s
                                         float(cp_gamma), ptr(mean_state), stream_ptr(counts.device)),
           'hiast_ias_meanprob_scan')
     return mean_state
+
+
+# ---------------------------------------------------------------------------- CBST
+def cbst_sample_hist(conf, label, num_classes, group_size, sample_interval, key_lo, hist):
+    """Accumulate the every-k-th-in-raster-order fp16 samples of one or more batches into hist i32 [C,row_stride]."""
+    require_cuda(conf, torch.float32, 'conf')
+    require_cuda(label, torch.uint8, 'label')
+    require_cuda(hist, torch.int32, 'hist')
+    n = conf.shape[0]
+    hw = conf[0].numel() if n else 1
+    dev = conf.device
+    need = lib().hiast_cbst_workspace_bytes(n, hw, int(num_classes))
+    ws = torch.empty(max(need, 16), dtype=torch.uint8, device=dev)
+    check(lib().hiast_cbst_sample_hist(ptr(conf), ptr(label), n, hw, int(num_classes), int(group_size), int(sample_interval),
+                                       int(key_lo), ptr(hist), ptr(ws), ws.numel(), stream_ptr(dev)), 'hiast_cbst_sample_hist')
+    return hist
+
+
+def cbst_quantile(hist, num_classes, key_lo, q, error_flag=None):
+    require_cuda(hist, torch.int32, 'hist')
+    thr = torch.empty(num_classes, dtype=torch.float64, device=hist.device)
+    check(lib().hiast_cbst_quantile(ptr(hist), int(num_classes), int(key_lo), float(q), ptr(thr), ptr(error_flag),
+                                    stream_ptr(hist.device)), 'hiast_cbst_quantile')
+    return thr
 
 
 # ---------------------------------------------------------------------- copy-paste

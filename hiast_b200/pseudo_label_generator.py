@@ -18,7 +18,7 @@ injected ``model`` / ``loader`` (any callable returning ``{'logits': [B,C,H,W]}`
 ``{'images', 'image_paths'}``).  Inside a reference checkout, bind the reference's own
 ``initialize`` instead (INTEGRATION.md).
 
-CBST (:142-165) is not ported yet.
+``CBSTPseudoGenerator`` ('CBST') :142-165 is implemented on the device as well (two passes over the loader).
 """
 
 from __future__ import annotations
@@ -249,7 +249,29 @@ class NoThresholdPseudoGenerator(ConstantThresholdPseudoGenerator):
 class CBSTPseudoGenerator(ConstantThresholdPseudoGenerator):
 
     def get_constant_threshold(self):
-        raise NotImplementedError('CBST (pseudo_label_generator.py:142-165) is not ported yet (SURVEY.md 8f rank 3)')
+        """:145-165.  First pass over the target set: per batch and class, every ``cbst.sample_interval``-th
+        confidence (raster order, fp16) goes into one per-class histogram on the device; the thresholds are the
+        (1 - cbst.p) quantiles.  ``run`` then makes the second pass with these constant thresholds (:115-132)."""
+        C = self.cfg.dataset.num_classes
+        cbst = self.cfg.pseudo_policy.cbst
+        key_lo = ops.ias_key_lo(C)
+        hist = None
+        for logits, _paths in self._iterate_logits():
+            b = logits.shape[0]
+            conf, label, _ = ops.ias_softmax_hist(logits, b)            # phase A (its own histogram is not used here)
+            if hist is None:
+                hist = torch.zeros((C, ops.ias_row_stride(key_lo)), dtype=torch.int32, device=logits.device)
+            ops.cbst_sample_hist(conf, label, C, b, int(cbst.sample_interval), key_lo, hist)
+        if hist is None:
+            raise IndexError('index -1 is out of bounds for axis 0 with size 0')     # np.quantile([]) on an empty set
+        flag = torch.zeros(1, dtype=torch.int32, device=hist.device)
+        thr = ops.cbst_quantile(hist, C, key_lo, 1 - cbst.p, flag)
+        code = int(flag.item())
+        if code & 4:
+            raise IndexError('index -1 is out of bounds for axis 0 with size 0')     # a class was never predicted
+        if code & 1:
+            raise ValueError('Quantiles must be in the range [0, 1]')
+        return thr.cpu().numpy()
 
 
 @PSEUDO_POLICY.register('IAS')

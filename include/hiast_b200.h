@@ -133,6 +133,19 @@ HIAST_API int hiast_ias_meanprob_scan(const uint64_t* confsum, const int64_t* co
                             int n_images, int group_size, int n_groups, int C, double cp_gamma,
                             double* mean_state, void* stream);
 
+/* CBST policy (8f rank 3)  :142-165.  Adds to hist u32 [C][row_stride] (one histogram for the whole data set,
+ * accumulated over calls) the fp16 keys of the pixels whose rank among the pixels of their class, in raster
+ * order over the images of their batch (group), is a multiple of sample_interval.  workspace: see
+ * hiast_cbst_workspace_bytes.  C <= 48.                                                                   */
+HIAST_API size_t hiast_cbst_workspace_bytes(int n_images, int64_t HW, int C);
+HIAST_API int hiast_cbst_sample_hist(const float* conf, const uint8_t* label, int n_images, int64_t HW, int C,
+                           int group_size, int sample_interval, int key_lo, uint32_t* hist,
+                           void* workspace, size_t workspace_bytes, void* stream);
+/* thr f64[C] = np.quantile(samples_c, q) ('linear') read off that histogram.  *error_flag |= 4 for a class
+ * without samples (numpy raises IndexError; thr = NaN), |= 1 for q outside [0,1].                          */
+HIAST_API int hiast_cbst_quantile(const uint32_t* hist, int C, int key_lo, double q, double* thr,
+                        int* error_flag, void* stream);
+
 /* ---- (2) hard-aware copy-paste  sseg/datasets/preprocessor.py:102-112 ------------------- */
 /* For image i with donor d = donor_index ? donor_index[i] : i, per pixel:
  *   M = hard[donor_lbl]; img = M ? donor_img : img; lbl = M ? donor_lbl : lbl;

@@ -216,3 +216,28 @@ class IASOracle:
             for logits, paths in batches:
                 self.step_logits(logits, paths)
         return self
+
+
+# ------------------------------------------------------------------------ CBST
+def cbst_thresholds(batches_conf_label, num_classes, sample_interval, p, f64_quantile=True):
+    """CBSTPseudoGenerator.get_constant_threshold (:145-165): every sample_interval-th fp16 confidence per class and
+    batch (raster order), then the (1 - p) quantile per class.  float64[C].
+
+    ``f64_quantile=True`` (default) evaluates the quantile in float64, which is what the reference's pinned numpy
+    1.19.2 does and what the CUDA path implements.  With numpy >= 2 the reference's call ``np.quantile(list of
+    np.float16, python float)`` casts q AND the virtual index (n-1)*q to float16 (NEP 50): the index is rounded
+    to ~3 digits and overflows to inf beyond 65 504 samples, so every threshold degenerates to the class's
+    largest sample on real data.  ``f64_quantile=False`` reproduces that installed-version behaviour (used only
+    to pin this restatement against the fixture generated with numpy 2.3.5)."""
+    samples = {c: [] for c in range(num_classes)}
+    for conf, label in batches_conf_label:
+        for c in range(num_classes):
+            vals = conf[label == c].astype(np.float16)
+            samples[c].extend(vals[0:len(vals):sample_interval])
+    thr = np.ones(num_classes)
+    for c in range(num_classes):
+        if f64_quantile:
+            thr[c] = np.quantile(np.asarray(samples[c], dtype=np.float64), 1 - p)
+        else:
+            thr[c] = np.quantile(samples[c], 1 - p)
+    return thr

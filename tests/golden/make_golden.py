@@ -9,6 +9,7 @@ none of the stubs touch the arithmetic of the hot path.  Every fixture is the
 output of the reference's own functions on seeded inputs:
 
 * ias_*.npz       IASPseudoGenerator.run        workflows/pseudo_label_generator.py:181-213
+* cbst_small.npz  CBSTPseudoGenerator.run       workflows/pseudo_label_generator.py:142-165,115-132
 * loss_cst_variants.npz  LOSS['KLDIV'], LOSS['MSE']      sseg/models/modules/losses.py:9-23
 * loss_*.npz      SelfTrainingSegmentor.compute_loss + autograd
                                                 sseg/models/segmentors/self_training_segmentor.py:30-53
@@ -139,6 +140,47 @@ def ias_fixture(name, spec, store_conf=True):
     print(name, 'thr', gen.class_threshold[:4], 'kept', counts.sum(), 'of', n_img * spec['H'] * spec['W'])
 
 
+def cbst_fixture(name, spec, interval, p):
+    """CBSTPseudoGenerator.run (two passes) of the reference, pseudo_label_generator.py:142-165 + :115-132."""
+    from workflows import pseudo_label_generator as plg
+    batches = gi.ias_batches(spec)
+
+    class Identity:
+        def eval(self):
+            return self
+
+        def __call__(self, x):
+            return {'logits': x}
+
+    class Harness(plg.CBSTPseudoGenerator):
+        def initialize(self):
+            self.model = Identity()
+            self.t_loader = [{'images': lg, 'image_paths': paths} for lg, paths in batches]
+            self.t_dataset = [None] * sum(len(pp) for _, pp in batches)
+            self.pseudo_label_save_dir = tempfile.mkdtemp()
+            self.captured = []
+
+        def save_pseudo_label(self, plbl, img_path):
+            self.captured.append(plbl.astype(np.uint8))
+
+        def save_data(self):
+            pass
+
+    cfg = SimpleNamespace(
+        dataset=SimpleNamespace(num_classes=spec['C']),
+        pseudo_policy=SimpleNamespace(type='CBST', cbst=SimpleNamespace(sample_interval=interval, p=p)),
+        preprocessor=SimpleNamespace(copy_paste=SimpleNamespace(gamma=spec['cp_gamma'])))
+    import contextlib
+    import io
+    gen = Harness(cfg)
+    with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+        gen.run()
+    np.savez_compressed(os.path.join(HERE, name + '.npz'), spec=np.array(repr(spec)), interval=interval, p=p,
+                        class_threshold=gen.class_threshold, plbl=np.stack(gen.captured),
+                        statics_class=np.asarray(gen.statics_class, dtype=np.int64), class_mean_probs=gen.class_mean_probs)
+    print(name, gen.class_threshold[:5])
+
+
 # ---------------------------------------------------------------------------- loss
 def loss_fixture(name, spec):
     from sseg.models.modules import losses
@@ -232,6 +274,7 @@ def main():
     install_shim()
     for name, spec in gi.IAS_SPECS.items():
         ias_fixture(name, spec, store_conf=spec.get('store_conf', True))
+    cbst_fixture('cbst_small', gi.IAS_SPECS['ias_small'], 4, 0.2)
     for name, spec in gi.LOSS_SPECS.items():
         loss_fixture(name, spec)
     cst_variant_fixture('loss_cst_variants', gi.CST_VARIANT_SPEC)

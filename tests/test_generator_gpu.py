@@ -221,3 +221,57 @@ def test_config5_full_round_example_small():
     assert out.returncode == 0, out.stderr[-2000:]
     res = json.loads(out.stdout.strip().splitlines()[-1])
     assert res['images'] == 5 and 0.0 <= res['miou'] <= 1.0 and res['pow_rounding_certified']
+
+
+def test_cbst_policy_matches_oracle_and_reference_fixture(tmp_path):
+    """PSEUDO_POLICY['CBST'] (pseudo_label_generator.py:142-165): every-k-th raster-order sampling, quantile thresholds,
+    second pass with the constant thresholds.  Bit-exact vs the oracle (float64 quantile = the reference's pinned
+    numpy 1.19 semantic, see oracle.ias.cbst_thresholds) on CUDA softmax; within one fp16 step of the fixture, which
+    numpy 2.3.5 computed with a float16 virtual index."""
+    import hiast_b200
+    hiast_b200.register_all()
+    from hiast_b200 import PSEUDO_POLICY
+    spec = gi.IAS_SPECS['ias_small']
+    gold = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'cbst_small.npz'))
+    batches = gi.ias_batches(spec)
+    captured = []
+
+    class Gen(PSEUDO_POLICY['CBST']):
+        def save_pseudo_label(self, plbl, img_path):
+            captured.append(plbl.copy())
+
+        def save_data(self):
+            pass
+
+    cfg = make_cfg(spec, 'CBST')
+    cfg.pseudo_policy.cbst = SimpleNamespace(sample_interval=int(gold['interval']), p=float(gold['p']))
+    gen = Gen(cfg, model=Identity(), loader=loader_of(batches), dataset_len=spec['N'], save_dir=str(tmp_path / 'p'),
+              window_batches=2)
+    gen.run()
+    cl = [oias.softmax_max(lg.cuda()) for lg, _ in batches]
+    thr = oias.cbst_thresholds(cl, spec['C'], int(gold['interval']), float(gold['p']))
+    assert np.array_equal(gen.class_threshold, thr)
+    want = [oias.select_confident(c[k], l[k], thr).astype(np.uint8) for c, l in cl for k in range(len(c))]
+    assert np.array_equal(np.stack(captured), np.stack(want))
+    assert np.abs(gen.class_threshold - gold['class_threshold']).max() < 2e-3
+
+
+def test_cbst_sampling_full_resolution_properties():
+    """19x1024x2048, batch 2: the sampled histogram holds ceil(n_c / k) samples per class and batch."""
+    from hiast_b200 import ops
+    g = torch.Generator(device='cuda').manual_seed(5)
+    logits = torch.randn(4, 19, 1024, 2048, generator=g, device='cuda') * 3
+    conf, label, _ = ops.ias_softmax_hist(logits, 2)
+    key_lo = ops.ias_key_lo(19)
+    hist = torch.zeros((19, ops.ias_row_stride(key_lo)), dtype=torch.int32, device='cuda')
+    ops.cbst_sample_hist(conf, label, 19, 2, 4, key_lo, hist)
+    want = torch.zeros(19, dtype=torch.int64, device='cuda')
+    for b in range(2):
+        n_c = torch.bincount(label[2 * b:2 * b + 2].flatten().long(), minlength=19)
+        want += (n_c + 3) // 4
+    assert torch.equal(hist.sum(1).long(), want)
+    # the samples of class c are exactly conf[label == c][::4] of each batch (raster order)
+    c = 7
+    vals = torch.cat([conf[2 * b:2 * b + 2][label[2 * b:2 * b + 2] == c][::4] for b in range(2)])
+    keys = vals.half().view(torch.int16).long() - key_lo
+    assert torch.equal(hist[c].long(), torch.bincount(keys, minlength=hist.shape[1]))
