@@ -220,49 +220,97 @@ __device__ __forceinline__ void block_reduce_store(const PixelSums& acc, Partial
   }
 }
 
-// Vector path: HW even, C compile-time.  Grid-stride over pairs of pixels.
+// Vector path: HW even, C compile-time.  Grid-stride over pairs of pixels, software-pipelined with cp.async:
+// every thread owns 2C x 8 bytes of shared memory (its pixel pair's z and t columns); at the top of an iteration it
+// pulls them into registers, immediately re-issues the 8-byte cp.async of ITS next pixel pair into the same
+// slots, and does the math while they are in flight (LDGSTS is tracked by async groups, not by the register
+// scoreboard the MUFU results of the math use -- same reasoning as k_softmax_hist_sp in ias.cu).
 template <int C>
-__global__ void __launch_bounds__(kThreadsL, 2) k_loss_fwd(LossArgs a, Partial* __restrict__ partials) {
-  const int64_t HW2 = a.HW / kPxL;
-  const long long total = static_cast<long long>(a.B) * HW2;
-  PixelSums acc = {0.0, 0.0, 0.0, 0.0, 0, 0, 0};
-  const bool need_t = (a.terms & HIAST_TERM_CST) != 0;
-  for (long long i = static_cast<long long>(blockIdx.x) * kThreadsL + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * kThreadsL) {
+struct LossStage {
+  float2* my;          // this thread's column: [2C][kThreadsL] float2, z channels then t channels
+  unsigned my_u32;
+  const LossArgs& a;
+  int64_t HW2;
+  bool need_t;
+
+  __device__ __forceinline__ LossStage(float2* smem, const LossArgs& args)
+      : my(smem + threadIdx.x), my_u32(static_cast<unsigned>(__cvta_generic_to_shared(smem + threadIdx.x))), a(args),
+        HW2(args.HW / kPxL), need_t((args.terms & HIAST_TERM_CST) != 0) {}
+
+  __device__ __forceinline__ void prefetch(long long i) const {
     const int b = static_cast<int>(i / HW2);
     const int64_t p2 = i - static_cast<long long>(b) * HW2;
     const float2* zs = reinterpret_cast<const float2*>(a.z + static_cast<size_t>(b) * C * a.HW) + p2;
-    float z[kPxL][C], t[kPxL][C];
 #pragma unroll
-    for (int c = 0; c < C; ++c) {
-      const float2 q = __ldcs(zs + static_cast<size_t>(c) * HW2);
-      z[0][c] = q.x; z[1][c] = q.y;
-    }
+    for (int c = 0; c < C; ++c)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(my_u32 + c * kThreadsL * 8),
+                   "l"(zs + static_cast<size_t>(c) * HW2) : "memory");
     if (need_t) {
       const float2* ts = reinterpret_cast<const float2*>(a.t + static_cast<size_t>(b) * C * a.HW) + p2;
 #pragma unroll
+      for (int c = 0; c < C; ++c)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(my_u32 + (C + c) * kThreadsL * 8),
+                     "l"(ts + static_cast<size_t>(c) * HW2) : "memory");
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  }
+  __device__ __forceinline__ void wait() const { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+  // registers <- shared; returns a value that depends on every load so that the refill can be ordered after it
+  __device__ __forceinline__ float load(float (&z)[kPxL][C], float (&t)[kPxL][C]) const {
+    float guard = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float2 q = my[c * kThreadsL];
+      z[0][c] = q.x; z[1][c] = q.y;
+      guard = fmaxf(guard, q.x);
+    }
+    if (need_t) {
+#pragma unroll
       for (int c = 0; c < C; ++c) {
-        const float2 q = __ldcs(ts + static_cast<size_t>(c) * HW2);
+        const float2 q = my[(C + c) * kThreadsL];
         t[0][c] = q.x; t[1][c] = q.y;
+        guard = fmaxf(guard, q.x);
       }
     } else {
 #pragma unroll
       for (int c = 0; c < C; ++c) t[0][c] = t[1][c] = 0.f;
     }
-    const size_t lp = static_cast<size_t>(b) * a.HW + p2 * kPxL;
+    return guard;
+  }
+};
+
+template <int C>
+__global__ void __launch_bounds__(kThreadsL, 2) k_loss_fwd(LossArgs a, Partial* __restrict__ partials) {
+  extern __shared__ __align__(16) float2 s_loss_stage[];
+  const LossStage<C> st(s_loss_stage, a);
+  const long long total = static_cast<long long>(a.B) * st.HW2;
+  const long long stride = static_cast<long long>(gridDim.x) * kThreadsL;
+  PixelSums acc = {0.0, 0.0, 0.0, 0.0, 0, 0, 0};
+  long long i = static_cast<long long>(blockIdx.x) * kThreadsL + threadIdx.x;
+  if (i < total) st.prefetch(i);
+  st.wait();
+  for (; i < total; i += stride) {
+    float z[kPxL][C], t[kPxL][C];
+    const float guard = st.load(z, t);
+    if (i + stride < total && guard == guard) st.prefetch(i + stride);
+    const int b = static_cast<int>(i / st.HW2);
+    const size_t lp = static_cast<size_t>(b) * a.HW + (i - static_cast<long long>(b) * st.HW2) * kPxL;
 #pragma unroll
     for (int j = 0; j < kPxL; ++j) pixel_forward<C>(z[j], t[j], load_label(a.plbl, a.plbl_bytes, lp + j), a.region, a.terms, acc);
+    st.wait();
   }
   block_reduce_store(acc, partials);
 }
 
 template <int C>
 __global__ void __launch_bounds__(kThreadsL, 2) k_loss_bwd(LossArgs a, const float* __restrict__ scales,
-                                                        float* __restrict__ grad) {
-  const int64_t HW2 = a.HW / kPxL;
-  const long long total = static_cast<long long>(a.B) * HW2;
+                                                           float* __restrict__ grad) {
+  extern __shared__ __align__(16) float2 s_loss_stage[];
+  const LossStage<C> st(s_loss_stage, a);
+  const long long total = static_cast<long long>(a.B) * st.HW2;
+  const long long stride = static_cast<long long>(gridDim.x) * kThreadsL;
   const float sc[4] = {scales[0], scales[1], scales[2], scales[3]};
-  const bool need_t = (a.terms & HIAST_TERM_CST) != 0;
   // The reference divides a masked sum by an element count: an empty region makes its scale inf/NaN and
   // autograd then yields NaN for EVERY element (inf * 0).  `poison` is 0 unless some enabled scale is
   // non-finite, in which case it is NaN.
@@ -270,28 +318,15 @@ __global__ void __launch_bounds__(kThreadsL, 2) k_loss_bwd(LossArgs a, const flo
 #pragma unroll
   for (int k = 0; k < 4; ++k)
     if (a.terms & (1 << k)) poison += 0.f * sc[k];
-  for (long long i = static_cast<long long>(blockIdx.x) * kThreadsL + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * kThreadsL) {
-    const int b = static_cast<int>(i / HW2);
-    const int64_t p2 = i - static_cast<long long>(b) * HW2;
-    const float2* zs = reinterpret_cast<const float2*>(a.z + static_cast<size_t>(b) * C * a.HW) + p2;
+  long long i = static_cast<long long>(blockIdx.x) * kThreadsL + threadIdx.x;
+  if (i < total) st.prefetch(i);
+  st.wait();
+  for (; i < total; i += stride) {
     float z[kPxL][C], t[kPxL][C];
-#pragma unroll
-    for (int c = 0; c < C; ++c) {
-      const float2 q = __ldcs(zs + static_cast<size_t>(c) * HW2);
-      z[0][c] = q.x; z[1][c] = q.y;
-    }
-    if (need_t) {
-      const float2* ts = reinterpret_cast<const float2*>(a.t + static_cast<size_t>(b) * C * a.HW) + p2;
-#pragma unroll
-      for (int c = 0; c < C; ++c) {
-        const float2 q = __ldcs(ts + static_cast<size_t>(c) * HW2);
-        t[0][c] = q.x; t[1][c] = q.y;
-      }
-    } else {
-#pragma unroll
-      for (int c = 0; c < C; ++c) t[0][c] = t[1][c] = 0.f;
-    }
+    const float guard = st.load(z, t);
+    if (i + stride < total && guard == guard) st.prefetch(i + stride);
+    const int b = static_cast<int>(i / st.HW2);
+    const int64_t p2 = i - static_cast<long long>(b) * st.HW2;
     const size_t lp = static_cast<size_t>(b) * a.HW + p2 * kPxL;
     PixelBwd<C> px0, px1;
     px0.init(z[0], t[0], load_label(a.plbl, a.plbl_bytes, lp), a.region, a.terms, sc);
@@ -299,8 +334,9 @@ __global__ void __launch_bounds__(kThreadsL, 2) k_loss_bwd(LossArgs a, const flo
     float2* gs = reinterpret_cast<float2*>(grad + static_cast<size_t>(b) * C * a.HW) + p2;
 #pragma unroll
     for (int c = 0; c < C; ++c)
-      __stcs(gs + static_cast<size_t>(c) * HW2,
+      __stcs(gs + static_cast<size_t>(c) * st.HW2,
              make_float2(px0.grad(c, z[0][c], t[0][c]) + poison, px1.grad(c, z[1][c], t[1][c]) + poison));
+    st.wait();
   }
 }
 
@@ -472,6 +508,24 @@ bool loss_vector_ok(const LossArgs& a, const void* extra) {
          (!a.t || reinterpret_cast<uintptr_t>(a.t) % 8 == 0) && (reinterpret_cast<uintptr_t>(extra) % 8 == 0);
 }
 
+size_t loss_stage_bytes(int C) { return sizeof(float2) * 2 * C * kThreadsL; }
+
+cudaError_t loss_configure_smem(int C, size_t smem) {
+  static thread_local bool done19 = false, done16 = false;
+  bool& done = (C == 19) ? done19 : done16;
+  if (done) return cudaSuccess;
+  cudaError_t e;
+  if (C == 19) {
+    e = cudaFuncSetAttribute(k_loss_fwd<19>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_loss_bwd<19>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  } else {
+    e = cudaFuncSetAttribute(k_loss_fwd<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_loss_bwd<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  }
+  done = (e == cudaSuccess);
+  return e;
+}
+
 }  // namespace hiast
 
 using namespace hiast;
@@ -503,10 +557,13 @@ extern "C" int hiast_st_loss_fwd(const float* z, const float* t, const void* plb
   cudaStream_t st = as_stream(stream);
   LossArgs a = {z, t, plbl, plbl_bytes, B, C, HW, region, terms};
   Partial* parts = static_cast<Partial*>(workspace);
-  const int grid = loss_grid(static_cast<long long>(B) * HW);
+  int grid = loss_grid(static_cast<long long>(B) * HW);
   if (loss_vector_ok(a, nullptr)) {
-    if (C == 19) k_loss_fwd<19><<<grid, kThreadsL, 0, st>>>(a, parts);
-    else k_loss_fwd<16><<<grid, kThreadsL, 0, st>>>(a, parts);
+    grid = std::min(grid, sm_count() * 2);   // persistent: one resident wave, every thread pipelines its own sequence
+    const size_t smem = loss_stage_bytes(C);
+    HIAST_CUDA_TRY(loss_configure_smem(C, smem));
+    if (C == 19) k_loss_fwd<19><<<grid, kThreadsL, smem, st>>>(a, parts);
+    else k_loss_fwd<16><<<grid, kThreadsL, smem, st>>>(a, parts);
   } else {
     k_loss_fwd_generic<<<grid, kThreadsL, 0, st>>>(a, parts);
   }
@@ -524,10 +581,13 @@ extern "C" int hiast_st_loss_bwd(const float* z, const float* t, const void* plb
   if (B == 0) return HIAST_OK;
   cudaStream_t st = as_stream(stream);
   LossArgs a = {z, t, plbl, plbl_bytes, B, C, HW, region, terms};
-  const int grid = loss_grid(static_cast<long long>(B) * HW);
+  int grid = loss_grid(static_cast<long long>(B) * HW);
   if (loss_vector_ok(a, grad_z)) {
-    if (C == 19) k_loss_bwd<19><<<grid, kThreadsL, 0, st>>>(a, scales, grad_z);
-    else k_loss_bwd<16><<<grid, kThreadsL, 0, st>>>(a, scales, grad_z);
+    grid = std::min(grid, sm_count() * 2);
+    const size_t smem = loss_stage_bytes(C);
+    HIAST_CUDA_TRY(loss_configure_smem(C, smem));
+    if (C == 19) k_loss_bwd<19><<<grid, kThreadsL, smem, st>>>(a, scales, grad_z);
+    else k_loss_bwd<16><<<grid, kThreadsL, smem, st>>>(a, scales, grad_z);
   } else {
     k_loss_bwd_generic<<<grid, kThreadsL, 0, st>>>(a, scales, grad_z);
   }

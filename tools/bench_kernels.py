@@ -132,7 +132,7 @@ def main():
     conf = torch.empty(n, H, W, device='cuda')
     label = torch.empty(n, H, W, dtype=torch.uint8, device='cuda')
     hist = ops.ias_new_hist(G, C, key_lo, 'cuda')
-    full = torch.empty(n, C, H, W, device='cuda')
+    full = torch.nn.functional.interpolate(lr, size=(H, W), mode='bilinear', align_corners=True).contiguous()
 
     def two_step():
         torch.nn.functional.interpolate(lr, size=(H, W), mode='bilinear', align_corners=True, out=None)
