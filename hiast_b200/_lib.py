@@ -47,6 +47,7 @@ _SIGNATURES = {
     'hiast_confusion_matrix': (_i, [_vp, _vp, _i, _i64, _i, _i, _vp, _vp, _vp]),
     'hiast_confusion_from_logits': (_i, [_vp, _vp, _i, _i, _i, _i64, _i, _i, _vp, _vp]),
     'hiast_iou_from_confusion': (_i, [_vp, _i, _vp, _vp, _vp]),
+    'hiast_selftest_packed_expf': (_i, [_vp, _vp]),
     'hiast_testhook_powi': (_d, [_d, _i]),
     'hiast_testhook_threshold_step': (_d, [_vp, _i, _d, _d, _d, _d, _vp, _vp]),
 }

@@ -202,6 +202,12 @@ HIAST_API double hiast_testhook_threshold_step(const uint32_t* prefix_row_host, 
                                      double thr, double alpha, double beta, double gamma,
                                      float* temp_out, int* error_out);
 
+/* ---- device-side self test (needs a GPU; used by tests only) ---------------------------- */
+/* Sweeps EVERY non-positive float (bit patterns 0x80000000..0xFF800000 and +0) through the packed
+ * (f32x2) exponential used by phase A and compares it bit for bit with CUDA's expf();
+ * *mismatches_dev (device u64) receives the number of differing inputs.                      */
+HIAST_API int hiast_selftest_packed_expf(unsigned long long* mismatches_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

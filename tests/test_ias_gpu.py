@@ -29,7 +29,7 @@ def torch_softmax_max(logits):
 
 
 @pytest.mark.parametrize('shape', [(2, 19, 64, 128), (3, 19, 33, 52), (1, 16, 40, 64), (2, 7, 31, 51), (1, 40, 9, 13)])
-@pytest.mark.parametrize('mode', [1, 2, 3, 4, 5, 6, 11, 16, 21, 25, 26, 31, 36, 41, 46])
+@pytest.mark.parametrize('mode', [1, 2, 3, 4, 5, 6, 11, 16, 21, 25, 26, 31, 36, 41, 46, 51, 56, 61, 66, 71, 76, 80])
 def test_phase_a_bit_exact_vs_torch_cuda(shape, mode):
     o = ops()
     g = torch.Generator().manual_seed(sum(shape) + mode)
@@ -50,6 +50,15 @@ def test_phase_a_bit_exact_vs_torch_cuda(shape, mode):
     assert np.array_equal(hist[:, :, :nb].cpu().numpy().astype(np.uint32), want_hist)
 
 
+def test_packed_expf_is_expf_for_every_non_positive_float():
+    """The f32x2 exponential of phase A (modes 51/56) against CUDA's expf(), all 2^31 - 2^23 + 2 inputs."""
+    import ctypes
+    from hiast_b200 import _lib
+    bad = torch.ones(1, dtype=torch.int64, device='cuda')
+    _lib.check(_lib.lib().hiast_selftest_packed_expf(_lib.ptr(bad), _lib.stream_ptr(bad.device)), 'selftest')
+    assert int(bad.item()) == 0
+
+
 def test_phase_a_ties_and_near_ties():
     """Exact logit ties, channels a hair below the max (expf -> 1.0f), constant maps, huge gaps."""
     o = ops()
@@ -63,9 +72,14 @@ def test_phase_a_ties_and_near_ties():
         x[1, k] = top * (1 - eps) - eps                     # a hair below the max, earlier channels
     x[2] = 0.0                                              # all equal -> conf = 1/19, label 0
     x[3, 5] += 40.0                                         # saturated: conf == 1.0
+    x[3, 9] = -1e4                                          # expf underflows to 0 / denormals (config-4 planes)
+    x[3, 14, :8] = -float('inf')
+    x[3, 16, 8:] = -95.0
+    x[3, 17, 4:12] = x[3, 5, 4:12] - 88.5                   # exp(x - m) is a denormal
+    x = torch.cat([x, x[:2] * 1e-6, x[:2] * 300.0])         # tiny logits: every channel a near tie; huge gaps
     x = x.cuda()
     want_conf, want_label = torch_softmax_max(x)
-    for mode in (0, 1, 6, 16, 26, 36, 46):
+    for mode in (0, 1, 6, 16, 26, 36, 46, 51, 56, 66, 76, 80):
         conf, label, _ = o.ias_softmax_hist(x, group_size=2, hist_mode=mode)
         assert torch.equal(conf, want_conf), mode
         assert torch.equal(label.long(), want_label), mode
@@ -133,7 +147,7 @@ def test_config0_vs_oracle():
     logits = torch.cat([lg for lg, _ in batches]).cuda()
     oracle = oias.IASOracle(C, spec['alpha'], spec['beta'], spec['gamma'], spec['cp_gamma'])
     oracle.run([(lg.cuda(), p) for lg, p in batches])
-    for mode in (1, 2, 3, 4, 5, 6, 11, 16, 21, 25, 26, 31, 36, 41, 46):
+    for mode in (1, 2, 3, 4, 5, 6, 11, 16, 21, 25, 26, 31, 36, 41, 46, 51, 56, 61, 66, 71, 76, 80):
         conf, label, hist = o.ias_softmax_hist(logits, group_size=B, hist_mode=mode)
         thr_state = torch.full((C,), 0.9, dtype=torch.float64, device='cuda')
         flag = torch.zeros(1, dtype=torch.int32, device='cuda')
@@ -181,6 +195,31 @@ def test_full_resolution_properties():
     # idempotence: same inputs, same outputs (atomics must not make anything order dependent)
     conf2, label2, hist2 = o.ias_softmax_hist(logits, group_size=B)
     assert torch.equal(hist2, hist_raw) and torch.equal(conf2, conf) and torch.equal(label2, label)
+
+
+@pytest.mark.parametrize('mode', [56, 80])
+def test_full_resolution_hist_variants_match_plain_red(mode):
+    """Full-size maps through the packed-math / group-resident kernels == the plain one-RED-per-pixel kernel, on
+    diffuse, peaked, saturated and CONSTANT maps (one (class, key) bin receives 2M pixels: exercises the 16-bit
+    wrap of the shared-memory table), odd group sizes and a trailing 1-image group."""
+    o = ops()
+    C, H, W = 19, 1024, 2048
+    g = torch.Generator(device='cuda').manual_seed(99)
+    logits = torch.randn(5, C, H, W, generator=g, device='cuda') * 3
+    low = torch.randn(2, C, 32, 64, generator=g, device='cuda')
+    logits[1] = torch.nn.functional.interpolate(low[:1] * 4, size=(H, W), mode='bilinear', align_corners=True)[0] + logits[1] / 6
+    logits[2] = torch.nn.functional.interpolate(low[1:] * 60, size=(H, W), mode='bilinear', align_corners=True)[0] + logits[2] / 6
+    const = torch.linspace(-1.0, 1.0, C, device='cuda')
+    const[7] = 2.0                                             # conf ~ 0.25: a bin of the shared table
+    logits[3] = const[:, None, None]
+    const[7] = -0.4                                            # conf ~ 0.13: a bin below the table (global REDs)
+    logits[4, :, :H // 2] = const[:, None, None]
+    for B in (2, 3):
+        conf, label, hist = o.ias_softmax_hist(logits, group_size=B, hist_mode=mode)
+        conf1, label1, hist1 = o.ias_softmax_hist(logits, group_size=B, hist_mode=1)
+        assert torch.equal(conf, conf1) and torch.equal(label, label1)
+        assert torch.equal(hist, hist1)
+        assert int(hist.sum()) == 5 * H * W
 
 
 def test_empty_and_single_image():
