@@ -236,6 +236,7 @@ def gpu_arm(args):
             torch.cuda.synchronize()
 
     a_events = []
+    fused_used = []
 
     class TimedEngine:
         """Forwards to the engine; brackets every phase-A launch with CUDA events on the launching stream."""
@@ -248,6 +249,16 @@ def gpu_arm(args):
             engine.phase_a(logits, first_image)
             e1.record()
             a_events.append((e0, e1))
+
+        def process_fused(self, logits, first_image=0):      # one rank: A + B + C in one persistent kernel
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            ok = engine.process_fused(logits, first_image)
+            e1.record()
+            if ok:
+                a_events.append((e0, e1))
+                fused_used.append(1)
+            return ok
 
     def run_job(n_steps, timed):
         total_windows = n_steps * world
@@ -293,14 +304,16 @@ def gpu_arm(args):
                        'images_per_step_per_gpu': WINDOW, 'images_total': images, 'alpha': ALPHA, 'beta': BETA,
                        'gamma': GAMMA, 'distribution': args.dist, 'resident_pool_maps': WINDOW,
                        'l2': 'inputs exceed L2 (10.2 GB streamed per step)',
-                       'parallelism': 'windows striped over %d rank(s); 19-double threshold state via NCCL send/recv' % world},
+                       'parallelism': ('one rank: fused A+B+C kernel per window, no collective' if world == 1 else
+                                       'windows striped over %d ranks; 19-double threshold state via NCCL send/recv' % world)},
             'hbm_frac_of_peak': ALG_BYTES_PER_IMAGE * value / world / 1e9 / peak,
-            'roofline': {'kernel': 'k_softmax_hist (phase A)', 'bound': 'hbm', 'achieved': achieved, 'peak': peak,
+            'roofline': {'kernel': 'k_ias_fused (phases A+B+C in one persistent kernel; the events also cover its 4 memsets)'
+                                   if fused_used else 'k_softmax_hist_gr (phase A)', 'bound': 'hbm', 'achieved': achieved, 'peak': peak,
                          'unit': 'GB/s', 'frac': achieved / peak, 'traffic': ncu_traffic(), 'peak_source': peak_src,
                          'algorithmic_bytes_per_launch': ALG_BYTES_PER_IMAGE * WINDOW, 'launch_ms': a_ms,
                          'share_of_step': a_ms / (ms / K)},
             'e2e': e2e,
-            'gpu_launches': 5 * K,
+            'gpu_launches': (2 if fused_used else 5) * K,
             'clocks': clocks,
             'pow_rounding_certified': bool(certified),
         }

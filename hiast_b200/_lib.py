@@ -37,6 +37,9 @@ _SIGNATURES = {
     'hiast_ias_threshold_scan': (_i, [_vp, _i, _i, _i, _d, _d, _d, _vp, _vp, _vp, _vp, _vp]),
     'hiast_ias_select': (_i, [_vp, _vp, _vp, _i, _i64, _i, _i, _vp, _vp, _vp, _vp]),
     'hiast_ias_meanprob_scan': (_i, [_vp, _vp, _i, _i, _i, _i, _d, _vp, _vp]),
+    'hiast_ias_fused_workspace_bytes': (_sz, [_i, _i]),
+    'hiast_ias_fused_window': (_i, [_vp, _i, _i, _i, _i, _i, _i, _d, _d, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                    _vp, _sz, _i, _vp]),
     'hiast_cbst_workspace_bytes': (_sz, [_i, _i64, _i]),
     'hiast_cbst_sample_hist': (_i, [_vp, _vp, _i, _i64, _i, _i, _i, _i, _vp, _vp, _sz, _vp]),
     'hiast_cbst_quantile': (_i, [_vp, _i, _i, _d, _vp, _vp, _vp]),
@@ -47,6 +50,7 @@ _SIGNATURES = {
     'hiast_confusion_matrix': (_i, [_vp, _vp, _i, _i64, _i, _i, _vp, _vp, _vp]),
     'hiast_confusion_from_logits': (_i, [_vp, _vp, _i, _i, _i, _i64, _i, _i, _vp, _vp]),
     'hiast_iou_from_confusion': (_i, [_vp, _i, _vp, _vp, _vp]),
+    'hiast_debug_set_fused_trace': (_i, [_vp]),
     'hiast_selftest_packed_expf': (_i, [_vp, _vp]),
     'hiast_testhook_powi': (_d, [_d, _i]),
     'hiast_testhook_threshold_step': (_d, [_vp, _i, _d, _d, _d, _d, _vp, _vp]),

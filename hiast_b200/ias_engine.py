@@ -23,7 +23,7 @@ from . import ops
 
 class IASEngine:
     def __init__(self, num_classes, height, width, group_size, alpha, beta, gamma, cp_gamma,
-                 max_images, device='cuda', key_lo=None, hist_mode=0):
+                 max_images, device='cuda', key_lo=None, hist_mode=0, fused=False):
         if max_images % group_size:
             raise ValueError('max_images must be a multiple of the group (batch) size')
         self.C, self.H, self.W, self.B = int(num_classes), int(height), int(width), int(group_size)
@@ -46,6 +46,14 @@ class IASEngine:
         self.thr_state = torch.full((c,), 0.9, dtype=torch.float64, device=dev)      # :185
         self.mean_state = torch.zeros(c, dtype=torch.float64, device=dev)            # :21
         self.error_flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        # fused=True sends single-GPU windows through the persistent kernel hiast_ias_fused_window (A + B + C in one
+        # launch, the conf / label spill stays in L2).  It is bit-identical to the three kernels but measured SLOWER
+        # on B200 (2.9 ms against 2.1 ms per 64-image window: every hand-over between units costs a 4-5 us round trip
+        # through a memory system that phase A keeps saturated), so it is off by default.
+        self.fused = bool(fused)
+        self.fused_ws = ops.ias_fused_workspace(n, self.B, dev)
+        self.groups_in_flight = 0
+        self.keep_spill = False
 
     # ------------------------------------------------------------------ phases
     def _groups(self, n_images):
@@ -122,18 +130,35 @@ class IASEngine:
     def process(self, logits, first_image=0):
         """A, B, C and the mean-prob EMA for one window.  Returns views (plbl, counts, thr_groups)."""
         n = logits.shape[0]
-        self.phase_a(logits, first_image)
-        self.phase_b(first_image, n)
-        self.phase_c(first_image, n)
+        if not (self.fused and self.process_fused(logits, first_image)):
+            self.phase_a(logits, first_image)
+            self.phase_b(first_image, n)
+            self.phase_c(first_image, n)
         self.mean_prob(first_image, n)
         g0 = first_image // self.B
         return (self.plbl[first_image:first_image + n], self.counts[first_image:first_image + n],
                 self.thr_groups[g0:g0 + self._groups(n)])
 
+    def process_fused(self, logits, first_image=0):
+        """A + B + C of one window in a single persistent kernel.  False (nothing launched) if the shape is not
+        covered.  self.conf / self.label hold no defined values afterwards."""
+        n = logits.shape[0]
+        if first_image % self.B or first_image + n > self.max_images:
+            raise ValueError('bad window')
+        g0, g = first_image // self.B, self._groups(n)
+        sl = slice(first_image, first_image + n)
+        return ops.ias_fused_window(logits, self.B, self.key_lo, self.alpha, self.beta, self.gamma, self.conf[sl],
+                                    self.label[sl], self.hist[g0:g0 + g], self.thr_state, self.thr_groups[g0:g0 + g],
+                                    self.temp_groups[g0:g0 + g], self.plbl[sl], self.counts[sl], self.confsum[g0:g0 + g],
+                                    self.error_flag, self.fused_ws, keep_spill=self.keep_spill,
+                                    groups_in_flight=self.groups_in_flight)
+
     def check_errors(self):
         """Host sync.  Mirrors numpy's ValueError for a quantile level outside [0,1] (np.quantile, :178).
         Returns True when every threshold is certified independent of the host libm's last-bit pow rounding."""
         flag = int(self.error_flag.item())
+        if flag & 4:
+            raise RuntimeError('hiast_ias_fused_window gave up waiting for a group to close (internal error)')
         if flag & 1:
             raise ValueError('Quantiles must be in the range [0, 1]')
         return not (flag & 2)

@@ -16,7 +16,7 @@ from ._lib import IGNORE, KEY_ONE, REGION, TERM_CE, TERM_CST, TERM_ENT, TERM_KLD
 
 __all__ = [
     'ias_key_lo', 'ias_num_bins', 'ias_row_stride', 'ias_new_hist', 'ias_softmax_hist', 'ias_upsample_softmax_hist', 'ias_conf_hist', 'ias_threshold_scan',
-    'ias_select', 'ias_meanprob_scan', 'cbst_sample_hist', 'cbst_quantile', 'copy_paste', 'hard_lut', 'st_loss_fwd', 'st_loss_bwd',
+    'ias_select', 'ias_meanprob_scan', 'ias_fused_window', 'UNSUPPORTED', 'cbst_sample_hist', 'cbst_quantile', 'copy_paste', 'hard_lut', 'st_loss_fwd', 'st_loss_bwd',
     'confusion_matrix', 'confusion_from_logits', 'iou_from_confusion',
 ]
 
@@ -162,6 +162,46 @@ def ias_select(conf, label, thr_groups, num_classes, group_size, plbl=None, coun
     check(lib().hiast_ias_select(ptr(conf), ptr(label), ptr(thr_groups), n, hw, int(num_classes), int(group_size),
                                  ptr(plbl), ptr(counts), ptr(confsum), stream_ptr(dev)), 'hiast_ias_select')
     return plbl, counts, confsum
+
+
+UNSUPPORTED = -2
+
+
+def ias_fused_window(logits, group_size, key_lo, alpha, beta, gamma, conf, label, hist, thr_state, thr_groups, temp_groups,
+                     plbl, counts, confsum, error_flag, workspace, keep_spill=False, groups_in_flight=0):
+    """Phases A + B + C of a window in one persistent kernel (single GPU).  All buffers are caller-owned CUDA tensors
+    (see include/hiast_b200.h).  Returns False when the shape is not covered by the fused kernel (nothing has been
+    launched then: use the three-kernel path), True otherwise."""
+    require_cuda(logits, torch.float32, 'logits')
+    n, c, h, w = logits.shape
+    require_cuda(conf, torch.float32, 'conf')
+    require_cuda(label, torch.uint8, 'label')
+    require_cuda(hist, torch.int32, 'hist')
+    require_cuda(thr_state, torch.float64, 'thr_state')
+    require_cuda(thr_groups, torch.float64, 'thr_groups')
+    require_cuda(plbl, torch.uint8, 'plbl')
+    require_cuda(counts, torch.int64, 'counts')
+    require_cuda(confsum, torch.int64, 'confsum')
+    require_cuda(error_flag, torch.int32, 'error_flag')
+    require_cuda(workspace, torch.int32, 'workspace')
+    g = _n_groups(n, group_size)
+    assert conf.numel() >= n * h * w and label.numel() >= n * h * w and plbl.numel() >= n * h * w
+    assert hist.numel() >= g * c * ias_row_stride(key_lo) and thr_groups.numel() >= g * c
+    assert counts.numel() >= n * c and confsum.numel() >= g * c
+    flags = (1 if keep_spill else 0) | ((int(groups_in_flight) & 0xf) << 4)
+    status = lib().hiast_ias_fused_window(
+        ptr(logits), n, c, h, w, int(group_size), int(key_lo), float(alpha), float(beta), float(gamma), ptr(conf), ptr(label),
+        ptr(hist), ptr(thr_state), ptr(thr_groups), ptr(temp_groups), ptr(plbl), ptr(counts), ptr(confsum), ptr(error_flag),
+        ptr(workspace), workspace.numel() * 4, flags, stream_ptr(logits.device))
+    if status == UNSUPPORTED:
+        return False
+    check(status, 'hiast_ias_fused_window')
+    return True
+
+
+def ias_fused_workspace(n_images, group_size, device):
+    nbytes = lib().hiast_ias_fused_workspace_bytes(int(n_images), int(group_size))
+    return torch.zeros((nbytes + 3) // 4, dtype=torch.int32, device=device)
 
 
 def ias_meanprob_scan(confsum, counts, group_size, num_classes, cp_gamma, mean_state):

@@ -81,19 +81,32 @@ class ShardedIAS:
         e = self.engine
         wins = self.my_windows
         self._stash = []
-        if wins:
+        # One rank: nothing to wait for, so a window goes through the fused persistent kernel (A + B + C in one launch,
+        # the conf / label spill never leaves L2).  With R > 1 the thresholds of a window arrive from another rank long
+        # after its phase A has run, so the three phases stay separate kernels.
+        fused = self.world == 1 and bool(getattr(e, 'fused', False)) and hasattr(e, 'process_fused')
+        if wins and not fused:
             self._phase_a(wins[0], 0, window_logits)
         for j, w in enumerate(wins):
-            if j + 1 < len(wins):
-                self._phase_a(wins[j + 1], j + 1, window_logits)
             _, n = window_images(w, self.window_size, self.n_total)
             slot = self._slot(j)
-            if w > 0 and self.world > 1:
-                dist.recv(e.thr_state, src=self._global((self.rank - 1) % self.world), group=self.pg)
-            e.phase_b(slot, n)
-            if w < self.n_windows_total - 1 and self.world > 1:
-                dist.send(e.thr_state, dst=self._global((self.rank + 1) % self.world), group=self.pg)
-            e.phase_c(slot, n)
+            if fused:
+                logits = window_logits(w)
+                if logits.shape[0] != n:
+                    raise ValueError('window %d must hold %d images, got %d' % (w, n, logits.shape[0]))
+                if not e.process_fused(logits, slot):
+                    e.phase_a(logits, slot)
+                    e.phase_b(slot, n)
+                    e.phase_c(slot, n)
+            else:
+                if j + 1 < len(wins):
+                    self._phase_a(wins[j + 1], j + 1, window_logits)
+                if w > 0 and self.world > 1:
+                    dist.recv(e.thr_state, src=self._global((self.rank - 1) % self.world), group=self.pg)
+                e.phase_b(slot, n)
+                if w < self.n_windows_total - 1 and self.world > 1:
+                    dist.send(e.thr_state, dst=self._global((self.rank + 1) % self.world), group=self.pg)
+                e.phase_c(slot, n)
             g0, g = slot // e.B, (n + e.B - 1) // e.B
             self._stash.append(torch.stack([e.confsum[g0:g0 + g], e.group_counts(slot, n)], dim=1).clone())
             if on_window is not None:

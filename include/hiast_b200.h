@@ -133,6 +133,25 @@ HIAST_API int hiast_ias_meanprob_scan(const uint64_t* confsum, const int64_t* co
                             int n_images, int group_size, int n_groups, int C, double cp_gamma,
                             double* mean_state, void* stream);
 
+/* a1-a7 in ONE launch for a window of images on a single GPU (the whole loop body of
+ * IASPseudoGenerator.run, :190-211, for n_images / group_size consecutive batches):
+ * phase A, the threshold chain and phase C run in one persistent kernel; the conf / label spill stays in L2
+ * (conf_scratch f32 [n,HW] / label_scratch u8 [n,HW] hold NO defined values afterwards).  Results are
+ * bit-identical to hiast_ias_softmax_hist + hiast_ias_threshold_scan + hiast_ias_select:
+ *   thr_state (in/out), thr_groups, temp_groups (may be NULL), plbl (hist is scratch: raw counts on return),
+ *   counts i64 [n,C] and confsum u64 [G,C] (both OVERWRITTEN here, not accumulated), *error_flag |= 1 / 2 as in
+ *   hiast_ias_threshold_scan, |= 4 if the kernel gave up waiting (internal error).
+ * workspace: hiast_ias_fused_workspace_bytes.  flags: bit 0 = keep the spill lines (no discard.global.L2);
+ * bits 4..7 = groups in flight (0 = default 2).  Returns HIAST_ERR_UNSUPPORTED for shapes the fused kernel
+ * does not cover (C not in {16, 19}, HW % 4 != 0, unaligned buffers): use the three calls above.          */
+HIAST_API size_t hiast_ias_fused_workspace_bytes(int n_images, int group_size);
+HIAST_API int hiast_ias_fused_window(const float* logits, int n_images, int C, int H, int W, int group_size,
+                           int key_lo, double alpha, double beta, double gamma,
+                           float* conf_scratch, uint8_t* label_scratch, uint32_t* hist,
+                           double* thr_state, double* thr_groups, float* temp_groups,
+                           uint8_t* plbl, int64_t* counts, uint64_t* confsum, int* error_flag,
+                           void* workspace, size_t workspace_bytes, int flags, void* stream);
+
 /* CBST policy (8f rank 3)  :142-165.  Adds to hist u32 [C][row_stride] (one histogram for the whole data set,
  * accumulated over calls) the fp16 keys of the pixels whose rank among the pixels of their class, in raster
  * order over the images of their batch (group), is a multiple of sample_interval.  workspace: see
@@ -201,6 +220,12 @@ HIAST_API double hiast_testhook_powi(double x, int n);
 HIAST_API double hiast_testhook_threshold_step(const uint32_t* prefix_row_host, int key_lo,
                                      double thr, double alpha, double beta, double gamma,
                                      float* temp_out, int* error_out);
+
+/* ---- development hooks -------------------------------------------------------------------- */
+/* Per-unit timeline of the next hiast_ias_fused_window launches: dev_buffer = u64 [n_SMs][256][6]
+ * (kind << 32 | unit, begin, end, closer: wait begin, wait end, published; %globaltimer ns), zeroed by the caller;
+ * NULL switches tracing off.                                                                   */
+HIAST_API int hiast_debug_set_fused_trace(void* dev_buffer);
 
 /* ---- device-side self test (needs a GPU; used by tests only) ---------------------------- */
 /* Sweeps EVERY non-positive float (bit patterns 0x80000000..0xFF800000 and +0) through the packed

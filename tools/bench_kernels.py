@@ -118,6 +118,19 @@ def main():
         ms = timeit(lambda: ops.ias_select(conf, label, thr_groups, C, B, plbl, counts, confsum))
         res['C_%s' % dist] = dict(ms=ms, gbs=n * H * W * 6 / ms / 1e6, kept=float((plbl != 255).float().mean()),
                                   top_bin=float((conf >= 0.99976).float().mean()))
+        from hiast_b200.ias_engine import IASEngine
+        eng = IASEngine(C, H, W, B, 0.5, 0.9, 8.0, 0.99, n, fused=True)
+        fv = {}
+        for gif in (2, 4):
+            for keep in (False,):
+                def f(gif=gif, keep=keep):
+                    eng.groups_in_flight, eng.keep_spill = gif, keep
+                    eng.process_fused(logits)
+                fv['gif%d%s' % (gif, '_keep' if keep else '')] = f
+        for name, ms in time_variants(fv, rounds=4, inner=2).items():
+            res['fused_%s_%s' % (dist, name)] = dict(ms=ms, img_s=n / ms * 1e3, frac=alg_a / ms / 1e6 / (PEAK / 1e9))
+        assert eng.check_errors() is not None
+        del eng
         tot = min(res['A_%s_mode%d' % (dist, m)]['ms'] for m in (36, 56, 80)) + res['B_%s' % dist]['ms'] + res['C_%s' % dist]['ms']
         res['pipeline_%s' % dist] = dict(ms=tot, img_s=n / tot * 1e3, frac=alg_a / tot / 1e6 / (PEAK / 1e9))
         # torch reference chain for context (what the reference launches on the GPU for a1 only)
