@@ -282,7 +282,7 @@ struct LossStage {
 
 template <int C>
 __global__ void __launch_bounds__(kThreadsL, 2) k_loss_fwd(LossArgs a, Partial* __restrict__ partials) {
-  extern __shared__ __align__(16) float2 s_loss_stage[];
+  extern __shared__ __align__(128) float2 s_loss_stage[];
   const LossStage<C> st(s_loss_stage, a);
   const long long total = static_cast<long long>(a.B) * st.HW2;
   const long long stride = static_cast<long long>(gridDim.x) * kThreadsL;
@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(kThreadsL, 2) k_loss_fwd(LossArgs a, Partial* 
 template <int C>
 __global__ void __launch_bounds__(kThreadsL, 2) k_loss_bwd(LossArgs a, const float* __restrict__ scales,
                                                            float* __restrict__ grad) {
-  extern __shared__ __align__(16) float2 s_loss_stage[];
+  extern __shared__ __align__(128) float2 s_loss_stage[];
   const LossStage<C> st(s_loss_stage, a);
   const long long total = static_cast<long long>(a.B) * st.HW2;
   const long long stride = static_cast<long long>(gridDim.x) * kThreadsL;

@@ -29,7 +29,7 @@ def torch_softmax_max(logits):
 
 
 @pytest.mark.parametrize('shape', [(2, 19, 64, 128), (3, 19, 33, 52), (1, 16, 40, 64), (2, 7, 31, 51), (1, 40, 9, 13)])
-@pytest.mark.parametrize('mode', [1, 2, 3, 4, 5, 6, 11, 16, 21, 25, 26, 31, 36, 41, 46, 51, 56, 61, 66, 71, 76, 80])
+@pytest.mark.parametrize('mode', [1, 2, 3, 4, 5, 6, 11, 16, 21, 25, 26, 31, 36, 41, 46, 51, 56, 61, 66, 71, 76, 80, 81, 83])
 def test_phase_a_bit_exact_vs_torch_cuda(shape, mode):
     o = ops()
     g = torch.Generator().manual_seed(sum(shape) + mode)
@@ -79,7 +79,7 @@ def test_phase_a_ties_and_near_ties():
     x = torch.cat([x, x[:2] * 1e-6, x[:2] * 300.0])         # tiny logits: every channel a near tie; huge gaps
     x = x.cuda()
     want_conf, want_label = torch_softmax_max(x)
-    for mode in (0, 1, 6, 16, 26, 36, 46, 51, 56, 66, 76, 80):
+    for mode in (0, 1, 6, 16, 26, 36, 46, 51, 56, 66, 76, 80, 81, 83):
         conf, label, _ = o.ias_softmax_hist(x, group_size=2, hist_mode=mode)
         assert torch.equal(conf, want_conf), mode
         assert torch.equal(label.long(), want_label), mode
@@ -147,7 +147,7 @@ def test_config0_vs_oracle():
     logits = torch.cat([lg for lg, _ in batches]).cuda()
     oracle = oias.IASOracle(C, spec['alpha'], spec['beta'], spec['gamma'], spec['cp_gamma'])
     oracle.run([(lg.cuda(), p) for lg, p in batches])
-    for mode in (1, 2, 3, 4, 5, 6, 11, 16, 21, 25, 26, 31, 36, 41, 46, 51, 56, 61, 66, 71, 76, 80):
+    for mode in (1, 2, 3, 4, 5, 6, 11, 16, 21, 25, 26, 31, 36, 41, 46, 51, 56, 61, 66, 71, 76, 80, 81, 83):
         conf, label, hist = o.ias_softmax_hist(logits, group_size=B, hist_mode=mode)
         thr_state = torch.full((C,), 0.9, dtype=torch.float64, device='cuda')
         flag = torch.zeros(1, dtype=torch.int32, device='cuda')
@@ -197,7 +197,7 @@ def test_full_resolution_properties():
     assert torch.equal(hist2, hist_raw) and torch.equal(conf2, conf) and torch.equal(label2, label)
 
 
-@pytest.mark.parametrize('mode', [56, 80])
+@pytest.mark.parametrize('mode', [56, 80, 81, 83])
 def test_full_resolution_hist_variants_match_plain_red(mode):
     """Full-size maps through the packed-math / group-resident kernels == the plain one-RED-per-pixel kernel, on
     diffuse, peaked, saturated and CONSTANT maps (one (class, key) bin receives 2M pixels: exercises the 16-bit
