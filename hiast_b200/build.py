@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libhiast_b200.so')
 SOURCES = ['api.cu', 'ias.cu', 'cbst.cu', 'loss.cu', 'confusion.cu', 'copy_paste.cu']
-HEADERS = ['common.cuh', 'scan_math.h', os.path.join('..', '..', 'include', 'hiast_b200.h')]
+HEADERS = ['common.cuh', 'packed_math.cuh', 'scan_math.h', os.path.join('..', '..', 'include', 'hiast_b200.h')]
 
 NVCC_FLAGS = [
     '-O3', '-std=c++17',

@@ -20,6 +20,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "packed_math.cuh"
 
 namespace hiast {
 
@@ -44,6 +45,12 @@ __device__ __forceinline__ int load_label(const void* p, int bytes, size_t i) {
   if (bytes == 1) return static_cast<const uint8_t*>(p)[i];
   const long long v = static_cast<const long long*>(p)[i];
   return (v < 0 || v > 255) ? 256 : static_cast<int>(v);  // 256 = out of range, not ignore
+}
+
+// labels of the pixel pair at element position lp (even): issued one iteration ahead so that the load is never waited for
+__device__ __forceinline__ void load_label_pair(const void* p, int bytes, size_t lp, int& ya, int& yb) {
+  ya = load_label(p, bytes, lp);
+  yb = load_label(p, bytes, lp + 1);
 }
 
 __device__ __forceinline__ bool in_region(int region, bool ignored) {
@@ -256,6 +263,48 @@ struct LossStage {
   }
   __device__ __forceinline__ void wait() const { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
+  // Split pipeline of the packed kernels: z and t travel in separate cp.async groups so that t never has to live in
+  // registers -- it is read from the staging slots channel by channel after the first (z-only) pass and its slots
+  // are refilled after the last pass.  wait_older() = every group but the most recent one has landed.
+  __device__ __forceinline__ void prefetch_z(long long i) const {
+    const int b = static_cast<int>(i / HW2);
+    const int64_t p2 = i - static_cast<long long>(b) * HW2;
+    const float2* zs = reinterpret_cast<const float2*>(a.z + static_cast<size_t>(b) * C * a.HW) + p2;
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(my_u32 + c * kThreadsL * 8),
+                   "l"(zs + static_cast<size_t>(c) * HW2) : "memory");
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  }
+  __device__ __forceinline__ void prefetch_t(long long i) const {
+    if (need_t) {
+      const int b = static_cast<int>(i / HW2);
+      const int64_t p2 = i - static_cast<long long>(b) * HW2;
+      const float2* ts = reinterpret_cast<const float2*>(a.t + static_cast<size_t>(b) * C * a.HW) + p2;
+#pragma unroll
+      for (int c = 0; c < C; ++c)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(my_u32 + (C + c) * kThreadsL * 8),
+                     "l"(ts + static_cast<size_t>(c) * HW2) : "memory");
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");   // an empty group keeps the group count uniform
+  }
+  __device__ __forceinline__ void wait_older() const { asm volatile("cp.async.wait_group 1;\n" ::: "memory"); }
+  __device__ __forceinline__ float load_z(float (&z)[kPxL][C]) const {
+    float guard = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float2 q = my[c * kThreadsL];
+      z[0][c] = q.x; z[1][c] = q.y;
+      guard = fmaxf(guard, q.x);
+    }
+    return guard;
+  }
+  __device__ __forceinline__ pk::u64 t2(int c) const {
+    if (!need_t) return 0ull;
+    const float2 q = my[(C + c) * kThreadsL];
+    return pk::pack(q.x, q.y);
+  }
+
   // registers <- shared; returns a value that depends on every load so that the refill can be ordered after it
   __device__ __forceinline__ float load(float (&z)[kPxL][C], float (&t)[kPxL][C]) const {
     float guard = 0.f;
@@ -338,6 +387,250 @@ __global__ void __launch_bounds__(kThreadsL, 2) k_loss_bwd(LossArgs a, const flo
              make_float2(px0.grad(c, z[0][c], t[0][c]) + poison, px1.grad(c, z[1][c], t[1][c]) + poison));
     st.wait();
   }
+}
+
+// ---- packed-pair kernels (consistency kind SoftCE, the HIAST configuration) --------------------------------------------
+// The scalar kernels above spend 1232 (backward) instructions per pixel -- up to three accurate expf per channel -- and
+// are issue-bound at 60 % of the HBM roofline.  Here the two pixels of a thread go through the f32x2 forms (packed_math.cuh):
+// the exponentials of a pass are recomputed instead of kept (registers hold z and t of both pixels), log-softmax keeps
+// ATen's operation sequence ((z - m) - log(sum), sum in channel order) so that the data-dependent SoftCE divisor
+// #(prod != 0) stays exact, and the count of non-zero products is C unless min_c |prod_c| == 0 (then it is recounted).
+template <int C>
+struct PairLS {
+  float ma, mb, sa, sb;
+  pk::u64 negm, logs2, inv2;
+  __device__ __forceinline__ void init(const float (&za)[C], const float (&zb)[C]) {
+    ma = za[0];
+    mb = zb[0];
+#pragma unroll
+    for (int c = 1; c < C; ++c) {
+      ma = fmaxf(ma, za[c]);
+      mb = fmaxf(mb, zb[c]);
+    }
+    negm = pk::pack(-ma, -mb);
+    pk::u64 s2 = 0;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const pk::u64 e2 = pk::exp2x(pk::add2(pk::pack(za[c], zb[c]), negm));
+      s2 = (c == 0) ? e2 : pk::add2(s2, e2);
+    }
+    pk::unpack(s2, sa, sb);
+    logs2 = pk::pack(logf(sa), logf(sb));
+    inv2 = pk::pack(1.0f / sa, 1.0f / sb);
+  }
+  __device__ __forceinline__ pk::u64 d(float a, float b) const { return pk::add2(pk::pack(a, b), negm); }
+};
+
+// lanes of a packed pair kept (mask all ones) or replaced by +0.0f (mask 0)
+__device__ __forceinline__ pk::u64 lane_mask(bool a, bool b) {
+  return (a ? 0x00000000ffffffffull : 0ull) | (b ? 0xffffffff00000000ull : 0ull);
+}
+
+// rare path: some -logp * t of the pixel at (b, p) is exactly zero; count the non-zero ones from global memory
+// (the registers and the staging slots have moved on)
+template <int C>
+__device__ __noinline__ int recount_nonzero(const LossArgs& a, int b, int64_t p, float m, float logs) {
+  int nz = 0;
+  for (int c = 0; c < C; ++c) {
+    const size_t i = (static_cast<size_t>(b) * C + c) * a.HW + p;
+    nz += (__fmul_rn(-((a.z[i] - m) - logs), a.t[i]) != 0.f);
+  }
+  return nz;
+}
+
+template <int C>
+__device__ __forceinline__ float pair_forward_softce(const float (&za)[C], const float (&zb)[C], const LossStage<C>& st,
+                                                    int ya, int yb, int region, int terms, const LossArgs& a, int b,
+                                                    int64_t p0, PixelSums& acc) {
+  PairLS<C> ls;
+  ls.init(za, zb);
+  st.wait_older();   // this pair's teacher probabilities have landed in the staging slots
+  const bool iga = (ya == HIAST_IGNORE_LABEL), igb = (yb == HIAST_IGNORE_LABEL);
+  acc.n_ign += static_cast<int>(iga) + static_cast<int>(igb);
+  acc.n_conf += static_cast<int>(!iga) + static_cast<int>(!igb);
+  const bool want_ent = (terms & HIAST_TERM_ENT) && (iga || igb);
+  const bool want_cst = (terms & HIAST_TERM_CST) != 0;
+  pk::u64 sl2 = 0, h2 = 0, sc2 = 0;
+  float lpya = 0.f, lpyb = 0.f, mna = INFINITY, mnb = INFINITY;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    const pk::u64 d2 = ls.d(za[c], zb[c]);
+    const pk::u64 lp2 = pk::sub2(d2, ls.logs2);
+    sl2 = (c == 0) ? lp2 : pk::add2(sl2, lp2);
+    float lpa, lpb;
+    pk::unpack(lp2, lpa, lpb);
+    lpya = (c == ya) ? lpa : lpya;
+    lpyb = (c == yb) ? lpb : lpyb;
+    if (want_ent) h2 = pk::fma2(pk::mul2(pk::exp2x(d2), ls.inv2), lp2, h2);
+    if (want_cst) {
+      const pk::u64 pr2 = pk::mul2(lp2, st.t2(c));   // = -(-lp * t), same magnitude and zero-ness
+      sc2 = (c == 0) ? pr2 : pk::add2(sc2, pr2);
+      float pa, pb;
+      pk::unpack(pr2, pa, pb);
+      mna = fminf(mna, fabsf(pa));
+      mnb = fminf(mnb, fabsf(pb));
+    }
+  }
+  float sla, slb, ha, hb, sca, scb;
+  pk::unpack(sl2, sla, slb);
+  pk::unpack(h2, ha, hb);
+  pk::unpack(sc2, sca, scb);
+  auto finish = [&](bool ign, int64_t p, float m, float logs, float lpy, float sl, float h, float sc, float mn) {
+    if (!ign) {
+      if (terms & HIAST_TERM_CE) acc.ce += static_cast<double>(-lpy);
+      if (terms & HIAST_TERM_KLD) acc.kld += static_cast<double>(-sl * (1.0f / C));
+    } else if (terms & HIAST_TERM_ENT) {
+      acc.ent += static_cast<double>(-h);
+    }
+    if (want_cst && in_region(region, ign)) {
+      acc.cst += static_cast<double>(-sc);
+      acc.n_nz += (mn > 0.f) ? C : recount_nonzero<C>(a, b, p, m, logs);   // a zero (or NaN) product: count the slow way
+    }
+  };
+  float logsa, logsb;
+  pk::unpack(ls.logs2, logsa, logsb);
+  finish(iga, p0, ls.ma, logsa, lpya, sla, ha, sca, mna);
+  finish(igb, p0 + 1, ls.mb, logsb, lpyb, slb, hb, scb, mnb);
+  return fminf(mna, mnb);   // never NaN; depends on every read of the t slots (they may be refilled once it is known)
+}
+
+template <int C>
+__global__ void __launch_bounds__(kThreadsL, 2) k_loss_fwd_pk(LossArgs a, Partial* __restrict__ partials) {
+  extern __shared__ __align__(128) float2 s_loss_stage[];
+  const LossStage<C> st(s_loss_stage, a);
+  const long long total = static_cast<long long>(a.B) * st.HW2;
+  const long long stride = static_cast<long long>(gridDim.x) * kThreadsL;
+  PixelSums acc = {0.0, 0.0, 0.0, 0.0, 0, 0, 0};
+  long long i = static_cast<long long>(blockIdx.x) * kThreadsL + threadIdx.x;
+  auto label_pos = [&](long long idx) {
+    const int bb = static_cast<int>(idx / st.HW2);
+    return static_cast<size_t>(bb) * a.HW + (idx - static_cast<long long>(bb) * st.HW2) * kPxL;
+  };
+  int ya = 0, yb = 0;
+  if (i < total) {
+    st.prefetch_z(i);
+    st.prefetch_t(i);
+    load_label_pair(a.plbl, a.plbl_bytes, label_pos(i), ya, yb);
+  }
+  for (; i < total; i += stride) {
+    st.wait_older();                       // z of this pair (its t may still be in flight)
+    float z[kPxL][C];
+    const float guard = st.load_z(z);
+    const bool more = i + stride < total;
+    int nya = 0, nyb = 0;
+    if (more && guard == guard) {
+      st.prefetch_z(i + stride);
+      load_label_pair(a.plbl, a.plbl_bytes, label_pos(i + stride), nya, nyb);
+    } else {
+      asm volatile("cp.async.commit_group;\n" ::: "memory");
+    }
+    const int b = static_cast<int>(i / st.HW2);
+    const float tguard = pair_forward_softce<C>(z[0], z[1], st, ya, yb, a.region, a.terms, a, b,
+                                                (i - static_cast<long long>(b) * st.HW2) * kPxL, acc);
+    if (more && tguard == tguard) st.prefetch_t(i + stride);
+    else asm volatile("cp.async.commit_group;\n" ::: "memory");
+    ya = nya;
+    yb = nyb;
+  }
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+  block_reduce_store(acc, partials);
+}
+
+template <int C>
+__global__ void __launch_bounds__(kThreadsL, 2) k_loss_bwd_pk(LossArgs a, const float* __restrict__ scales,
+                                                              float* __restrict__ grad) {
+  extern __shared__ __align__(128) float2 s_loss_stage[];
+  const LossStage<C> st(s_loss_stage, a);
+  const long long total = static_cast<long long>(a.B) * st.HW2;
+  const long long stride = static_cast<long long>(gridDim.x) * kThreadsL;
+  const float sc[4] = {scales[0], scales[1], scales[2], scales[3]};
+  float poison = 0.f;   // NaN iff an enabled scale is non-finite (empty region in the reference: every gradient is NaN)
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (a.terms & (1 << k)) poison += 0.f * sc[k];
+  const pk::u64 poison2 = pk::splat(poison);
+  const float s_ce = (a.terms & HIAST_TERM_CE) ? sc[0] : 0.f;
+  const float s_kld = (a.terms & HIAST_TERM_KLD) ? sc[1] : 0.f;
+  const float s_ent = (a.terms & HIAST_TERM_ENT) ? sc[2] : 0.f;
+  const float s_cst = (a.terms & HIAST_TERM_CST) ? sc[3] : 0.f;
+  long long i = static_cast<long long>(blockIdx.x) * kThreadsL + threadIdx.x;
+  auto label_pos = [&](long long idx) {
+    const int bb = static_cast<int>(idx / st.HW2);
+    return static_cast<size_t>(bb) * a.HW + (idx - static_cast<long long>(bb) * st.HW2) * kPxL;
+  };
+  int ya = 0, yb = 0;
+  if (i < total) {
+    st.prefetch_z(i);
+    st.prefetch_t(i);
+    load_label_pair(a.plbl, a.plbl_bytes, label_pos(i), ya, yb);
+  }
+  for (; i < total; i += stride) {
+    st.wait_older();                       // z of this pair
+    float z[kPxL][C];
+    const float guard = st.load_z(z);
+    const bool more = i + stride < total;
+    int nya = 0, nyb = 0;
+    if (more && guard == guard) {
+      st.prefetch_z(i + stride);
+      load_label_pair(a.plbl, a.plbl_bytes, label_pos(i + stride), nya, nyb);
+    } else {
+      asm volatile("cp.async.commit_group;\n" ::: "memory");
+    }
+    const int b = static_cast<int>(i / st.HW2);
+    const int64_t p2i = i - static_cast<long long>(b) * st.HW2;
+    const bool iga = (ya == HIAST_IGNORE_LABEL), igb = (yb == HIAST_IGNORE_LABEL);
+    PairLS<C> ls;
+    ls.init(z[0], z[1]);
+    // per-lane coefficients:  g = A p + K - [c == y] ce - ENT p (lp - h) - CST (t - p T)
+    const bool csa = (a.terms & HIAST_TERM_CST) && in_region(a.region, iga);
+    const bool csb = (a.terms & HIAST_TERM_CST) && in_region(a.region, igb);
+    const pk::u64 A2 = pk::pack(iga ? 0.f : s_ce + s_kld, igb ? 0.f : s_ce + s_kld);
+    const pk::u64 K2 = pk::pack(iga ? 0.f : -(s_kld * (1.0f / C)), igb ? 0.f : -(s_kld * (1.0f / C)));
+    const pk::u64 NE2 = pk::pack(iga ? -s_ent : 0.f, igb ? -s_ent : 0.f);
+    const pk::u64 NC2 = pk::pack(csa ? -s_cst : 0.f, csb ? -s_cst : 0.f);
+    const float cea = iga ? 0.f : s_ce, ceb = igb ? 0.f : s_ce;
+    const pk::u64 ign_mask = lane_mask(iga, igb);
+    pk::u64 h2 = 0, T2 = 0;
+    if ((a.terms & HIAST_TERM_ENT) && (iga || igb)) {
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const pk::u64 d2 = ls.d(z[0][c], z[1][c]);
+        const pk::u64 lpm2 = pk::sub2(d2, ls.logs2) & ign_mask;    // confident lanes contribute p * 0
+        h2 = pk::fma2(pk::mul2(pk::exp2x(d2), ls.inv2), lpm2, h2);
+      }
+    }
+    st.wait_older();                       // this pair's teacher probabilities
+    if (csa || csb) {
+#pragma unroll
+      for (int c = 0; c < C; ++c) T2 = (c == 0) ? st.t2(c) : pk::add2(T2, st.t2(c));
+    }
+    const pk::u64 NT2 = T2 ^ 0x8000000080000000ull;
+    float2* gs = reinterpret_cast<float2*>(grad + static_cast<size_t>(b) * C * a.HW) + p2i;
+    float tguard = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const pk::u64 d2 = ls.d(z[0][c], z[1][c]);
+      const pk::u64 p2 = pk::mul2(pk::exp2x(d2), ls.inv2);
+      const pk::u64 lpm2 = pk::sub2(d2, ls.logs2) & ign_mask;
+      const pk::u64 t2 = st.t2(c);
+      pk::u64 g2 = pk::fma2(p2, A2, K2);
+      g2 = pk::fma2(pk::mul2(p2, pk::sub2(lpm2, h2)), NE2, g2);      // - ent p (lp - h)   (0 on confident lanes)
+      g2 = pk::fma2(pk::fma2(p2, NT2, t2), NC2, g2);                  // - cst (t - p T)
+      g2 = pk::add2(g2, poison2);
+      float ga, gb, t0, t1;
+      pk::unpack(g2, ga, gb);
+      pk::unpack(t2, t0, t1);
+      tguard = fmaxf(tguard, t0);
+      if (c == ya) ga -= cea;
+      if (c == yb) gb -= ceb;
+      __stcs(gs + static_cast<size_t>(c) * st.HW2, make_float2(ga, gb));
+    }
+    if (more && tguard == tguard) st.prefetch_t(i + stride);          // the t slots have been read
+    else asm volatile("cp.async.commit_group;\n" ::: "memory");
+    ya = nya;
+    yb = nyb;
+  }
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
 }
 
 // Generic path: runtime C <= 255, any HW; channel column re-read through L1.
@@ -518,17 +811,29 @@ cudaError_t loss_configure_smem(int C, size_t smem) {
   if (C == 19) {
     e = cudaFuncSetAttribute(k_loss_fwd<19>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_loss_bwd<19>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_loss_fwd_pk<19>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_loss_bwd_pk<19>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   } else {
     e = cudaFuncSetAttribute(k_loss_fwd<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_loss_bwd<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_loss_fwd_pk<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_loss_bwd_pk<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   }
   done = (e == cudaSuccess);
   return e;
 }
 
+inline int cst_kind_host(int terms) { return terms & HIAST_CST_SOFTCE_LOGITS; }
+bool g_loss_scalar = false;   // development switch: force the scalar vector kernels (hiast_debug_loss_scalar)
+
 }  // namespace hiast
 
 using namespace hiast;
+
+extern "C" int hiast_debug_loss_scalar(int on) {
+  g_loss_scalar = on != 0;
+  return HIAST_OK;
+}
 
 extern "C" size_t hiast_st_loss_workspace_bytes(int B, int C, int64_t HW) {
   (void)C;
@@ -562,8 +867,14 @@ extern "C" int hiast_st_loss_fwd(const float* z, const float* t, const void* plb
     grid = std::min(grid, sm_count() * 2);   // persistent: one resident wave, every thread pipelines its own sequence
     const size_t smem = loss_stage_bytes(C);
     HIAST_CUDA_TRY(loss_configure_smem(C, smem));
-    if (C == 19) k_loss_fwd<19><<<grid, kThreadsL, smem, st>>>(a, parts);
-    else k_loss_fwd<16><<<grid, kThreadsL, smem, st>>>(a, parts);
+    const bool packed = cst_kind_host(terms) == HIAST_CST_SOFTCE && !g_loss_scalar;
+    if (packed) {
+      if (C == 19) k_loss_fwd_pk<19><<<grid, kThreadsL, smem, st>>>(a, parts);
+      else k_loss_fwd_pk<16><<<grid, kThreadsL, smem, st>>>(a, parts);
+    } else {
+      if (C == 19) k_loss_fwd<19><<<grid, kThreadsL, smem, st>>>(a, parts);
+      else k_loss_fwd<16><<<grid, kThreadsL, smem, st>>>(a, parts);
+    }
   } else {
     k_loss_fwd_generic<<<grid, kThreadsL, 0, st>>>(a, parts);
   }
@@ -586,8 +897,14 @@ extern "C" int hiast_st_loss_bwd(const float* z, const float* t, const void* plb
     grid = std::min(grid, sm_count() * 2);
     const size_t smem = loss_stage_bytes(C);
     HIAST_CUDA_TRY(loss_configure_smem(C, smem));
-    if (C == 19) k_loss_bwd<19><<<grid, kThreadsL, smem, st>>>(a, scales, grad_z);
-    else k_loss_bwd<16><<<grid, kThreadsL, smem, st>>>(a, scales, grad_z);
+    const bool packed = cst_kind_host(terms) == HIAST_CST_SOFTCE && !g_loss_scalar;
+    if (packed) {
+      if (C == 19) k_loss_bwd_pk<19><<<grid, kThreadsL, smem, st>>>(a, scales, grad_z);
+      else k_loss_bwd_pk<16><<<grid, kThreadsL, smem, st>>>(a, scales, grad_z);
+    } else {
+      if (C == 19) k_loss_bwd<19><<<grid, kThreadsL, smem, st>>>(a, scales, grad_z);
+      else k_loss_bwd<16><<<grid, kThreadsL, smem, st>>>(a, scales, grad_z);
+    }
   } else {
     k_loss_bwd_generic<<<grid, kThreadsL, 0, st>>>(a, scales, grad_z);
   }

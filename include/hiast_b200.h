@@ -226,6 +226,9 @@ HIAST_API double hiast_testhook_threshold_step(const uint32_t* prefix_row_host, 
  * (kind << 32 | unit, begin, end, closer: wait begin, wait end, published; %globaltimer ns), zeroed by the caller;
  * NULL switches tracing off.                                                                   */
 HIAST_API int hiast_debug_set_fused_trace(void* dev_buffer);
+/* on != 0: hiast_st_loss_fwd / _bwd use the scalar vector kernels instead of the packed-pair (f32x2) ones for
+ * the SoftCE consistency kind (A/B measurements and cross-checks).                               */
+HIAST_API int hiast_debug_loss_scalar(int on);
 
 /* ---- device-side self test (needs a GPU; used by tests only) ---------------------------- */
 /* Sweeps EVERY non-positive float (bit patterns 0x80000000..0xFF800000 and +0) through the packed

@@ -223,3 +223,31 @@ def test_softce_from_teacher_logits_equals_softce_of_softmax():
         b.backward()
         np.testing.assert_allclose(a.item(), b.item(), rtol=RTOL)
         grad_close(z1.grad, z2.grad)
+
+
+@pytest.mark.parametrize('region', ['ignored', 'confident', 'all'])
+def test_packed_pair_kernels_equal_scalar_kernels(region):
+    """The f32x2 kernels (SoftCE kind) against the scalar vector kernels: integer counts identical, sums / gradients to
+    float rounding.  Teacher probabilities with exact zeros exercise the recount of the non-zero-product divisor."""
+    from hiast_b200 import _lib, ops
+    g = torch.Generator().manual_seed(11)
+    z = (torch.randn(2, 19, 96, 160, generator=g) * 3).cuda()
+    z[0, 3, :8] = -1e4                                       # expf underflow lanes
+    t = torch.softmax(torch.randn(2, 19, 96, 160, generator=g) * 40, dim=1).cuda()      # many exact zeros
+    plbl = torch.randint(0, 19, (2, 96, 160), generator=g)
+    plbl[torch.rand(2, 96, 160, generator=g) < 0.5] = 255
+    plbl = plbl.cuda()
+    scales = torch.tensor([0.3, 0.02, 0.7, 0.11], device='cuda')
+    res = {}
+    for scalar in (1, 0):
+        _lib.lib().hiast_debug_loss_scalar(scalar)
+        try:
+            sums, counts = ops.st_loss_fwd(z, t, plbl, region)
+            grad = ops.st_loss_bwd(z, t, plbl, scales, region)
+        finally:
+            _lib.lib().hiast_debug_loss_scalar(0)
+        res[scalar] = (sums.cpu().numpy(), counts.cpu().numpy(), grad)
+    assert np.array_equal(res[0][1], res[1][1])
+    np.testing.assert_allclose(res[0][0], res[1][0], rtol=1e-6)
+    assert int(res[0][1][2]) < (plbl.numel() * 19)           # zeros were really present
+    grad_close(res[0][2], res[1][2])

@@ -175,7 +175,14 @@ def main():
     ms_f = timeit(lambda: ops.st_loss_fwd(z, t, plbl, 'ignored'), iters=10)
     ms_b = timeit(lambda: ops.st_loss_bwd(z, t, plbl, scales, 'ignored', grad=grad), iters=10)
     res['loss'] = dict(ms_fwd_bwd_cold=ms_all - ms_flush, ms_fwd_warm=ms_f, ms_bwd_warm=ms_b,
-                       gbs_cold=px * (160 + 236) / (ms_all - ms_flush) / 1e6)
+                       gbs_cold=px * (160 + 236) / (ms_all - ms_flush) / 1e6,
+                       fwd_gbs=px * 160 / ms_f / 1e6, bwd_gbs=px * 236 / ms_b / 1e6)
+    from hiast_b200 import _lib
+    _lib.lib().hiast_debug_loss_scalar(1)
+    ms_f = timeit(lambda: ops.st_loss_fwd(z, t, plbl, 'ignored'), iters=10)
+    ms_b = timeit(lambda: ops.st_loss_bwd(z, t, plbl, scales, 'ignored', grad=grad), iters=10)
+    _lib.lib().hiast_debug_loss_scalar(0)
+    res['loss_scalar_kernels'] = dict(ms_fwd_warm=ms_f, ms_bwd_warm=ms_b, fwd_gbs=px * 160 / ms_f / 1e6, bwd_gbs=px * 236 / ms_b / 1e6)
     # confusion, int64 2x1024x2048
     pred = torch.randint(0, 19, (8, 1024, 2048), device='cuda')
     tgt = torch.randint(0, 19, (8, 1024, 2048), device='cuda')
