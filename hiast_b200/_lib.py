@@ -52,6 +52,7 @@ _SIGNATURES = {
     'hiast_iou_from_confusion': (_i, [_vp, _i, _vp, _vp, _vp]),
     'hiast_debug_set_fused_trace': (_i, [_vp]),
     'hiast_debug_loss_scalar': (_i, [_i]),
+    'hiast_debug_upsample_v1': (_i, [_i]),
     'hiast_selftest_packed_expf': (_i, [_vp, _vp]),
     'hiast_testhook_powi': (_d, [_d, _i]),
     'hiast_testhook_threshold_step': (_d, [_vp, _i, _d, _d, _d, _d, _vp, _vp]),

@@ -229,6 +229,8 @@ HIAST_API int hiast_debug_set_fused_trace(void* dev_buffer);
 /* on != 0: hiast_st_loss_fwd / _bwd use the scalar vector kernels instead of the packed-pair (f32x2) ones for
  * the SoftCE consistency kind (A/B measurements and cross-checks).                               */
 HIAST_API int hiast_debug_loss_scalar(int on);
+/* on != 0: hiast_ias_upsample_softmax_hist uses its first kernel (4 horizontally adjacent pixels per thread).   */
+HIAST_API int hiast_debug_upsample_v1(int on);
 
 /* ---- device-side self test (needs a GPU; used by tests only) ---------------------------- */
 /* Sweeps EVERY non-positive float (bit patterns 0x80000000..0xFF800000 and +0) through the packed

@@ -244,9 +244,10 @@ def test_scan_error_flag_mirrors_numpy_valueerror():
 
 
 @pytest.mark.parametrize('shape', [((17, 33), (128, 256)), ((9, 21), (64, 160)), ((13, 17), (100, 132)), ((129, 257), (1024, 2048)),
-                                   ((16, 16), (16, 16))])
+                                   ((16, 16), (16, 16)), ((65, 129), (512, 1024)), ((20, 40), (157, 316))])
 @pytest.mark.parametrize('C', [19, 16])
-def test_fused_bilinear_upsample_bit_exact_vs_torch(shape, C):
+@pytest.mark.parametrize('v1', [0, 1])
+def test_fused_bilinear_upsample_bit_exact_vs_torch(shape, C, v1):
     """phase A straight from the stride-8 logits == softmax(F.interpolate(x, align_corners=True)).max(1)
     on CUDA, bit for bit (conf, label, histogram), without the full-resolution tensor."""
     o = ops()
@@ -256,7 +257,12 @@ def test_fused_bilinear_upsample_bit_exact_vs_torch(shape, C):
     lr = (torch.randn(n, C, h, w, generator=g) * 4).cuda()
     full = torch.nn.functional.interpolate(lr, size=(H, W), mode='bilinear', align_corners=True)
     want_conf, want_label = torch_softmax_max(full)
-    conf, label, hist = o.ias_upsample_softmax_hist(lr, (H, W), group_size=2)
+    from hiast_b200 import _lib
+    _lib.lib().hiast_debug_upsample_v1(v1)     # 1: the first kernel (4 px along x per thread); 0: column kernel where it applies
+    try:
+        conf, label, hist = o.ias_upsample_softmax_hist(lr, (H, W), group_size=2)
+    finally:
+        _lib.lib().hiast_debug_upsample_v1(0)
     assert torch.equal(conf, want_conf)
     assert torch.equal(label.long(), want_label)
     conf2, label2, hist2 = o.ias_softmax_hist(full.contiguous(), group_size=2)

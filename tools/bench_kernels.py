@@ -153,6 +153,11 @@ def main():
     ms_fused = timeit(lambda: ops.ias_upsample_softmax_hist(lr, (H, W), B, key_lo, conf, label, hist), iters=5)
     ms_interp = timeit(lambda: torch.nn.functional.interpolate(lr, size=(H, W), mode='bilinear', align_corners=True), iters=5)
     ms_a = timeit(lambda: ops.ias_softmax_hist(full, B, key_lo, conf, label, hist), iters=5)
+    from hiast_b200 import _lib as _l
+    _l.lib().hiast_debug_upsample_v1(1)
+    ms_fused_v1 = timeit(lambda: ops.ias_upsample_softmax_hist(lr, (H, W), B, key_lo, conf, label, hist), iters=5)
+    _l.lib().hiast_debug_upsample_v1(0)
+    res['upsample_fused_v1'] = dict(ms=ms_fused_v1, img_s=n / ms_fused_v1 * 1e3)
     res['upsample_fused'] = dict(ms_fused=ms_fused, img_s_fused=n / ms_fused * 1e3, ms_interpolate=ms_interp, ms_phase_a=ms_a,
                                  img_s_two_step=n / (ms_interp + ms_a) * 1e3)
     del lr, full
