@@ -158,7 +158,7 @@ class BasePseudoGenerator:
 
     # ------------------------------------------------------------ device loop
     def _make_engine(self, logits, alpha=0.0, beta=0.0, gamma=1.0):
-        b, c, h, w = logits.shape
+        b, c, h, w = logits.shape       # a LowResLogits reports the up-sampled (image) size
         group = int(_cfg_get(self.cfg, 'pseudo_policy.batch_size', b) or b)
         group = max(group, b)
         return IASEngine(c, h, w, group, alpha, beta, gamma, self._cp_gamma(), group * self.window_batches,
@@ -170,13 +170,40 @@ class BasePseudoGenerator:
         with torch.no_grad():
             for data in self.t_loader:
                 imgs = data['images'].to(self.device, non_blocking=True)
-                logits = self.model(imgs)['logits']
+                out = self.model(imgs)
+                if 'logits' not in out and 'logits_lr' in out:
+                    # the network's own (stride-8) output: the bilinear up-sampling of
+                    # self_training_segmentor.py:27 is fused into phase A
+                    lr = out['logits_lr']
+                    lr = lr.float() if lr.dtype != torch.float32 else lr
+                    yield LowResLogits(lr.contiguous(), tuple(out.get('size', imgs.shape[2:]))), list(data['image_paths'])
+                    continue
+                logits = out['logits']
                 if logits.dtype != torch.float32:
                     logits = logits.float()
                 yield logits.contiguous(), list(data['image_paths'])
 
     def _already_done(self):
         return self.t_dataset is not None and len(os.listdir(self.pseudo_label_save_dir)) >= len(self.t_dataset)
+
+
+class LowResLogits:
+    """Stride-8 logits [B,C,h,w] together with the size they are to be up-sampled to (bilinear, align_corners=True)."""
+
+    def __init__(self, logits_lr, size):
+        self.logits_lr, self.size = logits_lr, (int(size[0]), int(size[1]))
+
+    @property
+    def shape(self):
+        b, c = self.logits_lr.shape[:2]
+        return (b, c, self.size[0], self.size[1])
+
+
+def _phase_a(engine, logits, first_image):
+    if isinstance(logits, LowResLogits):
+        engine.phase_a_lowres(logits.logits_lr, first_image)
+    else:
+        engine.phase_a(logits, first_image)
 
 
 def _flush_window(gen, engine, paths, n_images, scan):
@@ -224,7 +251,7 @@ class ConstantThresholdPseudoGenerator(BasePseudoGenerator):
                 engine = self._engine = self._make_engine(logits)
                 engine.thr_groups.copy_(torch.from_numpy(np.tile(thr, (engine.max_groups, 1))))
             b = logits.shape[0]
-            engine.phase_a(logits, n)
+            _phase_a(engine, logits, n)
             paths += img_paths
             n += b
             if n + engine.B > engine.max_images or b != engine.B:
@@ -258,9 +285,12 @@ class CBSTPseudoGenerator(ConstantThresholdPseudoGenerator):
         hist = None
         for logits, _paths in self._iterate_logits():
             b = logits.shape[0]
-            conf, label, _ = ops.ias_softmax_hist(logits, b)            # phase A (its own histogram is not used here)
+            if isinstance(logits, LowResLogits):                        # phase A (its own histogram is not used here)
+                conf, label, _ = ops.ias_upsample_softmax_hist(logits.logits_lr, logits.size, b)
+            else:
+                conf, label, _ = ops.ias_softmax_hist(logits, b)
             if hist is None:
-                hist = torch.zeros((C, ops.ias_row_stride(key_lo)), dtype=torch.int32, device=logits.device)
+                hist = torch.zeros((C, ops.ias_row_stride(key_lo)), dtype=torch.int32, device=conf.device)
             ops.cbst_sample_hist(conf, label, C, b, int(cbst.sample_interval), key_lo, hist)
         if hist is None:
             raise IndexError('index -1 is out of bounds for axis 0 with size 0')     # np.quantile([]) on an empty set
@@ -325,7 +355,7 @@ class IASPseudoGenerator(BasePseudoGenerator):
                 engine.thr_state.copy_(torch.from_numpy(self.class_threshold))
                 engine.mean_state.copy_(torch.from_numpy(self.class_mean_probs))
             b = logits.shape[0]
-            engine.phase_a(logits, n)                     # asynchronous; overlaps the next forward pass
+            _phase_a(engine, logits, n)                   # asynchronous; overlaps the next forward pass
             paths += img_paths
             n += b
             if n + engine.B > engine.max_images or b != engine.B:

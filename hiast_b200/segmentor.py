@@ -73,6 +73,9 @@ class SelfTrainingSegmentor(nn.Module):
         if self.seg_model is None:
             raise RuntimeError('no seg_model was given: the DeepLabv2 backbone is outside this package')
         t_logits, backbone = self.seg_model(t_img)
+        if getattr(self, 'fused_upsample', False) and not torch.is_grad_enabled():
+            # pseudo-labelling: hand the stride-8 logits to the generator, which fuses the up-sampling into phase A
+            return {'logits_lr': t_logits, 'size': tuple(t_img.shape[2:]), 'backbone': backbone}
         t_logits = F.interpolate(t_logits, size=t_img.shape[2:], mode='bilinear', align_corners=True)
         return {'logits': t_logits, 'backbone': backbone}
 

@@ -275,3 +275,44 @@ def test_cbst_sampling_full_resolution_properties():
     vals = torch.cat([conf[2 * b:2 * b + 2][label[2 * b:2 * b + 2] == c][::4] for b in range(2)])
     keys = vals.half().view(torch.int16).long() - key_lo
     assert torch.equal(hist[c].long(), torch.bincount(keys, minlength=hist.shape[1]))
+
+
+@pytest.mark.parametrize('ptype', ['IAS', 'CT', 'CBST'])
+def test_generators_from_stride8_logits_equal_the_interpolated_path(ptype, tmp_path):
+    """SURVEY 8f rank 1 through the reference-facing API: a model that returns its stride-8 logits ('logits_lr') gives the
+    same thresholds / statistics / PNGs as the reference's F.interpolate(..., align_corners=True) inside the model."""
+    import cv2
+    import hiast_b200
+    hiast_b200.register_all()
+    from hiast_b200 import PSEUDO_POLICY
+    spec = dict(C=19, B=2, alpha=0.5, beta=0.9, gamma=8.0, cp_gamma=0.99)
+    H, W, h, w, N = 64, 128, 9, 17, 6
+    g = torch.Generator().manual_seed(5)
+    imgs = [torch.randn(2, 19, h, w, generator=g) * 4 for _ in range(N // 2)]      # stand-ins: the "image" IS the low-res logit map
+
+    class Full:
+        def eval(self):
+            return self
+
+        def __call__(self, x):
+            return {'logits': torch.nn.functional.interpolate(x, size=(H, W), mode='bilinear', align_corners=True)}
+
+    class Low(Full):
+        def __call__(self, x):
+            return {'logits_lr': x, 'size': (H, W)}
+
+    res = {}
+    for name, model in (('full', Full()), ('low', Low())):
+        cfg = make_cfg(spec, ptype)
+        cfg.pseudo_policy.cbst = SimpleNamespace(sample_interval=4, p=0.3) if ptype == 'CBST' else None
+        loader = [{'images': x, 'image_paths': ['%s_%d.png' % (name, 2 * i + k) for k in range(2)]} for i, x in enumerate(imgs)]
+        save_dir = str(tmp_path / name / 'pseudo_labels')
+        gen = PSEUDO_POLICY[ptype](cfg, model=model, loader=loader, dataset_len=N, save_dir=save_dir, window_batches=2)
+        gen.run()
+        pngs = [cv2.imread(os.path.join(save_dir, '%s_%d_pseudo_label.png' % (name, i)), cv2.IMREAD_UNCHANGED) for i in range(N)]
+        res[name] = (np.asarray(gen.class_threshold), np.asarray(gen.statics_class), np.asarray(gen.class_mean_probs), pngs)
+    assert np.array_equal(res['full'][0], res['low'][0])
+    assert np.array_equal(res['full'][1], res['low'][1])
+    assert np.array_equal(res['full'][2], res['low'][2])
+    for a, b in zip(res['full'][3], res['low'][3]):
+        assert a is not None and np.array_equal(a, b)
