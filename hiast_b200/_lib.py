@@ -50,6 +50,8 @@ _SIGNATURES = {
     'hiast_confusion_matrix': (_i, [_vp, _vp, _i, _i64, _i, _i, _vp, _vp, _vp]),
     'hiast_confusion_from_logits': (_i, [_vp, _vp, _i, _i, _i, _i64, _i, _i, _vp, _vp]),
     'hiast_iou_from_confusion': (_i, [_vp, _i, _vp, _vp, _vp]),
+    'hiast_ema_update': (_i, [_vp, _vp, _vp, _i, _i, C.c_float, C.c_float, _vp]),
+    'hiast_multi_copy': (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     'hiast_debug_set_fused_trace': (_i, [_vp]),
     'hiast_debug_loss_scalar': (_i, [_i]),
     'hiast_debug_upsample_v1': (_i, [_i]),

@@ -212,6 +212,18 @@ HIAST_API int hiast_confusion_from_logits(const float* logits, const void* targe
 HIAST_API int hiast_iou_from_confusion(const int64_t* cm, int K, float* intersection, float* area_union,
                              void* stream);
 
+/* ---- EMA teacher update (8f rank 4)  utils/utils.py:115-123 ------------------------------ */
+/* param_k = param_k * gamma + param_q * (1 - gamma) for a whole model in ONE launch (three float32 roundings per
+ * element like the reference; gamma / one_minus_gamma are the float32 roundings of the Python floats gamma and
+ * 1 - gamma).  segs_dev: device table of n_seg x {void* k, const void* q, int64 n}; the segments are cut into chunks
+ * of chunk_elems elements (multiple of 4): chunk_seg_dev i32 [n_chunks] names the segment of each chunk, chunk_off_dev
+ * i64 [n_chunks] its first element.  All pointers are float32 device memory.                       */
+HIAST_API int hiast_ema_update(const void* segs_dev, const int32_t* chunk_seg_dev, const int64_t* chunk_off_dev,
+                     int n_chunks, int chunk_elems, float gamma, float one_minus_gamma, void* stream);
+/* buffer_k = buffer_q (:120-121) with the same tables; n and the chunk size are in BYTES (multiple of 16).       */
+HIAST_API int hiast_multi_copy(const void* segs_dev, const int32_t* chunk_seg_dev, const int64_t* chunk_off_dev,
+                     int n_chunks, int chunk_bytes, void* stream);
+
 /* ---- host-side test hooks (no GPU needed; used by tests only) --------------------------- */
 /* x^n by double-double repeated squaring, the integer-gamma power used by the scan.          */
 HIAST_API double hiast_testhook_powi(double x, int n);

@@ -25,4 +25,4 @@ scalar ``**`` (glibc pow); torch 2.11 ``softmax`` / ``max`` / ``log_softmax`` /
 ``CrossEntropyLoss`` / ``histc``.
 """
 
-from . import ias, losses, metrics, copy_paste  # noqa: F401
+from . import ias, losses, metrics, copy_paste, ema  # noqa: F401

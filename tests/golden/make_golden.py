@@ -15,6 +15,7 @@ output of the reference's own functions on seeded inputs:
                                                 sseg/models/segmentors/self_training_segmentor.py:30-53
 * metric_*.npz    intersectionAndUnionGPU       utils/metrics.py:6-19
 * copy_paste.npz  CopyPaste.run_original        sseg/datasets/preprocessor.py:79-122
+* ema_update.npz  update_ema_model              utils/utils.py:115-123
 
 Inputs that are large are not stored: they are regenerated from a seeded CPU
 ``torch.Generator`` by ``tests/golden_inputs.py`` (same torch build on the GPU
@@ -270,8 +271,45 @@ def copy_paste_fixture(name, spec):
     print(name, 'hard', cp.hard_classes)
 
 
+def ema_fixture(name):
+    """utils.update_ema_model on a small conv net with BatchNorm buffers (float32 parameters, int64 / float32 buffers)."""
+    from utils import utils as ref_utils
+    g = torch.Generator().manual_seed(77)
+
+    def net():
+        m = torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3), torch.nn.BatchNorm2d(8), torch.nn.Conv2d(8, 5, 1, bias=False),
+                                torch.nn.Linear(7, 1031))
+        for p in m.parameters():
+            p.data = torch.randn(p.shape, generator=g) * (10.0 ** float(torch.randint(-6, 3, (1,), generator=g)))
+        for b in m.buffers():
+            if b.dtype.is_floating_point:
+                b.data = torch.rand(b.shape, generator=g)
+            else:
+                b.data = torch.randint(0, 1000, b.shape, generator=g)
+        return m
+
+    student, teacher = net(), net()
+    out = {'gamma': np.float64(0.999)}
+    for i, p in enumerate(student.parameters()):
+        out['q%d' % i] = p.data.numpy().copy()
+    for i, p in enumerate(teacher.parameters()):
+        out['k%d' % i] = p.data.numpy().copy()
+    for i, b in enumerate(student.buffers()):
+        out['bq%d' % i] = b.data.numpy().copy()
+    ref_utils.update_ema_model(teacher, student, 0.999)
+    for i, p in enumerate(teacher.parameters()):
+        out['new%d' % i] = p.data.numpy().copy()
+    for i, b in enumerate(teacher.buffers()):
+        out['bnew%d' % i] = b.data.numpy().copy()
+    out['n_params'] = np.int64(len(list(student.parameters())))
+    out['n_buffers'] = np.int64(len(list(student.buffers())))
+    np.savez_compressed(os.path.join(HERE, name + '.npz'), **out)
+    print(name, 'params', int(out['n_params']), 'buffers', int(out['n_buffers']))
+
+
 def main():
     install_shim()
+    ema_fixture('ema_update')
     for name, spec in gi.IAS_SPECS.items():
         ias_fixture(name, spec, store_conf=spec.get('store_conf', True))
     cbst_fixture('cbst_small', gi.IAS_SPECS['ias_small'], 4, 0.2)

@@ -196,3 +196,15 @@ def test_cbst_oracle_matches_reference():
     # pinned-version semantic (float64 quantile, numpy 1.19): within one fp16 step of it on this small fixture
     thr64 = oias.cbst_thresholds(cl, spec['C'], int(gold['interval']), float(gold['p']))
     assert np.abs(thr64 - thr).max() < 2e-3
+
+
+def test_ema_oracle_vs_reference_fixture():
+    """oracle.ema == utils.update_ema_model (utils/utils.py:115-123) run by tests/golden/make_golden.py, bit for bit."""
+    from oracle import ema
+    g = np.load(os.path.join(GOLD, 'ema_update.npz'))
+    n, nb = int(g['n_params']), int(g['n_buffers'])
+    new = ema.ema_update([g['k%d' % i] for i in range(n)], [g['q%d' % i] for i in range(n)], float(g['gamma']))
+    for i in range(n):
+        assert np.array_equal(new[i], g['new%d' % i])
+    for i, b in enumerate(ema.copy_buffers([g['bq%d' % i] for i in range(nb)])):
+        assert np.array_equal(b, g['bnew%d' % i])

@@ -205,6 +205,24 @@ def main():
     dlbl = (torch.arange(16 * 1024 * 2048, device='cuda') // 5000 % 19).to(torch.uint8).view(16, 1024, 2048)
     ms = timeit(lambda: ops.copy_paste(img, lbl, mask, dimg, dlbl, list(range(14))), iters=10)
     res['copy_paste'] = dict(ms=ms, img_s=16 / ms * 1e3, gbs=16 * 1024 * 2048 * 13 / ms / 1e6)
+    # EMA teacher update: a ResNet-101-sized parameter set (about 300 tensors, 44.5 M float32 parameters)
+    from hiast_b200.ema import update_ema_model
+
+    class Bag(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            sizes = [64 * 3 * 49] + [c * c * 9 for c in (64, 128, 256, 512) for _ in range(12)] + \
+                    [c * 4 * c for c in (64, 128, 256, 512) for _ in range(24)] + [2048 * 19 * 9 * 4] + [256] * 150
+            self.ps = torch.nn.ParameterList([torch.nn.Parameter(torch.randn(n, device='cuda')) for n in sizes])
+    student, teacher = Bag(), Bag()
+    n_par = sum(p.numel() for p in student.parameters())
+    ms = timeit(lambda: update_ema_model(teacher, student, 0.999), iters=10)
+
+    def torch_ema():       # the reference's eager loop, utils/utils.py:117-119
+        for pq, pk in zip(student.parameters(), teacher.parameters()):
+            pk.data = pk.data.clone() * 0.999 + pq.data.clone() * (1 - 0.999)
+    ms_ref = timeit(torch_ema, iters=5)
+    res['ema_update'] = dict(ms=ms, gbs=n_par * 12 / ms / 1e6, params=n_par, tensors=len(student.ps), ms_reference_loop=ms_ref)
     os.makedirs(os.path.dirname(args.out) or '.', exist_ok=True)
     json.dump(res, open(args.out, 'w'), indent=1)
     print(json.dumps(res, indent=1))
