@@ -116,11 +116,12 @@ def reference_arm(args):
         return
     n = args.cpu_images
     steps = max(1, min(args.steps, 2))
-    value, secs, threads = run_cpu_port(n, steps=steps, warmup=0)
+    warm = max(0, min(args.warmup, 1))     # a CPU step takes seconds: at most one untimed pass
+    value, secs, threads = run_cpu_port(n, steps=steps, warmup=warm)
     sample = '%d maps of 19x1024x2048, batch 2 (%d groups), per step; PNG write excluded' % (n, (n + 1) // 2)
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': steps,
-        'warmup': 0, 'ms_per_step': secs * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'warmup': warm, 'ms_per_step': secs * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': 'GTA5->Cityscapes IAS pseudo-labelling, 19x1024x2048 logit maps, batch 2 (configs[1])',
                    'note': 'reference is pure Python/numpy and cannot travel to the GPU box; this is the oracle port '
