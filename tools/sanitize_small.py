@@ -1,0 +1,44 @@
+#!/usr/bin/env python
+"""Small pass over every kernel family for compute-sanitizer (memcheck / racecheck / synccheck).
+
+    compute-sanitizer --tool racecheck python tools/sanitize_small.py
+"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from hiast_b200 import ops  # noqa: E402
+from hiast_b200.ema import update_ema_model  # noqa: E402
+from hiast_b200.ias_engine import IASEngine  # noqa: E402
+
+g = torch.Generator().manual_seed(3)
+C, H, W, B, N = 19, 64, 128, 2, 5
+logits = (torch.randn(N, C, H, W, generator=g) * 3).cuda()
+logits[1, 4] += 30.0                                         # saturated pixels: top-key counters
+for fused in (False, True):
+    eng = IASEngine(C, H, W, B, 0.5, 0.9, 8.0, 0.99, 6, fused=fused)
+    eng.process(logits)
+    assert eng.check_errors()
+for mode in (1, 6, 16, 36, 56, 80, 81, 83):
+    ops.ias_softmax_hist(logits, B, hist_mode=mode)
+lr = (torch.randn(3, C, 17, 33, generator=g) * 4).cuda()
+ops.ias_upsample_softmax_hist(lr, (128, 256), B)
+z = (torch.randn(2, C, 32, 64, generator=g) * 3).cuda()
+t = torch.softmax(torch.randn(2, C, 32, 64, generator=g) * 3, dim=1).cuda()
+y = torch.randint(0, C, (2, 32, 64), generator=g)
+y[torch.rand(2, 32, 64, generator=g) < 0.5] = 255
+y = y.cuda()
+ops.st_loss_fwd(z, t, y, 'ignored')
+ops.st_loss_bwd(z, t, y, torch.full((4,), 0.1, device='cuda'), 'ignored')
+pred = torch.randint(0, C, (2, 64, 64), generator=g).cuda()
+ops.confusion_matrix(pred, pred.clone(), C)
+img = torch.randint(0, 256, (2, 64, 64, 3), dtype=torch.uint8, generator=g).cuda()
+lbl = torch.randint(0, C, (2, 64, 64), dtype=torch.uint8, generator=g).cuda()
+mask = torch.full((2, 64, 64), 255, dtype=torch.uint8, device='cuda')
+ops.copy_paste(img, lbl, mask, img.clone(), lbl.clone(), list(range(14)))
+net = lambda: torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3), torch.nn.BatchNorm2d(8), torch.nn.Linear(7, 1031)).cuda()
+update_ema_model(net(), net(), 0.99)
+torch.cuda.synchronize()
+print('sanitize_small ok')
