@@ -59,6 +59,37 @@ def test_packed_expf_is_expf_for_every_non_positive_float():
     assert int(bad.item()) == 0
 
 
+@pytest.mark.parametrize('seed', range(12))
+def test_phase_a_randomised_stress_vs_torch_cuda(seed):
+    """Randomised shapes / magnitudes / quantisations for the packed-math kernels (modes 56, 80, 83) against
+    torch.softmax(...).max(1) on CUDA, bit for bit: logits scaled from 1e-4 to 300, quantised to multiples of 2^-k (many
+    exact ties and near ties), sprinkled with -inf, +-1e4 and denormals."""
+    o = ops()
+    g = torch.Generator().manual_seed(1000 + seed)
+    c = 19 if seed % 3 else 16
+    h = int(torch.randint(3, 70, (1,), generator=g))
+    w = 4 * int(torch.randint(1, 70, (1,), generator=g))
+    n = int(torch.randint(1, 6, (1,), generator=g))
+    scale = [1e-4, 1e-2, 1.0, 3.0, 30.0, 300.0][seed % 6]
+    x = torch.randn(n, c, h, w, generator=g) * scale
+    if seed % 2:
+        q = 2.0 ** -int(torch.randint(0, 12, (1,), generator=g))
+        x = torch.round(x / q) * q                                     # quantised: exact ties are common
+    m = torch.rand(n, c, h, w, generator=g)
+    x[m < 0.01] = -float('inf')
+    x[(m >= 0.01) & (m < 0.02)] = -1e4
+    x[(m >= 0.02) & (m < 0.03)] = 1e4
+    x[(m >= 0.03) & (m < 0.04)] = 1e-41                                # denormal
+    x[:, 0] = torch.where(torch.isinf(x).all(dim=1), torch.zeros(()), x[:, 0])      # no all -inf pixel (NaN in torch too)
+    x = x.cuda()
+    want_conf, want_label = torch_softmax_max(x)
+    for mode in (56, 80, 83):
+        conf, label, hist = o.ias_softmax_hist(x, group_size=2, hist_mode=mode)
+        assert torch.equal(conf, want_conf), (seed, mode)
+        assert torch.equal(label.long(), want_label), (seed, mode)
+        assert int(hist.sum()) == n * h * w
+
+
 def test_phase_a_ties_and_near_ties():
     """Exact logit ties, channels a hair below the max (expf -> 1.0f), constant maps, huge gaps."""
     o = ops()
