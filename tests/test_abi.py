@@ -68,3 +68,12 @@ def test_product_path_has_no_cpu_fallback(built_lib):
         ops.ias_softmax_hist(torch.zeros(1, 19, 4, 4), 2)
     with pytest.raises(_lib.HiastError):
         ops.confusion_matrix(torch.zeros(4, dtype=torch.int64), torch.zeros(4, dtype=torch.int64), 19)
+    with pytest.raises(_lib.HiastError):
+        ops.ias_upsample_softmax_hist(torch.zeros(1, 19, 3, 3), (8, 8), 2)
+    from hiast_b200.ema import update_ema_model
+    with pytest.raises(_lib.HiastError):                       # CPU models: no host path for the EMA update either
+        update_ema_model(torch.nn.Linear(3, 2), torch.nn.Linear(3, 2), 0.99)
+    l = _lib.lib()
+    assert l.hiast_ema_update(None, None, None, 1, 1024, 0.9, 0.1, None) == -1
+    assert l.hiast_ias_fused_window(None, 1, 19, 4, 4, 2, 0, 0.5, 0.9, 8.0, None, None, None, None, None, None, None, None, None,
+                                    None, None, 0, 0, None) == -1
