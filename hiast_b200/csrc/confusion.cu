@@ -8,8 +8,8 @@
 //
 // HBM stream of 2 x elem_bytes per pixel (16 B/px as the reference calls it, int64 + int64;
 // 4C+8 B/px for the fused argmax-from-logits form).  Contention (most pixels land on a handful
-// of diagonal cells) is removed with warp match.any aggregation + a per-CTA shared matrix;
-// int64 global atomics only once per CTA per non-zero cell.
+// of diagonal cells) is removed with one shared matrix per warp and a warp-uniform fast path (match.any
+// aggregation into a per-CTA matrix for K > 38); int64 global atomics only once per CTA per non-zero cell.
 #include <algorithm>
 
 #include "common.cuh"
@@ -20,10 +20,25 @@ constexpr int kThreadsM = 256;
 constexpr int kMaxSharedCells = 12288;  // 48 KB of uint32
 
 struct CmSink {
-  unsigned* s;          // shared cells or nullptr
+  unsigned* s;          // per-CTA shared cells or nullptr
   long long* g;         // global matrix
+  unsigned* w;          // this warp's PRIVATE shared matrix or nullptr
   __device__ __forceinline__ void add(bool valid, int cell) const {
     const unsigned active = __ballot_sync(0xffffffffu, valid);
+    if (w) {
+      // Warp-private matrix: when every valid lane hits the same cell (coherent label maps: almost always) one lane
+      // adds the count with one shared atomic; otherwise every lane issues its own shared atomic (random
+      // labels: 32 different cells, no serialisation, none of match.any's cost).
+      if (active == 0) return;
+      const int leader = __ffs(active) - 1;
+      const int c0 = __shfl_sync(0xffffffffu, cell, leader);
+      if (__all_sync(0xffffffffu, !valid || cell == c0)) {
+        if (lane_id() == leader) atomicAdd(w + c0, static_cast<unsigned>(__popc(active)));   // fire and forget
+      } else if (valid) {
+        atomicAdd(w + cell, 1u);
+      }
+      return;
+    }
     if (!valid) return;
     const unsigned peers = __match_any_sync(active, cell);
     if (lane_id() == __ffs(peers) - 1) {
@@ -34,6 +49,24 @@ struct CmSink {
   }
 };
 
+// use_shared: 0 global atomics, 1 one matrix per CTA, 2 one matrix per warp (cells * warps <= kMaxSharedCells)
+__device__ __forceinline__ void cm_init(unsigned* s_cm, int cells, int use_shared) {
+  const int n = use_shared == 2 ? cells * (kThreadsM / 32) : (use_shared ? cells : 0);
+  for (int i = threadIdx.x; i < n; i += kThreadsM) s_cm[i] = 0;
+  __syncthreads();
+}
+
+__device__ __forceinline__ void cm_flush(const unsigned* s_cm, int cells, int use_shared, long long* cm) {
+  if (!use_shared) return;
+  __syncthreads();
+  for (int i = threadIdx.x; i < cells; i += kThreadsM) {
+    unsigned v = s_cm[i];
+    if (use_shared == 2)
+      for (int wi = 1; wi < kThreadsM / 32; ++wi) v += s_cm[wi * cells + i];
+    if (v) atomicAdd(reinterpret_cast<unsigned long long*>(cm) + i, static_cast<unsigned long long>(v));
+  }
+}
+
 __device__ __forceinline__ int clamp_class(long long v, int K) { return (v >= 0 && v < K) ? static_cast<int>(v) : K; }
 
 template <typename T>
@@ -42,11 +75,8 @@ __global__ void __launch_bounds__(kThreadsM) k_confusion(const T* __restrict__ p
                                                          long long* __restrict__ cm, int use_shared) {
   extern __shared__ unsigned s_cm[];
   const int cells = (K + 1) * (K + 1);
-  if (use_shared) {
-    for (int i = threadIdx.x; i < cells; i += kThreadsM) s_cm[i] = 0;
-    __syncthreads();
-  }
-  CmSink sink = {use_shared ? s_cm : nullptr, cm};
+  cm_init(s_cm, cells, use_shared);
+  CmSink sink = {use_shared == 1 ? s_cm : nullptr, cm, use_shared == 2 ? s_cm + (threadIdx.x >> 5) * cells : nullptr};
   // per-CTA contiguous chunk, rounded so that every warp iteration is full except the last one
   const long long per = ((n + gridDim.x - 1) / gridDim.x + kThreadsM * 4 - 1) / (kThreadsM * 4) * (kThreadsM * 4);
   const long long i0 = per * blockIdx.x;
@@ -74,13 +104,7 @@ __global__ void __launch_bounds__(kThreadsM) k_confusion(const T* __restrict__ p
       sink.add(keep, clamp_class(t[u], K) * (K + 1) + clamp_class(p[u], K));
     }
   }
-  if (use_shared) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < cells; i += kThreadsM) {
-      const unsigned v = s_cm[i];
-      if (v) atomicAdd(reinterpret_cast<unsigned long long*>(cm) + i, static_cast<unsigned long long>(v));
-    }
-  }
+  cm_flush(s_cm, cells, use_shared, cm);
 }
 
 // pred = first-index argmax over C of logits [B,C,HW] (torch.argmax(dim=1), base_trainer.py:173)
@@ -90,11 +114,8 @@ __global__ void __launch_bounds__(kThreadsM) k_confusion_logits(const float* __r
                                                                 long long* __restrict__ cm, int use_shared) {
   extern __shared__ unsigned s_cm[];
   const int cells = (K + 1) * (K + 1);
-  if (use_shared) {
-    for (int i = threadIdx.x; i < cells; i += kThreadsM) s_cm[i] = 0;
-    __syncthreads();
-  }
-  CmSink sink = {use_shared ? s_cm : nullptr, cm};
+  cm_init(s_cm, cells, use_shared);
+  CmSink sink = {use_shared == 1 ? s_cm : nullptr, cm, use_shared == 2 ? s_cm + (threadIdx.x >> 5) * cells : nullptr};
   const long long n = static_cast<long long>(B) * HW;
   const long long per = ((n + gridDim.x - 1) / gridDim.x + kThreadsM - 1) / kThreadsM * kThreadsM;
   const long long i0 = per * blockIdx.x;
@@ -120,13 +141,7 @@ __global__ void __launch_bounds__(kThreadsM) k_confusion_logits(const float* __r
     const bool keep = in && (t != ignore_index);
     sink.add(keep, clamp_class(t, K) * (K + 1) + clamp_class(p, K));
   }
-  if (use_shared) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < cells; i += kThreadsM) {
-      const unsigned v = s_cm[i];
-      if (v) atomicAdd(reinterpret_cast<unsigned long long*>(cm) + i, static_cast<unsigned long long>(v));
-    }
-  }
+  cm_flush(s_cm, cells, use_shared, cm);
 }
 
 __global__ void k_iou_from_cm(const long long* __restrict__ cm, int K, float* __restrict__ inter, float* __restrict__ uni) {
@@ -160,8 +175,8 @@ extern "C" int hiast_confusion_matrix(const void* pred, const void* target, int 
   if (n < 0 || K < 1 || K > HIAST_MAX_CLASSES) return HIAST_ERR_INVALID_ARG;
   if (n == 0) return HIAST_OK;
   const int cells = (K + 1) * (K + 1);
-  const int use_shared = cells <= kMaxSharedCells;
-  const size_t smem = use_shared ? cells * sizeof(unsigned) : 0;
+  const int use_shared = cells * (kThreadsM / 32) <= kMaxSharedCells ? 2 : (cells <= kMaxSharedCells ? 1 : 0);
+  const size_t smem = (use_shared == 2 ? cells * (kThreadsM / 32) : (use_shared ? cells : 0)) * sizeof(unsigned);
   const int grid = cm_grid(n);
   cudaStream_t st = as_stream(stream);
   if (elem_bytes == 8)
@@ -185,8 +200,8 @@ extern "C" int hiast_confusion_from_logits(const float* logits, const void* targ
   if (B < 0 || C < 1 || HW < 1 || K < 1 || K > HIAST_MAX_CLASSES) return HIAST_ERR_INVALID_ARG;
   if (B == 0) return HIAST_OK;
   const int cells = (K + 1) * (K + 1);
-  const int use_shared = cells <= kMaxSharedCells;
-  const size_t smem = use_shared ? cells * sizeof(unsigned) : 0;
+  const int use_shared = cells * (kThreadsM / 32) <= kMaxSharedCells ? 2 : (cells <= kMaxSharedCells ? 1 : 0);
+  const size_t smem = (use_shared == 2 ? cells * (kThreadsM / 32) : (use_shared ? cells : 0)) * sizeof(unsigned);
   const int grid = cm_grid(static_cast<long long>(B) * HW);
   cudaStream_t st = as_stream(stream);
   if (target_bytes == 8)
