@@ -231,7 +231,7 @@ __device__ __forceinline__ void block_reduce_store(const PixelSums& acc, Partial
 // every thread owns 2C x 8 bytes of shared memory (its pixel pair's z and t columns); at the top of an iteration it
 // pulls them into registers, immediately re-issues the 8-byte cp.async of ITS next pixel pair into the same
 // slots, and does the math while they are in flight (LDGSTS is tracked by async groups, not by the register
-// scoreboard the MUFU results of the math use -- same reasoning as k_softmax_hist_sp in ias.cu).
+// scoreboard the MUFU results of the math use -- same reasoning as k_softmax_hist_sp in ias_phase_a.cu).
 template <int C>
 struct LossStage {
   float2* my;          // this thread's column: [2C][kThreadsL] float2, z channels then t channels

@@ -17,7 +17,7 @@
 #include <vector>
 
 #include "../hiast_b200/csrc/api.cu"
-#include "../hiast_b200/csrc/ias.cu"
+#include "../hiast_b200/csrc/ias_phase_a.cu"
 
 using namespace hiast;
 
