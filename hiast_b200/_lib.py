@@ -52,6 +52,10 @@ _SIGNATURES = {
     'hiast_iou_from_confusion': (_i, [_vp, _i, _vp, _vp, _vp]),
     'hiast_ema_update': (_i, [_vp, _vp, _vp, _i, _i, C.c_float, C.c_float, _vp]),
     'hiast_multi_copy': (_i, [_vp, _vp, _vp, _i, _i, _vp]),
+    'hiast_png_workspace_bytes': (_sz, [_i, _i, _i]),
+    'hiast_png_max_bytes': (_sz, [_i, _i]),
+    'hiast_png_segments': (_i, [_i, _i]),
+    'hiast_png_encode': (_i, [_vp, _i, _i, _i, _vp, _sz, _vp, _vp, _sz, _vp]),
     'hiast_debug_set_fused_trace': (_i, [_vp]),
     'hiast_debug_loss_scalar': (_i, [_i]),
     'hiast_debug_upsample_v1': (_i, [_i]),

@@ -17,7 +17,7 @@ from ._lib import IGNORE, KEY_ONE, REGION, TERM_CE, TERM_CST, TERM_ENT, TERM_KLD
 __all__ = [
     'ias_key_lo', 'ias_num_bins', 'ias_row_stride', 'ias_new_hist', 'ias_softmax_hist', 'ias_upsample_softmax_hist', 'ias_conf_hist', 'ias_threshold_scan',
     'ias_select', 'ias_meanprob_scan', 'ias_fused_window', 'UNSUPPORTED', 'cbst_sample_hist', 'cbst_quantile', 'copy_paste', 'hard_lut', 'st_loss_fwd', 'st_loss_bwd',
-    'confusion_matrix', 'confusion_from_logits', 'iou_from_confusion',
+    'confusion_matrix', 'confusion_from_logits', 'iou_from_confusion', 'PngEncoder',
 ]
 
 
@@ -356,3 +356,62 @@ def iou_from_confusion(cm, K):
     check(lib().hiast_iou_from_confusion(ptr(cm), int(K), ptr(inter), ptr(union), stream_ptr(cm.device)),
           'hiast_iou_from_confusion')
     return inter, union
+
+
+# ----------------------------------------------------------------------------- PNG
+class PngEncoder:
+    """Device PNG writer for uint8 label maps [N,H,W] (pseudo_label_generator.py:43-46 `cv2.imwrite`).
+
+    ``encode(labels)`` launches the three kernels on the current stream and returns ``(blob, offsets)``: device uint8
+    blob and device int64 [N+1] offsets; file i is ``blob[offsets[i]:offsets[i+1]]``.  ``encode_to_host(labels)`` also
+    copies the used part of the blob to pinned host memory (one sync) and returns a list of ``memoryview``-able numpy
+    slices.  The blob is sized for ``expect_ratio`` x compression and grown (to the worst case) if a batch does not fit."""
+
+    def __init__(self, H, W, max_images, device='cuda', expect_ratio=4.0):
+        self.H, self.W, self.max_images = int(H), int(W), int(max_images)
+        self.device = torch.device(device)
+        l = lib()
+        self.max_file = l.hiast_png_max_bytes(self.H, self.W)
+        if self.max_file == 0:
+            raise _lib.HiastError('unsupported PNG size %dx%d' % (H, W))
+        self.segments = l.hiast_png_segments(self.H, self.W)
+        need = l.hiast_png_workspace_bytes(self.max_images, self.H, self.W)
+        self._ws = torch.empty(max(need, 256), dtype=torch.uint8, device=self.device)
+        cap = int(self.max_file * self.max_images / max(1.0, float(expect_ratio))) + 4096
+        self._blob = torch.empty(cap, dtype=torch.uint8, device=self.device)
+        self._offsets = torch.empty(self.max_images + 1, dtype=torch.int64, device=self.device)
+        self._host = None
+        self._host_off = torch.empty(self.max_images + 1, dtype=torch.int64).pin_memory()
+
+    def _launch(self, labels):
+        n = labels.shape[0]
+        check(lib().hiast_png_encode(ptr(labels), n, self.H, self.W, ptr(self._blob), self._blob.numel(), ptr(self._offsets),
+                                     ptr(self._ws), self._ws.numel(), stream_ptr(self.device)), 'hiast_png_encode')
+
+    def encode(self, labels):
+        require_cuda(labels, torch.uint8, 'labels')
+        if labels.dim() == 2:
+            labels = labels.unsqueeze(0)
+        n = labels.shape[0]
+        if tuple(labels.shape[1:]) != (self.H, self.W) or n > self.max_images:
+            raise _lib.HiastError('labels must be [<=%d, %d, %d], got %s' % (self.max_images, self.H, self.W, tuple(labels.shape)))
+        self._launch(labels)
+        self._host_off[:n + 1].copy_(self._offsets[:n + 1], non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        total = int(self._host_off[n])
+        if total > self._blob.numel():                  # did not fit: grow to the worst case and run again
+            self._blob = torch.empty(self.max_file * self.max_images + 4096, dtype=torch.uint8, device=self.device)
+            self._launch(labels)
+        return self._blob[:total], self._offsets[:n + 1], self._host_off[:n + 1]
+
+    def encode_to_host(self, labels):
+        """List of numpy uint8 arrays (views of one pinned buffer, valid until the next call), one PNG file each."""
+        blob, _, off = self.encode(labels)
+        total = blob.numel()
+        if self._host is None or self._host.numel() < total:
+            self._host = torch.empty(max(total, 1 << 20), dtype=torch.uint8).pin_memory()
+        self._host[:total].copy_(blob, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        h = self._host.numpy()
+        o = off.tolist()
+        return [h[o[i]:o[i + 1]] for i in range(len(o) - 1)]

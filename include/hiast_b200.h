@@ -224,6 +224,20 @@ HIAST_API int hiast_ema_update(const void* segs_dev, const int32_t* chunk_seg_de
 HIAST_API int hiast_multi_copy(const void* segs_dev, const int32_t* chunk_seg_dev, const int64_t* chunk_off_dev,
                      int n_chunks, int chunk_bytes, void* stream);
 
+/* ---- pseudo-label PNG writer (8f rank 2)  workflows/pseudo_label_generator.py:43-46 -------- */
+/* Replaces `cv2.imwrite(path, plbl.astype(np.uint8))`: encodes n_images uint8 label maps [n,H,W] into complete
+ * 8-bit gray PNG files (read back by base_dataset.py:158-170 `Image.open`), packed back to back in `out`:
+ * file i = out[offsets[i] .. offsets[i+1]).  offsets is int64 [n_images + 1] on the device and always written;
+ * if offsets[n_images] > out_capacity nothing else is written (call again with a larger buffer;
+ * n_images * hiast_png_max_bytes(H, W) always suffices).  `out` must be 4-byte aligned, the workspace 256-byte
+ * aligned.  Format (Up filter, fixed-Huffman DEFLATE with distance-1 matches, one IDAT chunk per segment, stored
+ * fallback, Adler-32 and CRC-32 on the device): oracle/png.py restates it byte for byte.  W <= 32768.          */
+HIAST_API size_t hiast_png_workspace_bytes(int n_images, int H, int W);
+HIAST_API size_t hiast_png_max_bytes(int H, int W);
+HIAST_API int hiast_png_segments(int H, int W);
+HIAST_API int hiast_png_encode(const uint8_t* labels, int n_images, int H, int W, uint8_t* out, size_t out_capacity,
+                     int64_t* offsets, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- host-side test hooks (no GPU needed; used by tests only) --------------------------- */
 /* x^n by double-double repeated squaring, the integer-gamma power used by the scan.          */
 HIAST_API double hiast_testhook_powi(double x, int n);
