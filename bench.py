@@ -333,7 +333,9 @@ def measure_e2e(args, device, rank, world, barrier):
     import torch
     from types import SimpleNamespace
     from hiast_b200.pseudo_label_generator import IASPseudoGenerator
+    import shutil
     import tempfile
+    import torch.distributed as dist
 
     n_host = 8                                     # pinned host pool: 8 maps = 1.3 GB
     steps = max(1, args.e2e_steps)
@@ -429,6 +431,45 @@ def measure_e2e(args, device, rank, world, barrier):
                                   'h2d_bytes_per_step': WINDOW * C * h_lr * w_lr * 4,
                                   'd2h_bytes_per_step': res['d2h_bytes_per_step'],
                                   'api': "same call, model returns {'logits_lr': [B,19,129,257]}: fused up-sampling + IAS"}
+
+    # ... and with the on-disk output of the reference (pseudo_label_generator.py:43-46) INCLUDED: the label maps are
+    # encoded as PNG files on the device (hiast_png_encode), only the files cross PCIe, a thread pool writes them.
+    class GenPng(IASPseudoGenerator):
+        def save_data(self):
+            pass
+
+    def run_png(n_images, mode):
+        d = tempfile.mkdtemp()
+        try:
+            gen = GenPng(cfg, model=LowRes(), loader=loader_lr(n_images), dataset_len=None, save_dir=os.path.join(d, 'pl'),
+                         window_batches=WINDOW // GROUP, device=device, png=mode)
+            gen.run()
+            files = os.listdir(os.path.join(d, 'pl'))
+            return len(files), sum(os.path.getsize(os.path.join(d, 'pl', f)) for f in files)
+        finally:
+            shutil.rmtree(d, ignore_errors=True)
+
+    run_png(WINDOW, 'device')
+    barrier()
+    t0 = time.perf_counter()
+    n_files, n_bytes = run_png(steps * WINDOW, 'device')
+    torch.cuda.synchronize()
+    secs = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([secs], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        secs = float(t[0])
+    assert n_files == steps * WINDOW
+    png = {'value': steps * WINDOW * world / secs, 'unit': UNIT, 'steps': steps, 'files_written': n_files,
+           'mean_file_bytes': n_bytes / max(1, n_files), 'd2h_bytes_per_step': n_bytes / steps + WINDOW * C * 8,
+           'api': 'same call with the PNG files written (device encoder, %d writer threads)' % 4}
+    if rank == 0:                                   # the reference's writer (cv2.imwrite on host label maps) beside it
+        n_host_png = WINDOW
+        t0 = time.perf_counter()
+        run_png(n_host_png, 'host')
+        png['host_cv2_imwrite_images_per_s'] = n_host_png / (time.perf_counter() - t0)
+    barrier()
+    res['from_stride8_logits']['with_png_files'] = png
     return res
 
 

@@ -10,8 +10,10 @@ constructor (``PSEUDO_POLICY[type](cfg)``), same attributes (``class_threshold``
 What changes is where the work happens.  The reference copies conf (f32) + label (int64) of every
 batch to the host (12 B/px) and runs numpy / Python loops there; here logits never leave the GPU:
 each batch goes through phase A as it arrives, a window of batches is then scanned (phase B) and
-masked (phase C) on the device, and only the uint8 pseudo-labels (1 B/px), the per-image class
-counts and the thresholds come back.  PNG encoding stays on the host (thread pool).
+masked (phase C) on the device and ENCODED AS PNG FILES on the device (``hiast_png_encode``); only the finished
+files (typically 2-5 % of the label bytes), the per-image class counts and the thresholds come back, and a small
+thread pool writes the files.  ``png='host'`` (or an overridden ``save_pseudo_label`` hook) keeps the reference's
+``cv2.imwrite`` on uint8 label maps copied back at 1 B/px.
 
 The backbone and the datasets are outside this package: ``initialize`` takes an
 injected ``model`` / ``loader`` (any callable returning ``{'logits': [B,C,H,W]}``; any iterable of
@@ -46,7 +48,7 @@ def _cfg_get(node, path, default=None):
 class BasePseudoGenerator:
 
     def __init__(self, cfg, model=None, loader=None, dataset_len=None, save_dir=None, window_batches=8,
-                 device='cuda', png_workers=4):
+                 device='cuda', png_workers=4, png='device'):
         self.cfg = cfg
         self.statics_class = np.array([0] * self.cfg.dataset.num_classes)                # :18
         self.sample_stats = []                                                           # :19
@@ -58,6 +60,10 @@ class BasePseudoGenerator:
         self._model_arg, self._loader_arg, self._len_arg, self._save_dir_arg = model, loader, dataset_len, save_dir
         self._png_pool = ThreadPoolExecutor(max_workers=png_workers) if png_workers > 0 else None
         self._png_jobs = []
+        if png not in ('device', 'host'):
+            raise ValueError("png must be 'device' or 'host'")
+        self.png = png
+        self._png_encoder = None
         self._engine = None
         self.pow_rounding_certified = True
         self.initialize()
@@ -88,6 +94,23 @@ class BasePseudoGenerator:
         img_name = os.path.splitext(os.path.basename(img_path))[0]
         plbl_save_path = os.path.join(self.pseudo_label_save_dir, '{}_pseudo_label.png'.format(img_name))
         cv2.imwrite(plbl_save_path, plbl.astype(np.uint8))
+
+    def save_pseudo_label_file(self, png_bytes, img_path):
+        """:43-46 with the file already encoded on the device: same name, same decoded pixels."""
+        img_name = os.path.splitext(os.path.basename(img_path))[0]
+        plbl_save_path = os.path.join(self.pseudo_label_save_dir, '{}_pseudo_label.png'.format(img_name))
+        with open(plbl_save_path, 'wb') as f:
+            f.write(png_bytes)
+
+    def _device_png(self):
+        """The device writer is used unless the caller asked for the host one or hooked save_pseudo_label."""
+        return self.png == 'device' and type(self).save_pseudo_label is BasePseudoGenerator.save_pseudo_label
+
+    def _save_file_async(self, png_bytes, img_path):
+        if self._png_pool is None:
+            self.save_pseudo_label_file(png_bytes, img_path)
+        else:
+            self._png_jobs.append(self._png_pool.submit(self.save_pseudo_label_file, png_bytes, img_path))
 
     def _save_async(self, plbl, img_path):
         if self._png_pool is None or type(self).save_pseudo_label is not BasePseudoGenerator.save_pseudo_label:
@@ -215,11 +238,28 @@ def _flush_window(gen, engine, paths, n_images, scan):
         engine.phase_b(0, n_images)
     engine.phase_c(0, n_images)
     engine.mean_prob(0, n_images)
+    if gen._device_png():
+        cpin = getattr(gen, '_pinned_counts', None)
+        if cpin is None or cpin.shape != engine.counts.shape:
+            cpin = gen._pinned_counts = torch.empty(engine.counts.shape, dtype=torch.int64).pin_memory()
+        cpin[:n_images].copy_(engine.counts[:n_images], non_blocking=True)
+        enc = gen._png_encoder
+        if enc is None or (enc.H, enc.W) != tuple(engine.plbl.shape[1:]) or enc.max_images < engine.max_images:
+            enc = gen._png_encoder = ops.PngEncoder(engine.plbl.shape[1], engine.plbl.shape[2], engine.max_images,
+                                                    device=engine.device)
+        gen._wait_png()                               # the previous window's writers still read the pinned blob
+        files = enc.encode_to_host(engine.plbl[:n_images])     # finished PNG files; syncs the stream once
+        counts_h = cpin.numpy()
+        for i in range(n_images):
+            gen._record_image(counts_h[i], paths[i])
+            gen._save_file_async(files[i], paths[i])
+        gen._wait_png()
+        return
     pins = getattr(gen, '_pinned', None)
     if pins is None or pins[0].shape[0] < engine.max_images or pins[0].shape[1:] != engine.plbl.shape[1:]:
         pins = gen._pinned = (torch.empty(engine.plbl.shape, dtype=torch.uint8).pin_memory(),
                               torch.empty(engine.counts.shape, dtype=torch.int64).pin_memory())
-    pins[0][:n_images].copy_(engine.plbl[:n_images], non_blocking=True)   # the only per-pixel traffic back: 1 B/px
+    pins[0][:n_images].copy_(engine.plbl[:n_images], non_blocking=True)   # host PNG path: 1 B/px back
     pins[1][:n_images].copy_(engine.counts[:n_images], non_blocking=True)
     torch.cuda.current_stream(engine.device).synchronize()
     gen._wait_png()                                   # the previous window's encoders still read the pinned buffer

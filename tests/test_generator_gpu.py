@@ -35,8 +35,8 @@ def loader_of(batches):
 
 
 @pytest.mark.parametrize('name', ['ias_small', 'ias_c7'])
-@pytest.mark.parametrize('window_batches', [1, 3, 8])
-def test_ias_generator_run_matches_oracle_and_writes_reference_files(name, window_batches, tmp_path):
+@pytest.mark.parametrize('window_batches,png_mode', [(1, 'device'), (3, 'device'), (8, 'device'), (3, 'host')])
+def test_ias_generator_run_matches_oracle_and_writes_reference_files(name, window_batches, png_mode, tmp_path):
     import cv2
     import hiast_b200
     hiast_b200.register_all()
@@ -45,7 +45,7 @@ def test_ias_generator_run_matches_oracle_and_writes_reference_files(name, windo
     batches = gi.ias_batches(spec)
     save_dir = str(tmp_path / 'run' / 'pseudo_labels')
     gen = PSEUDO_POLICY['IAS'](make_cfg(spec), model=Identity(), loader=loader_of(batches), dataset_len=spec['N'],
-                               save_dir=save_dir, window_batches=window_batches)
+                               save_dir=save_dir, window_batches=window_batches, png=png_mode)
     gen.run()
     oracle = oias.IASOracle(spec['C'], spec['alpha'], spec['beta'], spec['gamma'], spec['cp_gamma'])
     oracle.run([(lg.cuda(), p) for lg, p in batches])
@@ -58,8 +58,12 @@ def test_ias_generator_run_matches_oracle_and_writes_reference_files(name, windo
     assert gen.pow_rounding_certified
     paths = [p for _, ps in batches for p in ps]
     for i, p in enumerate(paths):                                     # PNG payload == oracle label map
-        png = cv2.imread(os.path.join(save_dir, os.path.splitext(p)[0] + '_pseudo_label.png'), cv2.IMREAD_UNCHANGED)
+        file = os.path.join(save_dir, os.path.splitext(p)[0] + '_pseudo_label.png')
+        png = cv2.imread(file, cv2.IMREAD_UNCHANGED)
         assert np.array_equal(png, oracle.labels[i])
+        if png_mode == 'device':                                      # files written by hiast_png_encode: exact bytes
+            from oracle import png as opng
+            assert open(file, 'rb').read() == opng.encode_png(oracle.labels[i].astype(np.uint8))
     root = os.path.join(save_dir, '..')                               # save_data: same files as the reference
     assert np.array_equal(np.load(os.path.join(root, 'class_threshold.npy')), oracle.class_threshold)
     assert np.array_equal(np.load(os.path.join(root, 'statics_class.npy')), oracle.statics_class)
