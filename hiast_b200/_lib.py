@@ -56,6 +56,7 @@ _SIGNATURES = {
     'hiast_png_max_bytes': (_sz, [_i, _i]),
     'hiast_png_segments': (_i, [_i, _i]),
     'hiast_png_encode': (_i, [_vp, _i, _i, _i, _vp, _sz, _vp, _vp, _sz, _vp]),
+    'hiast_resize_nearest_u8': (_i, [_vp, _i, _i, _i, _vp, _i, _i, _d, _d, _vp]),
     'hiast_debug_set_fused_trace': (_i, [_vp]),
     'hiast_debug_loss_scalar': (_i, [_i]),
     'hiast_debug_upsample_v1': (_i, [_i]),

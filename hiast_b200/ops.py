@@ -17,7 +17,7 @@ from ._lib import IGNORE, KEY_ONE, REGION, TERM_CE, TERM_CST, TERM_ENT, TERM_KLD
 __all__ = [
     'ias_key_lo', 'ias_num_bins', 'ias_row_stride', 'ias_new_hist', 'ias_softmax_hist', 'ias_upsample_softmax_hist', 'ias_conf_hist', 'ias_threshold_scan',
     'ias_select', 'ias_meanprob_scan', 'ias_fused_window', 'UNSUPPORTED', 'cbst_sample_hist', 'cbst_quantile', 'copy_paste', 'hard_lut', 'st_loss_fwd', 'st_loss_bwd',
-    'confusion_matrix', 'confusion_from_logits', 'iou_from_confusion', 'PngEncoder',
+    'confusion_matrix', 'confusion_from_logits', 'iou_from_confusion', 'PngEncoder', 'resize_nearest_u8',
 ]
 
 
@@ -415,3 +415,19 @@ class PngEncoder:
         h = self._host.numpy()
         o = off.tolist()
         return [h[o[i]:o[i + 1]] for i in range(len(o) - 1)]
+
+
+def resize_nearest_u8(labels, size):
+    """``cv2.resize(lbl, (W, H), interpolation=cv2.INTER_NEAREST)`` (base_dataset.py:176) for uint8 label maps
+    [N,Hs,Ws] (or [Hs,Ws]) on the device -> [N,H,W]."""
+    require_cuda(labels, torch.uint8, 'labels')
+    single = labels.dim() == 2
+    src = labels.unsqueeze(0) if single else labels
+    n, hs, ws = src.shape
+    hd, wd = int(size[0]), int(size[1])
+    dst = torch.empty((n, hd, wd), dtype=torch.uint8, device=labels.device)
+    ifx = 1.0 / (float(wd) / float(ws))             # OpenCV: inv_scale = dsize / ssize; scale = 1. / inv_scale
+    ify = 1.0 / (float(hd) / float(hs))
+    check(lib().hiast_resize_nearest_u8(ptr(src), n, hs, ws, ptr(dst), hd, wd, ifx, ify, stream_ptr(labels.device)),
+          'hiast_resize_nearest_u8')
+    return dst[0] if single else dst

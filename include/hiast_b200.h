@@ -238,6 +238,13 @@ HIAST_API int hiast_png_segments(int H, int W);
 HIAST_API int hiast_png_encode(const uint8_t* labels, int n_images, int H, int W, uint8_t* out, size_t out_capacity,
                      int64_t* offsets, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- pseudo-label reader side (8f rank 2)  sseg/datasets/loader/base_dataset.py:176 --------- */
+/* `cv2.resize(lbl, (Wd, Hd), interpolation=cv2.INTER_NEAREST)` for n uint8 label maps [n,Hs,Ws] -> [n,Hd,Wd]:
+ * sx = min(floor(x * inv_scale_x), Ws - 1), sy likewise, in double; the caller passes OpenCV's own factors
+ * inv_scale_x = 1.0 / ((double)Wd / Ws), inv_scale_y = 1.0 / ((double)Hd / Hs).                              */
+HIAST_API int hiast_resize_nearest_u8(const uint8_t* src, int n_images, int Hs, int Ws, uint8_t* dst, int Hd, int Wd,
+                            double inv_scale_x, double inv_scale_y, void* stream);
+
 /* ---- host-side test hooks (no GPU needed; used by tests only) --------------------------- */
 /* x^n by double-double repeated squaring, the integer-gamma power used by the scan.          */
 HIAST_API double hiast_testhook_powi(double x, int n);

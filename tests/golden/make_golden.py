@@ -16,6 +16,8 @@ output of the reference's own functions on seeded inputs:
 * metric_*.npz    intersectionAndUnionGPU       utils/metrics.py:6-19
 * copy_paste.npz  CopyPaste.run_original        sseg/datasets/preprocessor.py:79-122
 * ema_update.npz  update_ema_model              utils/utils.py:115-123
+* pseudo_store.npz  BaseDataset.stat_samples_with_class / load_data (pseudo-label branch)
+                                                sseg/datasets/loader/base_dataset.py:61-77,158-178
 
 Inputs that are large are not stored: they are regenerated from a seeded CPU
 ``torch.Generator`` by ``tests/golden_inputs.py`` (same torch build on the GPU
@@ -53,7 +55,12 @@ def install_shim():
     tbx = ModuleType('tensorboardX')
     tbx.SummaryWriter = object
     sys.modules['tensorboardX'] = tbx
-    sys.modules['albumentations'] = ModuleType('albumentations')
+    alb = ModuleType('albumentations')
+    alb.core = ModuleType('albumentations.core')
+    alb.core.composition = ModuleType('albumentations.core.composition')
+    alb.core.composition.BaseCompose = object
+    sys.modules.update({'albumentations': alb, 'albumentations.core': alb.core,
+                        'albumentations.core.composition': alb.core.composition})
     tc = ModuleType('numpy.lib.type_check')
     tc.common_type = np.common_type
     sys.modules['numpy.lib.type_check'] = tc
@@ -307,8 +314,44 @@ def ema_fixture(name):
     print(name, 'params', int(out['n_params']), 'buffers', int(out['n_buffers']))
 
 
+def pseudo_store_fixture(name):
+    """Reader side of the on-disk pseudo-label outputs, run unbound on a SimpleNamespace `self`."""
+    import json
+    import cv2
+    from sseg.datasets.loader.base_dataset import BaseDataset
+    rng = np.random.default_rng(gi.PSEUDO_STORE_SPEC['seed'])
+    C = gi.PSEUDO_STORE_SPEC['C']
+    out = {}
+    with tempfile.TemporaryDirectory() as root:
+        samples = gi.pseudo_store_samples()
+        with open(os.path.join(root, 'samples_with_class.json'), 'w') as f:      # what save_data writes (:60-62)
+            f.write(json.dumps(samples))
+        self = SimpleNamespace(cfg=SimpleNamespace(dataset=SimpleNamespace(num_classes=C)))
+        res = BaseDataset.stat_samples_with_class(self, root)
+        out['stat_json'] = np.array(json.dumps(res))
+        pdir = os.path.join(root, 'pseudo_labels')
+        os.makedirs(pdir)
+        for k, (src, dst) in enumerate(gi.PSEUDO_STORE_SPEC['sizes']):
+            img = rng.integers(0, 256, (dst[0], dst[1], 3)).astype(np.uint8)
+            lbl = gi.pseudo_store_label(k, src)
+            img_path = os.path.join(root, 'img_%d.png' % k)
+            cv2.imwrite(img_path, img)
+            cv2.imwrite(os.path.join(pdir, 'img_%d_pseudo_label.png' % k), lbl)        # pseudo_label_generator.py:46
+            ds = SimpleNamespace(img_path_list=[img_path], lbl_path_list=['unused'], pseudo_dir=pdir, read_label=None)
+            img_r, lbl_r, path_r = BaseDataset.load_data(ds, 0)
+            assert path_r == img_path and img_r.shape == img.shape
+            out['lbl_%d' % k] = lbl_r
+            out['src_sha_%d' % k] = np.array(sha(lbl))
+    np.savez_compressed(os.path.join(HERE, name + '.npz'), **out)
+    print(name, {k: v.shape for k, v in out.items() if k.startswith('lbl_')})
+
+
 def main():
     install_shim()
+    if len(sys.argv) > 1 and sys.argv[1] == 'pseudo_store':
+        pseudo_store_fixture('pseudo_store')
+        return
+    pseudo_store_fixture('pseudo_store')
     ema_fixture('ema_update')
     for name, spec in gi.IAS_SPECS.items():
         ias_fixture(name, spec, store_conf=spec.get('store_conf', True))

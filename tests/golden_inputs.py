@@ -146,3 +146,27 @@ class CopyPasteDataset:
 
     def load_data(self, idx):
         return self.imgs[idx].copy(), self.lbls[idx].copy(), self.names[idx]
+
+
+# ------------------------------------------------------------------ reader side of the on-disk outputs
+PSEUDO_STORE_SPEC = dict(seed=21, C=5, sizes=[((18, 30), (24, 40)), ((12, 24), (16, 32)), ((7, 11), (24, 40)),
+                                               ((30, 50), (24, 40)), ((24, 40), (24, 40)), ((96, 192), (128, 256)),
+                                               ((1, 1), (5, 7)), ((33, 65), (100, 131))])
+
+
+def pseudo_store_samples():
+    """samples_with_class as save_data serialises it (pseudo_label_generator.py:60-62): {class: [[path, pixels], ...]},
+    with ties, an empty class and a class with fewer than 5 files (round(len * 0.1) == 0)."""
+    rng = np.random.default_rng(PSEUDO_STORE_SPEC['seed'])
+    out = {}
+    for c, n in enumerate([23, 0, 4, 15, 10]):
+        px = rng.integers(1, 40, n)
+        out[c] = [['/data/cityscapes/leftImg8bit/train/x/img_%d_%d.png' % (c, i), int(px[i])] for i in range(n)]
+    return out
+
+
+def pseudo_store_label(k, shape):
+    rng = np.random.default_rng(100 + k)
+    lbl = rng.integers(0, 19, shape).astype(np.uint8)
+    lbl[rng.random(shape) < 0.3] = 255
+    return lbl
