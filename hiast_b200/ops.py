@@ -380,7 +380,7 @@ class PngEncoder:
         cap = int(self.max_file * self.max_images / max(1.0, float(expect_ratio))) + 4096
         self._blob = torch.empty(cap, dtype=torch.uint8, device=self.device)
         self._offsets = torch.empty(self.max_images + 1, dtype=torch.int64, device=self.device)
-        self._host = None
+        self._host = {}
         self._host_off = torch.empty(self.max_images + 1, dtype=torch.int64).pin_memory()
 
     def _launch(self, labels):
@@ -404,15 +404,17 @@ class PngEncoder:
             self._launch(labels)
         return self._blob[:total], self._offsets[:n + 1], self._host_off[:n + 1]
 
-    def encode_to_host(self, labels):
-        """List of numpy uint8 arrays (views of one pinned buffer, valid until the next call), one PNG file each."""
+    def encode_to_host(self, labels, slot=0):
+        """List of numpy uint8 arrays, one PNG file each: views of the pinned buffer `slot`, valid until the next call
+        with the same slot (two slots let a writer thread pool drain one window while the next is encoded)."""
         blob, _, off = self.encode(labels)
         total = blob.numel()
-        if self._host is None or self._host.numel() < total:
-            self._host = torch.empty(max(total, 1 << 20), dtype=torch.uint8).pin_memory()
-        self._host[:total].copy_(blob, non_blocking=True)
+        host = self._host.get(slot)
+        if host is None or host.numel() < total:
+            host = self._host[slot] = torch.empty(max(total + total // 4, 1 << 20), dtype=torch.uint8).pin_memory()
+        host[:total].copy_(blob, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
-        h = self._host.numpy()
+        h = host.numpy()
         o = off.tolist()
         return [h[o[i]:o[i + 1]] for i in range(len(o) - 1)]
 

@@ -48,7 +48,7 @@ def _cfg_get(node, path, default=None):
 class BasePseudoGenerator:
 
     def __init__(self, cfg, model=None, loader=None, dataset_len=None, save_dir=None, window_batches=8,
-                 device='cuda', png_workers=4, png='device'):
+                 device='cuda', png_workers=8, png='device'):
         self.cfg = cfg
         self.statics_class = np.array([0] * self.cfg.dataset.num_classes)                # :18
         self.sample_stats = []                                                           # :19
@@ -60,6 +60,8 @@ class BasePseudoGenerator:
         self._model_arg, self._loader_arg, self._len_arg, self._save_dir_arg = model, loader, dataset_len, save_dir
         self._png_pool = ThreadPoolExecutor(max_workers=png_workers) if png_workers > 0 else None
         self._png_jobs = []
+        self._png_slot_jobs = [[], []]              # device PNG path: writers of the two pinned blob buffers
+        self._png_slot = 0
         if png not in ('device', 'host'):
             raise ValueError("png must be 'device' or 'host'")
         self.png = png
@@ -106,11 +108,16 @@ class BasePseudoGenerator:
         """The device writer is used unless the caller asked for the host one or hooked save_pseudo_label."""
         return self.png == 'device' and type(self).save_pseudo_label is BasePseudoGenerator.save_pseudo_label
 
-    def _save_file_async(self, png_bytes, img_path):
+    def _save_file_async(self, png_bytes, img_path, slot):
         if self._png_pool is None:
             self.save_pseudo_label_file(png_bytes, img_path)
         else:
-            self._png_jobs.append(self._png_pool.submit(self.save_pseudo_label_file, png_bytes, img_path))
+            self._png_slot_jobs[slot].append(self._png_pool.submit(self.save_pseudo_label_file, png_bytes, img_path))
+
+    def _wait_png_slot(self, slot):
+        for job in self._png_slot_jobs[slot]:
+            job.result()
+        self._png_slot_jobs[slot] = []
 
     def _save_async(self, plbl, img_path):
         if self._png_pool is None or type(self).save_pseudo_label is not BasePseudoGenerator.save_pseudo_label:
@@ -122,6 +129,8 @@ class BasePseudoGenerator:
         for job in self._png_jobs:
             job.result()
         self._png_jobs = []
+        self._wait_png_slot(0)
+        self._wait_png_slot(1)
 
     def save_data(self):
         """:48-62  same file names, formats and locations (one level above the PNG directory)."""
@@ -247,14 +256,14 @@ def _flush_window(gen, engine, paths, n_images, scan):
         if enc is None or (enc.H, enc.W) != tuple(engine.plbl.shape[1:]) or enc.max_images < engine.max_images:
             enc = gen._png_encoder = ops.PngEncoder(engine.plbl.shape[1], engine.plbl.shape[2], engine.max_images,
                                                     device=engine.device)
-        gen._wait_png()                               # the previous window's writers still read the pinned blob
-        files = enc.encode_to_host(engine.plbl[:n_images])     # finished PNG files; syncs the stream once
-        counts_h = cpin.numpy()
+        slot = gen._png_slot = 1 - gen._png_slot
+        gen._wait_png_slot(slot)                      # the writers of two windows ago still read this pinned blob
+        files = enc.encode_to_host(engine.plbl[:n_images], slot)     # finished PNG files; syncs the stream once
+        counts_h = cpin.numpy().copy()
         for i in range(n_images):
             gen._record_image(counts_h[i], paths[i])
-            gen._save_file_async(files[i], paths[i])
-        gen._wait_png()
-        return
+            gen._save_file_async(files[i], paths[i], slot)
+        return                                        # the files are written while the next window is computed
     pins = getattr(gen, '_pinned', None)
     if pins is None or pins[0].shape[0] < engine.max_images or pins[0].shape[1:] != engine.plbl.shape[1:]:
         pins = gen._pinned = (torch.empty(engine.plbl.shape, dtype=torch.uint8).pin_memory(),
