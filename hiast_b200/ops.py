@@ -17,7 +17,7 @@ from ._lib import IGNORE, KEY_ONE, REGION, TERM_CE, TERM_CST, TERM_ENT, TERM_KLD
 __all__ = [
     'ias_key_lo', 'ias_num_bins', 'ias_row_stride', 'ias_new_hist', 'ias_softmax_hist', 'ias_upsample_softmax_hist', 'ias_conf_hist', 'ias_threshold_scan',
     'ias_select', 'ias_meanprob_scan', 'ias_fused_window', 'UNSUPPORTED', 'cbst_sample_hist', 'cbst_quantile', 'copy_paste', 'hard_lut', 'st_loss_fwd', 'st_loss_bwd',
-    'confusion_matrix', 'confusion_from_logits', 'iou_from_confusion', 'PngEncoder', 'resize_nearest_u8',
+    'confusion_matrix', 'confusion_from_logits', 'iou_from_confusion', 'PngEncoder', 'resize_nearest_u8', 'softmax_flip_sum', 'probs_upsample_argmax',
 ]
 
 
@@ -433,3 +433,35 @@ def resize_nearest_u8(labels, size):
     check(lib().hiast_resize_nearest_u8(ptr(src), n, hs, ws, ptr(dst), hd, wd, ifx, ify, stream_ptr(labels.device)),
           'hiast_resize_nearest_u8')
     return dst[0] if single else dst
+
+
+# ----------------------------------------------------------------------- validator
+def softmax_flip_sum(logits, logits_of_flipped=None, out=None):
+    """softmax(logits, 1) [+ flip_x(softmax(logits_of_flipped, 1))] for f32 [B,C,h,w] (validator.py:37,48-50)."""
+    require_cuda(logits, torch.float32, 'logits')
+    if logits_of_flipped is not None:
+        require_cuda(logits_of_flipped, torch.float32, 'logits_of_flipped')
+        assert logits_of_flipped.shape == logits.shape
+    b, c, h, w = logits.shape
+    if out is None:
+        out = torch.empty_like(logits)
+    check(lib().hiast_softmax_flip_sum(ptr(logits), ptr(logits_of_flipped), b, c, h, w, ptr(out), stream_ptr(logits.device)),
+          'hiast_softmax_flip_sum')
+    return out
+
+
+def probs_upsample_argmax(probs_list, size):
+    """uint8 [B,H,W] = argmax_c sum_s interpolate(probs_s, size, bilinear, align_corners=True) (validator.py:52-55,93)."""
+    n = len(probs_list)
+    for p in probs_list:
+        require_cuda(p, torch.float32, 'probs')
+    b, c = probs_list[0].shape[:2]
+    assert all(p.shape[:2] == (b, c) for p in probs_list)
+    H, W = int(size[0]), int(size[1])
+    label = torch.empty((b, H, W), dtype=torch.uint8, device=probs_list[0].device)
+    ptrs = (C.c_void_p * n)(*[p.data_ptr() for p in probs_list])
+    hs = (C.c_int * n)(*[p.shape[2] for p in probs_list])
+    ws = (C.c_int * n)(*[p.shape[3] for p in probs_list])
+    check(lib().hiast_probs_upsample_argmax(C.cast(ptrs, C.c_void_p), C.cast(hs, C.c_void_p), C.cast(ws, C.c_void_p), n, b, c,
+                                            H, W, ptr(label), stream_ptr(label.device)), 'hiast_probs_upsample_argmax')
+    return label

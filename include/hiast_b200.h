@@ -245,6 +245,17 @@ HIAST_API int hiast_png_encode(const uint8_t* labels, int n_images, int H, int W
 HIAST_API int hiast_resize_nearest_u8(const uint8_t* src, int n_images, int Hs, int Ws, uint8_t* dst, int Hd, int Wd,
                             double inv_scale_x, double inv_scale_y, void* stream);
 
+/* ---- validator: multi-scale / flip softmax sum + arg-max (8f rank 4)  workflows/validator.py:34-55,92-93 ---- */
+/* probs = softmax(logits, dim=1) [+ flip_x(softmax(logits_of_flipped, dim=1))] for float32 [B,C,h,w] tensors
+ * (validator.py:37,46,48-50: `pred_result += torch.flip(flip_logits, dims=[3])`); logits_of_flipped may be NULL.   */
+HIAST_API int hiast_softmax_flip_sum(const float* logits, const float* logits_of_flipped, int B, int C, int h, int w,
+                           float* probs, void* stream);
+/* label u8 [B,H,W] = first-index argmax over C of sum_s interpolate(probs_s [B,C,h_s,w_s], (H,W), bilinear,
+ * align_corners=True), summed in list order (validator.py:52-55,93).  probs_host / h_host / w_host are HOST arrays of
+ * n_scales (<= 8) device pointers / sizes.                                                                     */
+HIAST_API int hiast_probs_upsample_argmax(const float* const* probs_host, const int* h_host, const int* w_host, int n_scales,
+                                int B, int C, int H, int W, uint8_t* label, void* stream);
+
 /* ---- host-side test hooks (no GPU needed; used by tests only) --------------------------- */
 /* x^n by double-double repeated squaring, the integer-gamma power used by the scan.          */
 HIAST_API double hiast_testhook_powi(double x, int n);

@@ -16,6 +16,7 @@ output of the reference's own functions on seeded inputs:
 * metric_*.npz    intersectionAndUnionGPU       utils/metrics.py:6-19
 * copy_paste.npz  CopyPaste.run_original        sseg/datasets/preprocessor.py:79-122
 * ema_update.npz  update_ema_model              utils/utils.py:115-123
+* validator.npz   Validator.get_multi_scale_and_flip_logits + argmax   workflows/validator.py:34-55,92-93
 * pseudo_store.npz  BaseDataset.stat_samples_with_class / load_data (pseudo-label branch)
                                                 sseg/datasets/loader/base_dataset.py:61-77,158-178
 
@@ -346,11 +347,34 @@ def pseudo_store_fixture(name):
     print(name, {k: v.shape for k, v in out.items() if k.startswith('lbl_')})
 
 
+def validator_fixture(name):
+    """Validator.get_multi_scale_and_flip_logits + argmax (workflows/validator.py:34-55,92-93) run unbound on CPU."""
+    from workflows.validator import Validator
+    out = {}
+    for key, spec in gi.VALIDATOR_SPECS.items():
+        model = gi.ToyModel(spec['C'], spec['seed'])
+        imgs = gi.validator_images(spec)
+        self = SimpleNamespace(model=model, cfg=SimpleNamespace(validate=SimpleNamespace(resize_sizes=spec['sizes'],
+                                                                                         is_flip=spec['flip'])))
+        with torch.no_grad():
+            results = Validator.get_multi_scale_and_flip_logits(self, imgs)
+            lbls_pred = results.argmax(dim=1)                         # :93
+        out[key + '_results'] = results.numpy()
+        out[key + '_labels'] = lbls_pred.numpy().astype(np.uint8)
+        out[key + '_imgs_sha'] = np.array(sha(imgs.numpy()))
+    np.savez_compressed(os.path.join(HERE, name + '.npz'), **out)
+    print(name, {k: v.shape for k, v in out.items() if k.endswith('_labels')})
+
+
 def main():
     install_shim()
     if len(sys.argv) > 1 and sys.argv[1] == 'pseudo_store':
         pseudo_store_fixture('pseudo_store')
         return
+    if len(sys.argv) > 1 and sys.argv[1] == 'validator':
+        validator_fixture('validator')
+        return
+    validator_fixture('validator')
     pseudo_store_fixture('pseudo_store')
     ema_fixture('ema_update')
     for name, spec in gi.IAS_SPECS.items():

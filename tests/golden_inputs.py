@@ -170,3 +170,39 @@ def pseudo_store_label(k, shape):
     lbl = rng.integers(0, 19, shape).astype(np.uint8)
     lbl[rng.random(shape) < 0.3] = 255
     return lbl
+
+
+# ------------------------------------------------------------------ validator (multi-scale / flip prediction)
+VALIDATOR_SPECS = {
+    'single_scale': dict(seed=31, B=2, C=19, H=16, W=32, sizes=[[12, 24]], flip=False),
+    'multi_scale_flip': dict(seed=32, B=2, C=19, H=16, W=32, sizes=[[12, 24], [16, 32], [20, 40]], flip=True),
+    'flip_c7_odd': dict(seed=33, B=1, C=7, H=15, W=33, sizes=[[9, 21], [15, 33]], flip=True),
+}
+
+
+class ToyModel:
+    """Deterministic stand-in for the segmentation network: a fixed 1x1 projection of the image plus a position term,
+    evaluated at the size of its input (what SelfTrainingSegmentor.forward returns after its own interpolate)."""
+
+    def __init__(self, C, seed):
+        g = torch.Generator().manual_seed(seed)
+        self.weight = torch.randn(C, 3, generator=g) * 2.0
+        self.C = C
+
+    def eval(self):
+        return self
+
+    def __call__(self, x):
+        w = self.weight.to(x.device)
+        b, _, h, wd = x.shape
+        logits = torch.einsum('kc,bchw->bkhw', w, x)
+        yy = torch.arange(h, device=x.device, dtype=torch.float32).view(1, 1, h, 1)
+        xx = torch.arange(wd, device=x.device, dtype=torch.float32).view(1, 1, 1, wd)
+        kk = torch.arange(self.C, device=x.device, dtype=torch.float32).view(1, self.C, 1, 1)
+        logits = logits + torch.sin(0.37 * yy + 0.11 * xx * (kk + 1.0)) * 1.5
+        return {'logits': logits.contiguous()}
+
+
+def validator_images(spec):
+    g = torch.Generator().manual_seed(spec['seed'])
+    return torch.randn(spec['B'], 3, spec['H'], spec['W'], generator=g)
