@@ -40,5 +40,18 @@ mask = torch.full((2, 64, 64), 255, dtype=torch.uint8, device='cuda')
 ops.copy_paste(img, lbl, mask, img.clone(), lbl.clone(), list(range(14)))
 net = lambda: torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3), torch.nn.BatchNorm2d(8), torch.nn.Linear(7, 1031)).cuda()
 update_ema_model(net(), net(), 0.99)
+# round-1 additions: device PNG writer (fixed + stored segments, odd sizes), nearest resize, validator kernels
+import numpy as np  # noqa: E402
+rng = np.random.default_rng(0)
+for (ph, pw) in ((40, 300), (33, 256), (5, 7)):
+    maps = np.stack([np.repeat(np.repeat(rng.integers(0, 19, ((ph + 7) // 8, (pw + 15) // 16)), 8, 0), 16, 1)[:ph, :pw],
+                     rng.integers(0, 256, (ph, pw))]).astype(np.uint8)
+    ops.PngEncoder(ph, pw, 2).encode_to_host(torch.from_numpy(maps).cuda())
+ops.resize_nearest_u8(lbl, (96, 130))
+zs = [(torch.randn(2, C, h, w, generator=g) * 3).cuda() for h, w in ((24, 48), (32, 64), (17, 33))]
+probs = [ops.softmax_flip_sum(a, a.flip(3).contiguous()) for a in zs]
+ops.probs_upsample_argmax(probs, (32, 64))
+ops.probs_upsample_argmax(probs[:1], (32, 64))
+ops.probs_upsample_argmax(probs + probs[:1], (33, 65))
 torch.cuda.synchronize()
 print('sanitize_small ok')
