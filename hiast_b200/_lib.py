@@ -59,6 +59,7 @@ _SIGNATURES = {
     'hiast_resize_nearest_u8': (_i, [_vp, _i, _i, _i, _vp, _i, _i, _d, _d, _vp]),
     'hiast_softmax_flip_sum': (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     'hiast_probs_upsample_argmax': (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    'hiast_debug_validate_direct': (_i, [_i]),
     'hiast_debug_set_fused_trace': (_i, [_vp]),
     'hiast_debug_loss_scalar': (_i, [_i]),
     'hiast_debug_upsample_v1': (_i, [_i]),

@@ -163,18 +163,19 @@ struct ScaleSet {
 constexpr int kRowsV = 4;  // output rows per thread; adjacent lanes own adjacent columns, so every source load of a warp
                            // covers <= 32 consecutive floats (4 px wide per thread: lanes 3 floats apart, 3x the wavefronts)
 
-// Per-thread interpolation set-up of one scale: none of it depends on the channel.  The first version recomputed it inside the
-// channel loop and was instruction-bound at 52 instructions per (pixel, channel) (ncu: issue active 74 %, 1.1 TB/s).
+// Per-thread interpolation taps of one scale (ATen upsample_bilinear2d, align_corners=True:
+// w1r = rwidth * x; w1 = (int)w1r; w1p = w1 < ws - 1; l1 = w1r - w1; l0 = 1 - l1; rows likewise).  Offsets are relative to
+// (row0, col0) of a window with row pitch `pitch` (the whole plane: row0 = col0 = 0, pitch = ws).
 struct ScaleTaps {
-  int off0[kRowsV];   // h1 * ws + w1
-  int offp[kRowsV];   // ws if h1 < hs - 1 else 0
+  int off0[kRowsV];   // (h1 - row0) * pitch + (w1 - col0)
+  int offp[kRowsV];   // pitch if h1 < hs - 1 else 0
   float h0l[kRowsV], h1l[kRowsV];
   int w1p;
   float w0l, w1l;
 };
 
-__device__ __forceinline__ void make_taps(const ScaleSet& sc, int s, int x, int y0, int H, ScaleTaps& t) {
-  // ATen upsample_bilinear2d (align_corners=True): w1r = rwidth * x; w1 = (int)w1r; w1p = w1 < ws - 1; l1 = w1r - w1; l0 = 1 - l1
+__device__ __forceinline__ void make_taps(const ScaleSet& sc, int s, int x, int y0, int H, int row0, int col0, int pitch,
+                                          ScaleTaps& t) {
   const int hs = sc.h[s], ws = sc.w[s];
   const float w1r = __fmul_rn(sc.rw[s], static_cast<float>(x));
   const int w1 = static_cast<int>(w1r);
@@ -188,11 +189,12 @@ __device__ __forceinline__ void make_taps(const ScaleSet& sc, int s, int x, int 
     const int h1 = static_cast<int>(h1r);
     t.h1l[j] = __fsub_rn(h1r, static_cast<float>(h1));
     t.h0l[j] = __fsub_rn(1.0f, t.h1l[j]);
-    t.off0[j] = h1 * ws + w1;
-    t.offp[j] = h1 < hs - 1 ? ws : 0;
+    t.off0[j] = (h1 - row0) * pitch + (w1 - col0);
+    t.offp[j] = h1 < hs - 1 ? pitch : 0;
   }
 }
 
+template <bool SHARED>
 __device__ __forceinline__ void tap_channel(const float* __restrict__ plane, const ScaleTaps& t, bool first,
                                             float (&acc)[kRowsV]) {
   float v[kRowsV][4];
@@ -200,10 +202,17 @@ __device__ __forceinline__ void tap_channel(const float* __restrict__ plane, con
   for (int j = 0; j < kRowsV; ++j) {  // all loads first
     const float* r0 = plane + t.off0[j];
     const float* r1 = r0 + t.offp[j];
-    v[j][0] = __ldg(r0);
-    v[j][1] = __ldg(r0 + t.w1p);
-    v[j][2] = __ldg(r1);
-    v[j][3] = __ldg(r1 + t.w1p);
+    if (SHARED) {
+      v[j][0] = r0[0];
+      v[j][1] = r0[t.w1p];
+      v[j][2] = r1[0];
+      v[j][3] = r1[t.w1p];
+    } else {
+      v[j][0] = __ldg(r0);
+      v[j][1] = __ldg(r0 + t.w1p);
+      v[j][2] = __ldg(r1);
+      v[j][3] = __ldg(r1 + t.w1p);
+    }
   }
 #pragma unroll
   for (int j = 0; j < kRowsV; ++j) {
@@ -214,11 +223,21 @@ __device__ __forceinline__ void tap_channel(const float* __restrict__ plane, con
   }
 }
 
-// NS = 1..3: the taps of every scale live in registers; NS = 0: any number of scales, taps rebuilt per (channel, scale).
-template <int NS>
-__global__ void __launch_bounds__(kValThreads, NS >= 2 ? 2 : 3) k_probs_upsample_argmax(ScaleSet sc, int B, int C, int H, int W,
-                                                                                       uint8_t* __restrict__ label) {
-  constexpr int kS = NS > 0 ? NS : 1;
+__device__ __forceinline__ void argmax_step(const float (&acc)[kRowsV], int c, float (&best)[kRowsV], int (&arg)[kRowsV]) {
+#pragma unroll
+  for (int j = 0; j < kRowsV; ++j) {
+    if (acc[j] > best[j] || (c == 0)) {
+      best[j] = acc[j];
+      arg[j] = c;
+    }
+  }
+}
+
+// Direct version: every thread reads its taps from global memory (any number of scales and any ratio).  Latency-bound:
+// a warp's 16 loads per (channel, scale) touch ~20 distinct sectors, so few bytes are in flight per register (ncu: 1.1 TB/s,
+// long_scoreboard 14.6 once the index arithmetic is hoisted).  Used when the staged version's windows do not fit.
+__global__ void __launch_bounds__(kValThreads) k_probs_upsample_argmax(ScaleSet sc, int B, int C, int H, int W,
+                                                                       uint8_t* __restrict__ label) {
   const int rgroups = (H + kRowsV - 1) / kRowsV;
   const int64_t n = static_cast<int64_t>(B) * rgroups * W;
   for (int64_t idx = blockIdx.x * static_cast<int64_t>(kValThreads) + threadIdx.x; idx < n;
@@ -227,46 +246,16 @@ __global__ void __launch_bounds__(kValThreads, NS >= 2 ? 2 : 3) k_probs_upsample
     const int64_t rg = idx / W;
     const int y0 = static_cast<int>(rg % rgroups) * kRowsV;
     const int b = static_cast<int>(rg / rgroups);
-    ScaleTaps taps[kS];
-    const float* plane[kS];
-    int plane_sz[kS];
-    if (NS > 0) {
-#pragma unroll
-      for (int s = 0; s < kS; ++s) {
-        make_taps(sc, s, x, y0, H, taps[s]);
-        plane_sz[s] = sc.h[s] * sc.w[s];
-        plane[s] = sc.p[s] + static_cast<int64_t>(b) * C * plane_sz[s];
-      }
-    }
     float best[kRowsV];
     int arg[kRowsV];
-#pragma unroll
-    for (int j = 0; j < kRowsV; ++j) {
-      best[j] = -INFINITY;
-      arg[j] = 0;
-    }
-#pragma unroll 1
     for (int c = 0; c < C; ++c) {
       float acc[kRowsV];
-      if (NS > 0) {
-#pragma unroll
-        for (int s = 0; s < kS; ++s) {
-          tap_channel(plane[s], taps[s], s == 0, acc);
-          plane[s] += plane_sz[s];
-        }
-      } else {
-        for (int s = 0; s < sc.n; ++s) {
-          make_taps(sc, s, x, y0, H, taps[0]);
-          tap_channel(sc.p[s] + (static_cast<int64_t>(b) * C + c) * sc.h[s] * sc.w[s], taps[0], s == 0, acc);
-        }
+      for (int s = 0; s < sc.n; ++s) {
+        ScaleTaps t;
+        make_taps(sc, s, x, y0, H, 0, 0, sc.w[s], t);
+        tap_channel<false>(sc.p[s] + (static_cast<int64_t>(b) * C + c) * sc.h[s] * sc.w[s], t, s == 0, acc);
       }
-#pragma unroll
-      for (int j = 0; j < kRowsV; ++j) {
-        if (acc[j] > best[j] || (c == 0)) {
-          best[j] = acc[j];
-          arg[j] = c;
-        }
-      }
+      argmax_step(acc, c, best, arg);
     }
     uint8_t* o = label + (static_cast<int64_t>(b) * H + y0) * W + x;
 #pragma unroll
@@ -275,10 +264,136 @@ __global__ void __launch_bounds__(kValThreads, NS >= 2 ? 2 : 3) k_probs_upsample
   }
 }
 
+// Staged version: a CTA owns a tile of kRowsV output rows x 256 output columns.  The source window of the tile (<= nr_max rows
+// x nc_max columns per scale and channel) is brought into shared memory with cp.async for a group of `cg` channels at a time,
+// so the bytes in flight no longer depend on registers and every source element is fetched once per tile; the taps are then
+// shared-memory reads.  NS = number of scales (taps of all scales live in registers).
+struct StageGeom {
+  int nr_max[kMaxScales], nc_max[kMaxScales];  // window bounds per scale (nc_max multiple of 4)
+  int base[kMaxScales];                        // float offset of the scale's region for one channel group
+  int per_channel;                             // floats per channel over all scales
+  int cg;                                      // channels per group
+  int vec16;                                   // 16-byte cp.async allowed (every ws % 4 == 0, planes 16-byte aligned)
+};
+
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem))), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem))), "l"(gmem));
+}
+
+template <int NS>
+__global__ void __launch_bounds__(kValThreads) k_probs_upsample_argmax_staged(ScaleSet sc, StageGeom sg, int B, int C, int H,
+                                                                              int W, uint8_t* __restrict__ label) {
+  extern __shared__ __align__(128) float s_win[];
+  const int tiles_x = (W + kValThreads - 1) / kValThreads;
+  const int rgroups = (H + kRowsV - 1) / kRowsV;
+  int tile = blockIdx.x;
+  const int tx = tile % tiles_x;
+  tile /= tiles_x;
+  const int y0 = (tile % rgroups) * kRowsV;
+  const int b = tile / rgroups;
+  const int x0 = tx * kValThreads;
+  const int x = min(x0 + static_cast<int>(threadIdx.x), W - 1);
+  const int x_last = min(x0 + kValThreads - 1, W - 1);
+  const int y_last = min(y0 + kRowsV - 1, H - 1);
+
+  ScaleTaps taps[NS];
+  int row0[NS], col0[NS], nrows[NS], ncols[NS];
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    // window of the tile: rows h1(y0) .. h1(y_last) + 1, columns w1(x0) .. w1(x_last) + 1 (clamped), start aligned down to 4
+    row0[s] = static_cast<int>(__fmul_rn(sc.rh[s], static_cast<float>(y0)));
+    const int row1 = min(static_cast<int>(__fmul_rn(sc.rh[s], static_cast<float>(y_last))) + 1, sc.h[s] - 1);
+    col0[s] = static_cast<int>(__fmul_rn(sc.rw[s], static_cast<float>(x0))) & ~3;
+    const int col1 = min(static_cast<int>(__fmul_rn(sc.rw[s], static_cast<float>(x_last))) + 1, sc.w[s] - 1);
+    nrows[s] = row1 - row0[s] + 1;
+    ncols[s] = min((col1 - col0[s] + 4) & ~3, sg.nc_max[s]);
+    make_taps(sc, s, x, y0, H, row0[s], col0[s], sg.nc_max[s], taps[s]);
+  }
+  float best[kRowsV];
+  int arg[kRowsV];
+  const int group_floats = sg.per_channel * sg.cg;  // one pipeline stage
+  auto issue_group = [&](int c0, float* stage) {
+    const int nc = min(sg.cg, C - c0);
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      const int ws = sc.w[s];
+      const int64_t plane_sz = static_cast<int64_t>(sc.h[s]) * ws;
+      const float* src = sc.p[s] + (static_cast<int64_t>(b) * C + c0) * plane_sz + static_cast<int64_t>(row0[s]) * ws + col0[s];
+      float* dst = stage + static_cast<size_t>(sg.base[s]) * sg.cg;
+      const int pitch = sg.nc_max[s], cstride = sg.nr_max[s] * pitch;
+      if (sg.vec16) {
+        const int q = ncols[s] >> 2, per_c = nrows[s] * q, total = nc * per_c;
+        for (int i = threadIdx.x; i < total; i += kValThreads) {
+          const int c = i / per_c, rem = i - c * per_c, r = rem / q, k = rem - r * q;
+          cp_async16(dst + c * cstride + r * pitch + 4 * k, src + c * plane_sz + static_cast<int64_t>(r) * ws + 4 * k);
+        }
+      } else {
+        const int cols = min(ncols[s], ws - col0[s]);
+        const int per_c = nrows[s] * cols, total = nc * per_c;
+        for (int i = threadIdx.x; i < total; i += kValThreads) {
+          const int c = i / per_c, rem = i - c * per_c, r = rem / cols, k = rem - r * cols;
+          cp_async4(dst + c * cstride + r * pitch + k, src + c * plane_sz + static_cast<int64_t>(r) * ws + k);
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;");
+  };
+  // two-stage pipeline over channel groups: group g + 1 is in flight while group g is consumed
+  issue_group(0, s_win);
+  int stage = 0;
+  for (int c0 = 0; c0 < C; c0 += sg.cg) {
+    const int nc = min(sg.cg, C - c0);
+    if (c0 + sg.cg < C) {
+      issue_group(c0 + sg.cg, s_win + (stage ^ 1) * group_floats);
+      asm volatile("cp.async.wait_group 1;");
+    } else {
+      asm volatile("cp.async.wait_group 0;");
+    }
+    __syncthreads();
+    const float* win = s_win + stage * group_floats;
+    for (int c = 0; c < nc; ++c) {
+      float acc[kRowsV];
+#pragma unroll
+      for (int s = 0; s < NS; ++s)
+        tap_channel<true>(win + static_cast<size_t>(sg.base[s]) * sg.cg + c * (sg.nr_max[s] * sg.nc_max[s]), taps[s], s == 0, acc);
+      argmax_step(acc, c0 + c, best, arg);
+    }
+    __syncthreads();  // the stage may be refilled by the next iteration's issue
+    stage ^= 1;
+  }
+  if (x0 + static_cast<int>(threadIdx.x) < W) {
+    uint8_t* o = label + (static_cast<int64_t>(b) * H + y0) * W + x;
+#pragma unroll
+    for (int j = 0; j < kRowsV; ++j)
+      if (y0 + j < H) o[static_cast<int64_t>(j) * W] = static_cast<uint8_t>(arg[j]);
+  }
+}
+
+template <int NS>
+int launch_staged(const ScaleSet& sc, const StageGeom& sg, size_t smem, int B, int C, int H, int W, uint8_t* label,
+                  cudaStream_t st) {
+  HIAST_CUDA_TRY(cudaFuncSetAttribute(k_probs_upsample_argmax_staged<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(smem)));
+  const long long tiles = static_cast<long long>(B) * ((H + kRowsV - 1) / kRowsV) * ((W + kValThreads - 1) / kValThreads);
+  if (tiles > 0x7FFFFFFFll) return HIAST_ERR_UNSUPPORTED;
+  k_probs_upsample_argmax_staged<NS><<<static_cast<int>(tiles), kValThreads, smem, st>>>(sc, sg, B, C, H, W, label);
+  HIAST_CHECK_LAUNCH();
+  return HIAST_OK;
+}
+
 }  // namespace
 }  // namespace hiast
 
 using namespace hiast;
+
+static int g_val_direct = 0;
+extern "C" int hiast_debug_validate_direct(int on) {
+  g_val_direct = on;
+  return HIAST_OK;
+}
 
 extern "C" int hiast_softmax_flip_sum(const float* logits, const float* logits_of_flipped, int B, int C, int h, int w,
                                       float* probs, void* stream) {
@@ -318,12 +433,39 @@ extern "C" int hiast_probs_upsample_argmax(const float* const* probs_host, const
   const int64_t n = static_cast<int64_t>(B) * ((H + kRowsV - 1) / kRowsV) * W;
   const int grid = static_cast<int>(std::min<int64_t>((n + kValThreads - 1) / kValThreads, static_cast<int64_t>(sm_count()) * 16));
   cudaStream_t st = as_stream(stream);
-  switch (n_scales) {
-    case 1: k_probs_upsample_argmax<1><<<grid, kValThreads, 0, st>>>(sc, B, C, H, W, label); break;
-    case 2: k_probs_upsample_argmax<2><<<grid, kValThreads, 0, st>>>(sc, B, C, H, W, label); break;
-    case 3: k_probs_upsample_argmax<3><<<grid, kValThreads, 0, st>>>(sc, B, C, H, W, label); break;
-    default: k_probs_upsample_argmax<0><<<grid, kValThreads, 0, st>>>(sc, B, C, H, W, label); break;
+  // staged version: window bounds per scale, channel groups sized for a two-stage cp.async pipeline
+  if (n_scales <= 3 && !g_val_direct) {
+    StageGeom sg;
+    sg.per_channel = 0;
+    sg.vec16 = 1;
+    for (int s = 0; s < n_scales; ++s) {
+      sg.nr_max[s] = std::min(sc.h[s], static_cast<int>(static_cast<double>(sc.rh[s]) * (kRowsV - 1)) + 3);
+      sg.nc_max[s] = (std::min(sc.w[s], static_cast<int>(static_cast<double>(sc.rw[s]) * (kValThreads - 1)) + 3) + 3 + 3) & ~3;
+      sg.base[s] = sg.per_channel;
+      sg.per_channel += sg.nr_max[s] * sg.nc_max[s];
+      if (sc.w[s] % 4 != 0 || reinterpret_cast<uintptr_t>(sc.p[s]) % 16 != 0) sg.vec16 = 0;
+    }
+    // All channels in one shot when they fit in 100 KB (2 CTAs per SM cover each other's load phase: measured faster than
+    // a two-stage pipeline over smaller channel groups, the tap phase being shared-memory bound); otherwise two stages.
+    const size_t per_channel_bytes = sizeof(float) * sg.per_channel;
+    size_t smem = 0;
+    if (per_channel_bytes * C <= 100 * 1024) {
+      sg.cg = C;
+      smem = per_channel_bytes * C;
+    } else {
+      sg.cg = static_cast<int>(std::min<size_t>(C, 50 * 1024 / per_channel_bytes));
+      if (sg.cg < 1 && per_channel_bytes * 2 <= 200 * 1024) sg.cg = 1;   // wide windows: one channel per stage
+      smem = per_channel_bytes * sg.cg * 2;
+    }
+    if (sg.cg >= 1) {
+      switch (n_scales) {
+        case 1: return launch_staged<1>(sc, sg, smem, B, C, H, W, label, st);
+        case 2: return launch_staged<2>(sc, sg, smem, B, C, H, W, label, st);
+        default: return launch_staged<3>(sc, sg, smem, B, C, H, W, label, st);
+      }
+    }
   }
+  k_probs_upsample_argmax<<<grid, kValThreads, 0, st>>>(sc, B, C, H, W, label);
   HIAST_CHECK_LAUNCH();
   return HIAST_OK;
 }

@@ -75,8 +75,31 @@ def test_kernels_equal_aten_on_random_logits(B, C, H, W, sizes, flip):
         assert torch.equal(got, ref)
         probs.append(got)
         want = want + F.interpolate(ref, (H, W), mode='bilinear', align_corners=True)
-    lbl = ops.probs_upsample_argmax(probs, (H, W))
+    lbl = ops.probs_upsample_argmax(probs, (H, W))                 # staged kernel (<= 3 scales)
     assert torch.equal(lbl.long(), want.argmax(1))
+    from hiast_b200._lib import lib
+    lib().hiast_debug_validate_direct(1)
+    try:
+        lbl_direct = ops.probs_upsample_argmax(probs, (H, W))      # direct kernel
+    finally:
+        lib().hiast_debug_validate_direct(0)
+    assert torch.equal(lbl_direct, lbl)
+
+
+@pytest.mark.gpu
+def test_five_scales_and_downsampling_take_the_general_paths():
+    from hiast_b200 import ops
+    from torch.nn import functional as F
+    g = torch.Generator(device='cuda').manual_seed(4)
+    B, C, H, W = 2, 6, 40, 72
+    sizes = [(20, 36), (40, 72), (64, 128), (30, 50), (80, 144)]         # up- and down-sampling, widths not multiples of 4
+    probs = [torch.softmax(torch.randn(B, C, h, w, generator=g, device='cuda') * 3, 1) for h, w in sizes]
+    for k in (5, 3, 1):
+        want = sum(F.interpolate(p, (H, W), mode='bilinear', align_corners=True) for p in probs[:k])
+        assert torch.equal(ops.probs_upsample_argmax(probs[:k], (H, W)).long(), want.argmax(1)), k
+    big = [torch.softmax(torch.randn(1, 3, 512, 1024, generator=g, device='cuda'), 1)]   # 8x down-sampling: wide windows
+    want = F.interpolate(big[0], (64, 128), mode='bilinear', align_corners=True)
+    assert torch.equal(ops.probs_upsample_argmax(big, (64, 128)).long(), want.argmax(1))
 
 
 @pytest.mark.gpu

@@ -51,13 +51,21 @@ def main():
             return ops.probs_upsample_argmax(probs, (H, W))
 
         assert torch.equal(fused().long(), torch_chain())
-        ms = time_variants({'torch': torch_chain, 'fused': fused, 'k1': k1_only, 'k2': k2_only})
+        from hiast_b200._lib import lib
+
+        def k2_direct():
+            lib().hiast_debug_validate_direct(1)
+            r = ops.probs_upsample_argmax(probs, (H, W))
+            lib().hiast_debug_validate_direct(0)
+            return r
+
+        ms = time_variants({'torch': torch_chain, 'fused': fused, 'k1': k1_only, 'k2': k2_only, 'k2_direct': k2_direct})
         px = sum(h * w for h, w in sizes)
         k1_bytes = B * C * px * 4 * (3 if flip else 2)
         k2_bytes = B * (C * px * 4 + H * W)
         res[name] = dict(batch=B, torch_ms=ms['torch'], fused_ms=ms['fused'], speedup=ms['torch'] / ms['fused'],
                          k1_ms=ms['k1'], k1_gbs=k1_bytes / ms['k1'] / 1e6, k1_frac_of_measured_peak=k1_bytes / ms['k1'] / 1e-3 / PEAK,
-                         k2_ms=ms['k2'], k2_gbs=k2_bytes / ms['k2'] / 1e6, k2_frac_of_measured_peak=k2_bytes / ms['k2'] / 1e-3 / PEAK,
+                         k2_ms=ms['k2'], k2_direct_ms=ms['k2_direct'], k2_gbs=k2_bytes / ms['k2'] / 1e6, k2_frac_of_measured_peak=k2_bytes / ms['k2'] / 1e-3 / PEAK,
                          images_per_s_fused=B / ms['fused'] * 1e3, images_per_s_torch=B / ms['torch'] * 1e3)
     os.makedirs(os.path.dirname(args.out) or '.', exist_ok=True)
     json.dump(res, open(args.out, 'w'), indent=1)
