@@ -16,7 +16,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libhiast_b200.so')
-SOURCES = ['api.cu', 'ias_phase_a.cu', 'ias_upsample.cu', 'ias_scan_select.cu', 'ias_fused.cu', 'cbst.cu', 'loss.cu', 'confusion.cu', 'copy_paste.cu', 'ema.cu', 'png.cu', 'resize.cu', 'validate.cu']
+SOURCES = ['api.cu', 'ias_phase_a.cu', 'ias_upsample.cu', 'ias_scan_select.cu', 'ias_fused.cu', 'cbst.cu', 'loss.cu', 'confusion.cu', 'copy_paste.cu', 'ema.cu', 'png.cu', 'resize.cu', 'validate.cu', 'ce_general.cu']
 HEADERS = ['common.cuh', 'ias_common.cuh', 'packed_math.cuh', 'scan_math.h', os.path.join('..', '..', 'include', 'hiast_b200.h')]
 
 NVCC_FLAGS = [

@@ -7,8 +7,9 @@ returning a 0-d float32 tensor with autograd; the whole chain of log_softmax / m
 count kernels is one forward kernel + one backward kernel (hiast_b200/csrc/loss.cu).
 
 ``kl_div`` :16-23 and ``mse`` :9-13 (the other consistency-loss types) run on the
-same kernels with a different per-element term.  Not ported (raise NotImplementedError): class ``weights``
-for CE and ``refer_labels`` for CE; ``BCEWithLogits`` is the adversarial warm-up loss and out of scope.
+same kernels with a different per-element term.  ``ce`` with class ``weights`` and / or ``refer_labels`` (no HIAST
+config reaches it) runs on the plain kernels of csrc/ce_general.cu.  ``BCEWithLogits`` is the adversarial warm-up loss
+and out of scope.
 """
 
 from __future__ import annotations
@@ -87,14 +88,41 @@ def fused_terms(logits, plbl, target=None, region='ignored', terms=TERM_CE | TER
     return FusedSelfTrainingLoss.apply(z, t, _prep_labels(plbl), region, terms, cst_mean_all)
 
 
+class GeneralCE(torch.autograd.Function):
+    """CE with class weights and / or a refer_labels region (losses.py:32-36 through :68-89), hiast_ce_general_fwd/bwd."""
+
+    @staticmethod
+    def forward(ctx, z, labels, weights, refer_labels, region, ignore_index):
+        sums, count = ops.ce_general_fwd(z, labels, weights, refer_labels, region, ignore_index)
+        denom = sums[1] if refer_labels is None else count[0].to(torch.float64)
+        ctx.save_for_backward(z, labels, weights, refer_labels, denom)
+        ctx.region, ctx.ignore_index = region, ignore_index
+        return (sums[0] / denom).to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, gout):
+        z, labels, weights, refer_labels, denom = ctx.saved_tensors
+        scale = (gout.to(torch.float64) / denom).to(torch.float32).reshape(1).contiguous()
+        grad = ops.ce_general_bwd(z, labels, weights, refer_labels, ctx.region, ctx.ignore_index, scale)
+        return grad, None, None, None, None, None
+
+
 @LOSS.register('CE')
 def ce(logits, labels, weights=None, ignore_index=IGNORE, refer_labels=None, region='confident'):
-    """losses.py:32-36 with refer_labels=None: nn.CrossEntropyLoss(ignore_index=255), mean over kept pixels."""
-    if weights is not None or refer_labels is not None:
-        raise NotImplementedError('CE with class weights / refer_labels is not ported (SURVEY.md 8f rank 3)')
-    if ignore_index != IGNORE:
-        raise NotImplementedError('only ignore_index=255 is supported')
-    return fused_terms(logits, labels, terms=TERM_CE)[0]
+    """losses.py:32-36.  The hot-path form (no weights, no refer_labels, ignore_index 255) is the CE term of the fused
+    kernel; class ``weights`` (f32 [C]) and ``refer_labels`` (+ ``region``) take the general kernels, which keep the
+    reference's [B,B,H,W] broadcast of the [B,H,W] loss against the [B,1,H,W] mask (:86-87)."""
+    if weights is None and refer_labels is None and ignore_index == IGNORE:
+        return fused_terms(logits, labels, terms=TERM_CE)[0]
+    if refer_labels is not None and region not in ('ignored', 'confident', 'all'):
+        raise ValueError('{} is not a valid region'.format(region))      # losses.py:84
+    z = _prep_logits(logits)
+    w = None
+    if weights is not None:
+        w = torch.as_tensor(weights, dtype=torch.float32, device=z.device).contiguous()
+        assert w.numel() == z.shape[1]
+    r = None if refer_labels is None else _prep_labels(refer_labels)
+    return GeneralCE.apply(z, _prep_labels(labels), w, r, region, int(ignore_index))
 
 
 @LOSS.register('SoftCE')

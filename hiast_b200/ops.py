@@ -17,7 +17,7 @@ from ._lib import IGNORE, KEY_ONE, REGION, TERM_CE, TERM_CST, TERM_ENT, TERM_KLD
 __all__ = [
     'ias_key_lo', 'ias_num_bins', 'ias_row_stride', 'ias_new_hist', 'ias_softmax_hist', 'ias_upsample_softmax_hist', 'ias_conf_hist', 'ias_threshold_scan',
     'ias_select', 'ias_meanprob_scan', 'ias_fused_window', 'UNSUPPORTED', 'cbst_sample_hist', 'cbst_quantile', 'copy_paste', 'hard_lut', 'st_loss_fwd', 'st_loss_bwd',
-    'confusion_matrix', 'confusion_from_logits', 'iou_from_confusion', 'PngEncoder', 'resize_nearest_u8', 'softmax_flip_sum', 'probs_upsample_argmax',
+    'confusion_matrix', 'confusion_from_logits', 'iou_from_confusion', 'PngEncoder', 'resize_nearest_u8', 'softmax_flip_sum', 'probs_upsample_argmax', 'ce_general_fwd', 'ce_general_bwd',
 ]
 
 
@@ -465,3 +465,37 @@ def probs_upsample_argmax(probs_list, size):
     check(lib().hiast_probs_upsample_argmax(C.cast(ptrs, C.c_void_p), C.cast(hs, C.c_void_p), C.cast(ws, C.c_void_p), n, b, c,
                                             H, W, ptr(label), stream_ptr(label.device)), 'hiast_probs_upsample_argmax')
     return label
+
+
+# ------------------------------------------------------ CE with class weights / refer_labels
+def _ce_general_args(z, labels, weights, refer_labels, region):
+    require_cuda(z, torch.float32, 'logits')
+    require_cuda(labels, (torch.uint8, torch.int64), 'labels')
+    if weights is not None:
+        require_cuda(weights, torch.float32, 'weights')
+    if refer_labels is not None:
+        require_cuda(refer_labels, (torch.uint8, torch.int64), 'refer_labels')
+    b, c = z.shape[:2]
+    hw = z[0, 0].numel() if b else 1
+    return (ptr(z), ptr(labels), labels.element_size(), ptr(weights), ptr(refer_labels),
+            refer_labels.element_size() if refer_labels is not None else 0, REGION.get(region, 1)), b, c, hw
+
+
+def ce_general_fwd(z, labels, weights=None, refer_labels=None, region='confident', ignore_index=IGNORE):
+    """(sums f64[2], count i64[1]) of hiast_ce_general_fwd (losses.py:32-36 with weights / refer_labels)."""
+    head, b, c, hw = _ce_general_args(z, labels, weights, refer_labels, region)
+    sums = torch.empty(2, dtype=torch.float64, device=z.device)
+    count = torch.empty(1, dtype=torch.int64, device=z.device)
+    ws = torch.empty(max(lib().hiast_ce_general_workspace_bytes(hw), 8), dtype=torch.uint8, device=z.device)
+    check(lib().hiast_ce_general_fwd(*head, int(ignore_index), b, c, hw, ptr(sums), ptr(count), ptr(ws), ws.numel(),
+                                     stream_ptr(z.device)), 'hiast_ce_general_fwd')
+    return sums, count
+
+
+def ce_general_bwd(z, labels, weights, refer_labels, region, ignore_index, scale):
+    head, b, c, hw = _ce_general_args(z, labels, weights, refer_labels, region)
+    require_cuda(scale, torch.float32, 'scale')
+    grad = torch.empty_like(z)
+    check(lib().hiast_ce_general_bwd(*head, int(ignore_index), b, c, hw, ptr(scale), ptr(grad), stream_ptr(z.device)),
+          'hiast_ce_general_bwd')
+    return grad

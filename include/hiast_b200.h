@@ -256,6 +256,21 @@ HIAST_API int hiast_softmax_flip_sum(const float* logits, const float* logits_of
 HIAST_API int hiast_probs_upsample_argmax(const float* const* probs_host, const int* h_host, const int* w_host, int n_scales,
                                 int B, int C, int H, int W, uint8_t* label, void* stream);
 
+/* ---- CE with class weights / refer_labels (8f rank 3)  sseg/models/modules/losses.py:32-36,68-89 ---------------- */
+/* refer_labels == NULL: sums[0] = sum_{y != ignore} w[y] * nll, sums[1] = sum_{y != ignore} w[y]   (loss = sums[0] / sums[1],
+ *   nn.CrossEntropyLoss(ignore_index, weight)); class_weights f32 [C] or NULL (all ones).
+ * refer_labels != NULL: L = CE(weight, reduction='none') [B,H,W], mask = region(refer_labels) [B,1,H,W]; the product
+ *   broadcasts to [B,B,H,W] (losses.py:86-87): sums[0] = its sum, count[0] = its non-zero count (loss = sums[0] / count[0]);
+ *   labels outside [0,C) contribute 0 (the reference's CrossEntropyLoss would raise on them).
+ * Backward: grad = *scale * d(sums[0])/d(logits), scale a device float (g / sums[1] or g / count[0]).                  */
+HIAST_API size_t hiast_ce_general_workspace_bytes(int64_t HW);
+HIAST_API int hiast_ce_general_fwd(const float* logits, const void* labels, int label_bytes, const float* class_weights,
+                         const void* refer_labels, int refer_bytes, int region, int ignore_index, int B, int C,
+                         int64_t HW, double* sums, int64_t* count, void* workspace, size_t workspace_bytes, void* stream);
+HIAST_API int hiast_ce_general_bwd(const float* logits, const void* labels, int label_bytes, const float* class_weights,
+                         const void* refer_labels, int refer_bytes, int region, int ignore_index, int B, int C,
+                         int64_t HW, const float* scale, float* grad_logits, void* stream);
+
 /* ---- host-side test hooks (no GPU needed; used by tests only) --------------------------- */
 /* x^n by double-double repeated squaring, the integer-gamma power used by the scan.          */
 HIAST_API double hiast_testhook_powi(double x, int n);

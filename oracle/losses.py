@@ -48,6 +48,16 @@ def ce(logits, labels, ignore_index=IGNORE):
     return F.cross_entropy(logits, labels, ignore_index=ignore_index)
 
 
+def ce_general(logits, labels, weights=None, ignore_index=IGNORE, refer_labels=None, region='confident'):
+    """losses.py:32-36 with class weights and / or refer_labels (:68-72, :75-89).  With refer_labels the [B,H,W] loss times
+    the [B,1,H,W] mask broadcasts to [B,B,H,W] exactly as in the reference."""
+    if refer_labels is None:
+        return F.cross_entropy(logits, labels, weight=weights, ignore_index=ignore_index)
+    loss_tensor = F.cross_entropy(logits, labels, weight=weights, reduction='none')
+    loss_tensor = loss_tensor * _region_mask(refer_labels, ignore_index, region).unsqueeze(dim=1)
+    return loss_tensor.sum() / (loss_tensor != 0).sum()
+
+
 def _region_mask(refer_labels, ignore_index, region):
     if region == 'ignored':
         return refer_labels == ignore_index

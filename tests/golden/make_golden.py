@@ -16,6 +16,7 @@ output of the reference's own functions on seeded inputs:
 * metric_*.npz    intersectionAndUnionGPU       utils/metrics.py:6-19
 * copy_paste.npz  CopyPaste.run_original        sseg/datasets/preprocessor.py:79-122
 * ema_update.npz  update_ema_model              utils/utils.py:115-123
+* loss_ce_general.npz  LOSS['CE'] with class weights / refer_labels   sseg/models/modules/losses.py:32-36,68-89
 * validator.npz   Validator.get_multi_scale_and_flip_logits + argmax   workflows/validator.py:34-55,92-93
 * pseudo_store.npz  BaseDataset.stat_samples_with_class / load_data (pseudo-label branch)
                                                 sseg/datasets/loader/base_dataset.py:61-77,158-178
@@ -347,6 +348,22 @@ def pseudo_store_fixture(name):
     print(name, {k: v.shape for k, v in out.items() if k.startswith('lbl_')})
 
 
+def ce_general_fixture(name):
+    """LOSS['CE'] of the reference (losses.py:32-36) with class weights and / or refer_labels, + gradients."""
+    from sseg.models.modules import losses
+    res = {}
+    for key, spec in gi.CE_GENERAL_SPECS.items():
+        z, labels, weights, refer = gi.ce_general_inputs(spec)
+        for case, kw in gi.ce_general_cases(labels, weights, refer).items():
+            zz = z.clone().requires_grad_(True)
+            val = losses.ce(zz, **kw)
+            val.backward()
+            res['%s_%s' % (key, case)] = np.float64(val.item())
+            res['%s_%s_grad' % (key, case)] = zz.grad.numpy()
+    np.savez_compressed(os.path.join(HERE, name + '.npz'), **res)
+    print(name, {k: float(v) for k, v in res.items() if not k.endswith('_grad')})
+
+
 def validator_fixture(name):
     """Validator.get_multi_scale_and_flip_logits + argmax (workflows/validator.py:34-55,92-93) run unbound on CPU."""
     from workflows.validator import Validator
@@ -371,10 +388,14 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == 'pseudo_store':
         pseudo_store_fixture('pseudo_store')
         return
+    if len(sys.argv) > 1 and sys.argv[1] == 'ce_general':
+        ce_general_fixture('loss_ce_general')
+        return
     if len(sys.argv) > 1 and sys.argv[1] == 'validator':
         validator_fixture('validator')
         return
     validator_fixture('validator')
+    ce_general_fixture('loss_ce_general')
     pseudo_store_fixture('pseudo_store')
     ema_fixture('ema_update')
     for name, spec in gi.IAS_SPECS.items():

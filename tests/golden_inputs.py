@@ -206,3 +206,36 @@ class ToyModel:
 def validator_images(spec):
     g = torch.Generator().manual_seed(spec['seed'])
     return torch.randn(spec['B'], 3, spec['H'], spec['W'], generator=g)
+
+
+# ------------------------------------------------------------------ CE with class weights / refer_labels
+CE_GENERAL_SPECS = {
+    'b2_c19': dict(B=2, C=19, H=12, W=20, seed=41),
+    'b3_c7': dict(B=3, C=7, H=9, W=11, seed=42),
+    'b1_c19': dict(B=1, C=19, H=8, W=16, seed=43),
+}
+
+
+def ce_general_inputs(spec):
+    g = torch.Generator().manual_seed(spec['seed'])
+    B, C, H, W = spec['B'], spec['C'], spec['H'], spec['W']
+    z = torch.randn(B, C, H, W, generator=g) * 3
+    labels = torch.randint(0, C, (B, H, W), generator=g)
+    weights = torch.rand(C, generator=g) * 2 + 0.1
+    weights[1] = 0.0                                           # a zero-weight class: its pixels drop out of the non-zero count
+    refer = torch.randint(0, C, (B, H, W), generator=g)
+    refer[torch.rand(B, H, W, generator=g) < 0.5] = 255
+    return z, labels, weights, refer
+
+
+def ce_general_cases(labels, weights, refer):
+    """keyword sets for LOSS['CE'](logits, **kw)."""
+    with_ignore = labels.clone()
+    with_ignore[refer == 255] = 255
+    return {
+        'weighted': dict(labels=with_ignore, weights=weights),
+        'plain_ignore': dict(labels=with_ignore),
+        'refer_ignored': dict(labels=labels, refer_labels=refer, region='ignored'),
+        'refer_confident_w': dict(labels=labels, weights=weights, refer_labels=refer, region='confident'),
+        'refer_all': dict(labels=labels, refer_labels=refer, region='all'),
+    }

@@ -251,3 +251,38 @@ def test_packed_pair_kernels_equal_scalar_kernels(region):
     np.testing.assert_allclose(res[0][0], res[1][0], rtol=1e-6)
     assert int(res[0][1][2]) < (plbl.numel() * 19)           # zeros were really present
     grad_close(res[0][2], res[1][2])
+
+
+# ------------------------------------------------------------------ CE with class weights / refer_labels (losses.py:32-36)
+CE_GOLD = os.path.join(os.path.dirname(__file__), 'golden', 'loss_ce_general.npz')
+
+
+@pytest.mark.parametrize('key', list(gi.CE_GENERAL_SPECS))
+def test_ce_general_matches_reference_fixture_and_oracle(key):
+    import hiast_b200
+    hiast_b200.register_all()
+    from hiast_b200 import LOSS
+    from oracle import losses as oloss
+    gold = np.load(CE_GOLD)
+    spec = gi.CE_GENERAL_SPECS[key]
+    z, labels, weights, refer = gi.ce_general_inputs(spec)
+    for case, kw in gi.ce_general_cases(labels, weights, refer).items():
+        kw_dev = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in kw.items()}
+        zz = z.cuda().requires_grad_(True)
+        val = LOSS['CE'](zz, **kw_dev)
+        val.backward()
+        want, want_grad = gold['%s_%s' % (key, case)], gold['%s_%s_grad' % (key, case)]
+        np.testing.assert_allclose(val.item(), want, rtol=1e-5, err_msg=case)
+        np.testing.assert_allclose(zz.grad.cpu().numpy(), want_grad, rtol=1e-4, atol=1e-8, err_msg=case)
+        zo = z.cuda().requires_grad_(True)                       # the reference expression on CUDA
+        ref = oloss.ce_general(zo, **kw_dev)
+        ref.backward()
+        np.testing.assert_allclose(val.item(), ref.item(), rtol=1e-5, err_msg=case)
+        np.testing.assert_allclose(zz.grad.cpu().numpy(), zo.grad.cpu().numpy(), rtol=1e-4, atol=1e-8, err_msg=case)
+    # uint8 labels take the same path
+    lbl8 = kw_dev['labels'].to(torch.uint8)
+    a = LOSS['CE'](z.cuda(), lbl8, weights=weights.cuda())
+    b = LOSS['CE'](z.cuda(), kw_dev['labels'], weights=weights.cuda())
+    assert a.item() == b.item()
+    with pytest.raises(ValueError):
+        LOSS['CE'](z.cuda(), labels.cuda(), refer_labels=refer.cuda(), region='nowhere')

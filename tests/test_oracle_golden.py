@@ -208,3 +208,18 @@ def test_ema_oracle_vs_reference_fixture():
         assert np.array_equal(new[i], g['new%d' % i])
     for i, b in enumerate(ema.copy_buffers([g['bq%d' % i] for i in range(nb)])):
         assert np.array_equal(b, g['bnew%d' % i])
+
+
+def test_ce_general_oracle_equals_reference_fixture():
+    """LOSS['CE'] with class weights / refer_labels (losses.py:32-36,68-89): values and gradients, CPU torch both sides."""
+    import golden_inputs as gi
+    from oracle import losses as oloss
+    gold = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'loss_ce_general.npz'))
+    for key, spec in gi.CE_GENERAL_SPECS.items():
+        z, labels, weights, refer = gi.ce_general_inputs(spec)
+        for case, kw in gi.ce_general_cases(labels, weights, refer).items():
+            zz = z.clone().requires_grad_(True)
+            val = oloss.ce_general(zz, **kw)
+            val.backward()
+            assert val.item() == gold['%s_%s' % (key, case)], (key, case)
+            assert np.array_equal(zz.grad.numpy(), gold['%s_%s_grad' % (key, case)]), (key, case)
