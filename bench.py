@@ -96,6 +96,8 @@ def run_cpu_port(n_images, steps=1, warmup=0):
     """The reference's CPU path (oracle port, faithful op sequence) on a bounded sample.  images/s."""
     import torch
     from oracle import ias as oias
+    # torchrun exports OMP_NUM_THREADS=1; only one rank runs this leg, so it may use every host core
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
     logits = synth_logits_cpu(n_images)
     batches = [(logits[i:i + GROUP], ['img_%05d.png' % (i + j) for j in range(min(GROUP, n_images - i))])
                for i in range(0, n_images, GROUP)]
