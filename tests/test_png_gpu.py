@@ -88,3 +88,25 @@ def test_invalid_arguments():
         PngEncoder(8, 8, 2).encode(torch.zeros(1, 8, 8, dtype=torch.uint8))     # CPU tensor: no host path
     with pytest.raises(_lib.HiastError):
         PngEncoder(8, 8, 2).encode(torch.zeros(3, 8, 8, dtype=torch.uint8, device='cuda'))
+
+
+def test_random_shapes_and_contents_equal_oracle_bytes():
+    """The same seeded sweep as the host test, device bytes against oracle bytes (runs of every length, every chunk tail)."""
+    from hiast_b200.ops import PngEncoder
+    rng = np.random.default_rng(2024)
+    for trial in range(60):
+        H = int(rng.integers(1, 70))
+        W = int(rng.choice([1, 2, 3, 4, 5, 127, 128, 129, 130, 255, 256, 257, 383, 384, 385, 511, 513, int(rng.integers(1, 700))]))
+        kind = trial % 4
+        if kind == 0:
+            flat = np.repeat(rng.integers(0, 256, H * W), rng.geometric(0.15, H * W))[:H * W]
+        elif kind == 1:
+            row = rng.integers(0, 19, W)
+            flat = np.concatenate([np.where(rng.random(W) < 0.02 * (r % 5), rng.integers(0, 19, W), row) for r in range(H)])
+        elif kind == 2:
+            flat = np.where(rng.random(H * W) < 0.8, 7, 255)
+        else:
+            flat = rng.integers(0, 256, H * W)
+        lbl = flat.astype(np.uint8).reshape(H, W)
+        got = bytes(PngEncoder(H, W, 1).encode_to_host(torch.from_numpy(lbl).cuda())[0])
+        assert got == opng.encode_png(lbl), (trial, H, W, kind)

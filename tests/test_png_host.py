@@ -80,3 +80,26 @@ def test_golden_stream_hash():
 
 
 GOLDEN = (3505, 1597620267)
+
+
+def test_random_shapes_and_contents_round_trip():
+    """Seeded sweep over sizes around the chunk / segment boundaries and contents with runs of every length."""
+    rng = np.random.default_rng(2024)
+    for trial in range(60):
+        H = int(rng.integers(1, 70))
+        W = int(rng.choice([1, 2, 3, 4, 5, 127, 128, 129, 130, 255, 256, 257, 383, 384, 385, 511, 513, int(rng.integers(1, 700))]))
+        kind = trial % 4
+        if kind == 0:                                   # runs of random length (geometric), random values
+            flat = np.repeat(rng.integers(0, 256, H * W), rng.geometric(0.15, H * W))[:H * W]
+        elif kind == 1:                                 # vertical structure: rows repeat with sparse changes
+            row = rng.integers(0, 19, W)
+            flat = np.concatenate([np.where(rng.random(W) < 0.02 * (r % 5), rng.integers(0, 19, W), row) for r in range(H)])
+        elif kind == 2:                                 # two-valued noise (matches and literals interleave at every length)
+            flat = np.where(rng.random(H * W) < 0.8, 7, 255)
+        else:
+            flat = rng.integers(0, 256, H * W)
+        lbl = flat.astype(np.uint8).reshape(H, W)
+        blob = png.encode_png(lbl)
+        assert np.array_equal(png.decode_png(blob), lbl), (H, W, kind)
+        a = cv2.imdecode(np.frombuffer(blob, np.uint8), cv2.IMREAD_UNCHANGED)
+        assert np.array_equal(a.reshape(H, W), lbl), (H, W, kind)
