@@ -63,6 +63,7 @@ _SIGNATURES = {
     'hiast_ce_general_workspace_bytes': (_sz, [_i64]),
     'hiast_ce_general_fwd': (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i64, _vp, _vp, _vp, _sz, _vp]),
     'hiast_ce_general_bwd': (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i64, _vp, _vp, _vp]),
+    'hiast_debug_png_variant': (_i, [_i]),
     'hiast_debug_set_fused_trace': (_i, [_vp]),
     'hiast_debug_loss_scalar': (_i, [_i]),
     'hiast_debug_upsample_v1': (_i, [_i]),

@@ -26,7 +26,11 @@ constexpr uint32_t kFilterUp = 2;
 constexpr int kCrcLevels = 8;
 constexpr int kCrcMaxPiece = 144;
 
-typedef unsigned __int128 u128;
+// 128-bit chunk masks as two words.  (`unsigned __int128` compiles, but nvcc lowers its variable shifts to out-of-line
+// library routines: half of the emit kernel's samples had no source line.)
+struct u128 {
+  unsigned long long lo, hi;
+};
 
 struct PngGeom {
   int H, W, cpr, R, S, Lmax;
@@ -121,17 +125,35 @@ __device__ __forceinline__ uint32_t multmodp(uint32_t a, uint32_t b) {
 }
 
 // ---- 128-bit mask helpers ----
+__device__ __forceinline__ u128 mk(unsigned long long lo, unsigned long long hi) {
+  u128 r;
+  r.lo = lo;
+  r.hi = hi;
+  return r;
+}
+__device__ __forceinline__ u128 operator&(u128 a, u128 b) { return mk(a.lo & b.lo, a.hi & b.hi); }
+__device__ __forceinline__ u128 operator|(u128 a, u128 b) { return mk(a.lo | b.lo, a.hi | b.hi); }
+__device__ __forceinline__ u128 operator~(u128 a) { return mk(~a.lo, ~a.hi); }
+__device__ __forceinline__ bool is_zero(u128 a) { return (a.lo | a.hi) == 0ull; }
+__device__ __forceinline__ u128 shr(u128 a, int s) {  // 0 <= s < 128
+  if (s & 64) return mk(a.hi >> (s & 63), 0ull);
+  return mk((a.lo >> s) | ((a.hi << 1) << (63 - s)), a.hi >> s);
+}
+__device__ __forceinline__ u128 shl_small(u128 a, int s) {  // 0 < s < 64
+  return mk(a.lo << s, (a.hi << s) | (a.lo >> (64 - s)));
+}
+__device__ __forceinline__ u128 low_mask(int n) {  // n low bits set, 0 <= n <= 128
+  if (n >= 128) return mk(~0ull, ~0ull);
+  if (n >= 64) return mk(~0ull, (1ull << (n - 64)) - 1ull);
+  return mk((1ull << n) - 1ull, 0ull);
+}
 __device__ __forceinline__ int ctz128(u128 v) {  // v != 0
-  const unsigned long long lo = static_cast<unsigned long long>(v);
-  if (lo) return __ffsll(static_cast<long long>(lo)) - 1;
-  return 64 + __ffsll(static_cast<long long>(static_cast<unsigned long long>(v >> 64))) - 1;
+  if (v.lo) return __ffsll(static_cast<long long>(v.lo)) - 1;
+  return 64 + __ffsll(static_cast<long long>(v.hi)) - 1;
 }
-__device__ __forceinline__ int popc128(u128 v) {
-  return __popcll(static_cast<unsigned long long>(v)) + __popcll(static_cast<unsigned long long>(v >> 64));
-}
+__device__ __forceinline__ int popc128(u128 v) { return __popcll(v.lo) + __popcll(v.hi); }
 __device__ __forceinline__ u128 make128(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  return (static_cast<u128>(static_cast<unsigned long long>(d) << 32 | c) << 64) |
-         (static_cast<unsigned long long>(b) << 32 | a);
+  return mk(static_cast<unsigned long long>(b) << 32 | a, static_cast<unsigned long long>(d) << 32 | c);
 }
 __device__ __forceinline__ uint32_t byte_mask_to_nibble(uint32_t m) {  // 0xFF/0x00 per byte -> 4 bits
   return (((m & 0x01010101u) * 0x01020408u) >> 24) & 0xFu;
@@ -239,29 +261,28 @@ __device__ __forceinline__ void chunk_masks(const Chunk& c, u128* E3, u128* G) {
     g[k >> 3] |= byte_mask_to_nibble(__vcmpgeu4(c.w[k], 0x90909090u)) << (4 * (k & 7));
   }
   u128 E = make128(e[0], e[1], e[2], e[3]);
-  if (c.prev < 0) E &= ~static_cast<u128>(1);
-  const u128 nmask = c.n >= 128 ? ~static_cast<u128>(0) : ((static_cast<u128>(1) << c.n) - 1);
-  E &= nmask;
-  const u128 a = E & (E >> 1) & (E >> 2);
-  *E3 = a | (a << 1) | (a << 2);
+  if (c.prev < 0) E.lo &= ~1ull;
+  const u128 nmask = low_mask(c.n);
+  E = E & nmask;
+  const u128 a = E & shr(E, 1) & shr(E, 2);
+  *E3 = a | shl_small(a, 1) | shl_small(a, 2);
   *G = make128(g[0], g[1], g[2], g[3]) & nmask;
 }
 
 __device__ __forceinline__ uint32_t chunk_token_bits(const Chunk& c, u128 E3, u128 G) {
-  const u128 nmask = c.n >= 128 ? ~static_cast<u128>(0) : ((static_cast<u128>(1) << c.n) - 1);
-  const u128 lit = ~E3 & nmask;
+  const u128 lit = ~E3 & low_mask(c.n);
   uint32_t bits = 8u * popc128(lit) + popc128(lit & G);
   u128 m = E3;
-  while (m != 0) {
-    m >>= ctz128(m);
+  while (!is_zero(m)) {
+    m = shr(m, ctz128(m));
     const u128 t = ~m;
-    if (t == 0) {
+    if (is_zero(t)) {
       bits += match_bits(128);
       break;
     }
     const int run = ctz128(t);
     bits += match_bits(run);
-    m >>= run;
+    m = shr(m, run);
   }
   return bits;
 }
@@ -430,6 +451,8 @@ struct BitWriter {
   }
 };
 
+// VAR 0: per-lane token loop with an inner literal loop (lanes diverge); VAR 1 (default): one token per iteration, branch-free body.
+template <int VAR>
 __global__ void __launch_bounds__(kPngThreads) k_png_emit(const uint8_t* __restrict__ labels, PngGeom g, int vec,
                                                           PngWorkspace ws, uint8_t* __restrict__ out,
                                                           unsigned long long capacity,
@@ -467,7 +490,7 @@ __global__ void __launch_bounds__(kPngThreads) k_png_emit(const uint8_t* __restr
   const uint8_t* image = labels + static_cast<size_t>(img) * g.H * g.W;
   Chunk c;
   c.n = 0;
-  if (active) load_chunk(image, g.W, r0 + rr, x0, vec != 0, c);
+  if (active && !stored) load_chunk(image, g.W, r0 + rr, x0, vec != 0, c);
 
   // exclusive scan of the chunks' bit counts
   const uint32_t my_bits = ws.chunk_bits[static_cast<size_t>(seg) * kPngThreads + threadIdx.x];
@@ -498,36 +521,73 @@ __global__ void __launch_bounds__(kPngThreads) k_png_emit(const uint8_t* __restr
       const uint8_t* cur = image + static_cast<size_t>(r0 + rr) * g.W + x0;
       const bool has_up = r0 + rr > 0;
       int i = 0;
-      while (i < c.n) {
-        const u128 t = E3 >> i;
-        if (static_cast<uint32_t>(t) & 1u) {
-          const u128 z = ~t;
-          const int run = z == 0 ? 128 : ctz128(z);
-          const uint32_t v = match_token(run, &nb);
-          bw.put(v, nb);
-          i += run;
-        } else {
-          int nl = t == 0 ? 128 : ctz128(t);
-          nl = min(nl, c.n - i);
-          for (int j = 0; j < nl; ++j) {
-            const uint32_t b = (__ldg(cur + i + j) - (has_up ? __ldg(cur + i + j - g.W) : 0u)) & 0xFFu;
-            const uint32_t v = lit_token(b, &nb);
+      if (VAR == 0) {
+        while (i < c.n) {
+          const u128 t = shr(E3, i);
+          if (t.lo & 1ull) {
+            const u128 z = ~t;
+            const int run = is_zero(z) ? 128 : ctz128(z);
+            const uint32_t v = match_token(run, &nb);
             bw.put(v, nb);
+            i += run;
+          } else {
+            int nl = is_zero(t) ? 128 : ctz128(t);
+            nl = min(nl, c.n - i);
+            for (int j = 0; j < nl; ++j) {
+              const uint32_t b = (__ldg(cur + i + j) - (has_up ? __ldg(cur + i + j - g.W) : 0u)) & 0xFFu;
+              const uint32_t v = lit_token(b, &nb);
+              bw.put(v, nb);
+            }
+            i += nl;
           }
-          i += nl;
+        }
+      } else {
+        // One token per iteration, both kinds evaluated and selected: the lanes of a warp (32 different chunks) stay
+        // converged, the warp runs max-over-lanes iterations instead of the union of 32 different branch sequences.
+        while (i < c.n) {
+          const u128 t = shr(E3, i);
+          const bool is_match = (t.lo & 1ull) != 0ull;
+          const u128 z = ~t;
+          const int run = is_zero(z) ? 128 : ctz128(z);
+          uint32_t b = 0;
+          if (!is_match) b = (__ldg(cur + i) - (has_up ? __ldg(cur + i - g.W) : 0u)) & 0xFFu;
+          int nbm, nbl;
+          const uint32_t vm = match_token(max(run, 3), &nbm);
+          const uint32_t vl = lit_token(b, &nbl);
+          bw.put(is_match ? vm : vl, is_match ? nbm : nbl);
+          i += is_match ? run : 1;
         }
       }
       bw.finish();
     }
-  } else if (active) {
-    const uint32_t raw0 = data0 + 5 + static_cast<uint32_t>(rr) * (g.W + 1);
-    if (ck == 0) s_bytes[raw0] = static_cast<uint8_t>(kFilterUp);
-    uint8_t* q = s_bytes + raw0 + 1 + x0;
+  } else {
+    // Stored segment: the raw stream (filter byte + Up-filtered row, row after row) is assembled one aligned shared word per
+    // thread from global memory.  (Writing each thread's own 128 chunk bytes put all lanes of a warp on one bank -- chunks
+    // are 128 bytes apart -- a 32-way conflict on every byte store: 13 % of the kernel on maps with a few stored segments.)
+    const uint32_t raw_base = data0 + 5;
+    const int Wp = g.W + 1;
+    const uint8_t* seg_rows = image + static_cast<size_t>(r0) * g.W;
+    for (uint32_t wi = raw_base / 4 + threadIdx.x; wi < (raw_base + L + 3) / 4; wi += kPngThreads) {
+      int o = static_cast<int>(wi * 4) - static_cast<int>(raw_base);
+      int r = o >= 0 ? o / Wp : 0;
+      int col = o >= 0 ? o - r * Wp : o;  // negative: bytes in front of the raw stream (header, written later)
+      uint32_t word = 0;
 #pragma unroll
-    for (int k = 0; k < 32; ++k) {
-#pragma unroll
-      for (int b = 0; b < 4; ++b)
-        if (4 * k + b < c.n) q[4 * k + b] = static_cast<uint8_t>(c.w[k] >> (8 * b));
+      for (int b = 0; b < 4; ++b) {
+        if (col >= 0 && r < rows) {
+          uint32_t v = kFilterUp;
+          if (col > 0) {
+            const uint8_t* p = seg_rows + static_cast<size_t>(r) * g.W + (col - 1);
+            v = (__ldg(p) - ((r0 + r > 0) ? __ldg(p - g.W) : 0u)) & 0xFFu;
+          }
+          word |= v << (8 * b);
+        }
+        if (++col == Wp) {
+          col = 0;
+          ++r;
+        }
+      }
+      s_buf[wi] = word;
     }
   }
   __syncthreads();
@@ -605,6 +665,12 @@ __global__ void __launch_bounds__(kPngThreads) k_png_emit(const uint8_t* __restr
 
 using namespace hiast;
 
+static int g_png_variant = 1;
+extern "C" int hiast_debug_png_variant(int v) {
+  g_png_variant = v;
+  return HIAST_OK;
+}
+
 extern "C" size_t hiast_png_workspace_bytes(int n_images, int H, int W) {
   PngGeom g;
   if (n_images < 0 || !png_geom(H, W, &g)) return 0;
@@ -647,8 +713,12 @@ extern "C" int hiast_png_encode(const uint8_t* labels, int n_images, int H, int 
   HIAST_CHECK_LAUNCH();
   const size_t smem = (static_cast<size_t>(g.Lmax) + 5 + 3 + 12 + 2 + 6 + 15) / 16 * 16;
   if (smem + 3 * 1024 > 48 * 1024) return HIAST_ERR_UNSUPPORTED;  // cannot happen: Lmax <= 256 * 129
-  k_png_emit<<<n_seg, kPngThreads, smem, st>>>(labels, g, vec, ws, out, static_cast<unsigned long long>(out_capacity),
-                                              reinterpret_cast<const long long*>(offsets), n_images);
+  if (g_png_variant == 0)
+    k_png_emit<0><<<n_seg, kPngThreads, smem, st>>>(labels, g, vec, ws, out, static_cast<unsigned long long>(out_capacity),
+                                                   reinterpret_cast<const long long*>(offsets), n_images);
+  else
+    k_png_emit<1><<<n_seg, kPngThreads, smem, st>>>(labels, g, vec, ws, out, static_cast<unsigned long long>(out_capacity),
+                                                   reinterpret_cast<const long long*>(offsets), n_images);
   HIAST_CHECK_LAUNCH();
   return HIAST_OK;
 }

@@ -285,6 +285,7 @@ HIAST_API double hiast_testhook_threshold_step(const uint32_t* prefix_row_host, 
  * (kind << 32 | unit, begin, end, closer: wait begin, wait end, published; %globaltimer ns), zeroed by the caller;
  * NULL switches tracing off.                                                                   */
 HIAST_API int hiast_debug_validate_direct(int on);   /* 1: hiast_probs_upsample_argmax always takes the direct (unstaged) kernel */
+HIAST_API int hiast_debug_png_variant(int v);         /* emit kernel token loop: 0 nested (divergent), 1 (default) one token per iteration */
 HIAST_API int hiast_debug_set_fused_trace(void* dev_buffer);
 /* on != 0: hiast_st_loss_fwd / _bwd use the scalar vector kernels instead of the packed-pair (f32x2) ones for
  * the SoftCE consistency kind (A/B measurements and cross-checks).                               */
