@@ -369,36 +369,81 @@ __device__ uint32_t crc32_bitwise(const uint8_t* p, int n) {
 
 __global__ void __launch_bounds__(kPngThreads) k_png_offsets(PngGeom g, int n_images, PngWorkspace ws, uint8_t* out,
                                                              unsigned long long capacity, long long* offsets) {
-  for (int img = threadIdx.x; img < n_images; img += blockDim.x) {
-    unsigned long long A = 1, B = 0;
+  // one warp per image, lanes over its segments: sizes and modes, chunk offsets by a warp scan, the Adler-32 state of every
+  // segment start from the prefix sums of the byte sums (A_s = 1 + sum_{k<s} s1_k; B = sum_s (L_s * A_s + s2_s), all mod 65521)
+  const int lane = lane_id(), warp = threadIdx.x >> 5;
+  for (int img = warp; img < n_images; img += kPngThreads / 32) {
     uint32_t pos = 8 + 25;
-    for (int s = 0; s < g.S; ++s) {
-      const int seg = img * g.S + s;
-      const int rows = min(g.R, g.H - s * g.R);
+    unsigned long long a_run = 1, b_acc = 0;
+    for (int s0 = 0; s0 < g.S; s0 += 32) {
+      const int s = s0 + lane;
+      const bool in = s < g.S;
+      const int seg = img * g.S + (in ? s : 0);
+      const int rows = min(g.R, g.H - (in ? s : 0) * g.R);
       const uint32_t L = static_cast<uint32_t>(rows) * (g.W + 1);
       const uint32_t fixed = (ws.seg_bits[seg] + 13 + 7) / 8 + 4;
       const uint32_t stored = 5 + L;
       const uint32_t mode = fixed > stored ? 1u : 0u;
       const uint32_t d = (s == 0 ? 2u : 0u) + (mode ? stored : fixed) + (s == g.S - 1 ? 6u : 0u);
-      ws.seg_off[seg] = pos;
-      ws.seg_len[seg] = d | (mode << 31);
-      pos += 12 + d;
-      B = (B + (L % kAdlerMod) * A + ws.seg_s2[seg] % kAdlerMod) % kAdlerMod;
-      A = (A + ws.seg_s1[seg]) % kAdlerMod;
+      const uint32_t bytes = in ? 12 + d : 0u;
+      unsigned long long s1 = in ? ws.seg_s1[seg] : 0ull;
+      const unsigned long long s2 = in ? ws.seg_s2[seg] % kAdlerMod : 0ull;
+      uint32_t incl = bytes;
+      unsigned long long s1_incl = s1;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        const unsigned long long u = __shfl_up_sync(0xffffffffu, s1_incl, o);
+        if (lane >= o) {
+          incl += t;
+          s1_incl += u;
+        }
+      }
+      if (in) {
+        ws.seg_off[seg] = pos + incl - bytes;
+        ws.seg_len[seg] = d | (mode << 31);
+      }
+      const unsigned long long a_s = (a_run + (s1_incl - s1)) % kAdlerMod;   // Adler A at the start of segment s
+      unsigned long long term = in ? ((L % kAdlerMod) * a_s + s2) % kAdlerMod : 0ull;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) term += __shfl_xor_sync(0xffffffffu, term, o);
+      b_acc = (b_acc + term) % kAdlerMod;
+      pos += __shfl_sync(0xffffffffu, incl, 31);
+      a_run = (a_run + __shfl_sync(0xffffffffu, s1_incl, 31)) % kAdlerMod;
     }
-    ws.adler[img] = static_cast<uint32_t>((B << 16) | A);
-    offsets[img + 1] = pos + 12;
+    if (lane == 0) {
+      ws.adler[img] = static_cast<uint32_t>((b_acc << 16) | a_run);
+      offsets[img + 1] = pos + 12;
+    }
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    long long acc = 0;
-    offsets[0] = 0;
-    for (int i = 0; i < n_images; ++i) {
-      acc += offsets[i + 1];
-      offsets[i + 1] = acc;
+  {  // inclusive scan of the file sizes over the images, 256 at a time
+    __shared__ long long s_scan[kPngThreads / 32];
+    __shared__ long long s_carry;
+    if (threadIdx.x == 0) {
+      s_carry = 0;
+      offsets[0] = 0;
+    }
+    __syncthreads();
+    for (int base = 0; base < n_images; base += kPngThreads) {
+      const int i = base + threadIdx.x;
+      long long v = i < n_images ? offsets[i + 1] : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const long long t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+      }
+      if (lane == 31) s_scan[warp] = v;
+      __syncthreads();
+      long long add = s_carry;
+      for (int k = 0; k < warp; ++k) add += s_scan[k];
+      v += add;
+      if (i < n_images) offsets[i + 1] = v;
+      __syncthreads();
+      if (threadIdx.x == kPngThreads - 1) s_carry = v;
+      __syncthreads();
     }
   }
-  __syncthreads();
   if (static_cast<unsigned long long>(offsets[n_images]) > capacity) return;
   for (int img = threadIdx.x; img < n_images; img += blockDim.x) {
     uint8_t* f = out + offsets[img];
@@ -630,18 +675,16 @@ __global__ void __launch_bounds__(kPngThreads) k_png_emit(const uint8_t* __restr
   const int tn = 1 << lv;
   const uint32_t m = (n_crc + tn - 1) / tn;  // < kCrcMaxPiece
   if (threadIdx.x < tn) {
-    const long long hi = static_cast<long long>(n_crc) - static_cast<long long>(tn - 1 - threadIdx.x) * m;
-    long long lo = hi - m;
-    if (lo < 0) lo = 0;
+    const int hi = static_cast<int>(n_crc) - (tn - 1 - static_cast<int>(threadIdx.x)) * static_cast<int>(m);
+    const int lo = max(hi - static_cast<int>(m), 0);
     uint32_t cr = 0xFFFFFFFFu;
-    for (long long k = lo; k < hi; ++k) cr = s_tab[(cr ^ crc_src[k]) & 0xFFu] ^ (cr >> 8);
+    for (int k = lo; k < hi; ++k) cr = s_tab[(cr ^ crc_src[k]) & 0xFFu] ^ (cr >> 8);
     s_crc[threadIdx.x] = hi > lo ? cr ^ 0xFFFFFFFFu : 0u;
   }
   __syncthreads();
-  for (int l = 0; l < lv; ++l) {
-    const int stride = 1 << l;
-    if (threadIdx.x < tn && (threadIdx.x & (2 * stride - 1)) == 0)
-      s_crc[threadIdx.x] = multmodp(c_crc_shift.v[l][m], s_crc[threadIdx.x]) ^ s_crc[threadIdx.x + stride];
+  for (int l = 0; l < lv; ++l) {  // thread j combines pieces (2j, 2j + 1) << l: the active threads stay contiguous
+    const int left = static_cast<int>(threadIdx.x) << (l + 1);
+    if (left < tn) s_crc[left] = multmodp(c_crc_shift.v[l][m], s_crc[left]) ^ s_crc[left + (1 << l)];
     __syncthreads();
   }
   if (threadIdx.x == 0) put_be32(s_bytes + pad + 8 + d, s_crc[0]);

@@ -110,3 +110,22 @@ def test_random_shapes_and_contents_equal_oracle_bytes():
         lbl = flat.astype(np.uint8).reshape(H, W)
         got = bytes(PngEncoder(H, W, 1).encode_to_host(torch.from_numpy(lbl).cuda())[0])
         assert got == opng.encode_png(lbl), (trial, H, W, kind)
+
+
+def test_many_small_images_and_tall_images():
+    """More than 256 images in one call (block-wide offset scan in several rounds) and more than 32 segments per image."""
+    from hiast_b200.ops import PngEncoder
+    rng = np.random.default_rng(8)
+    maps = rng.integers(0, 4, (300, 6, 10)).astype(np.uint8)
+    files = PngEncoder(6, 10, 300).encode_to_host(torch.from_numpy(maps).cuda())
+    assert len(files) == 300
+    for i in (0, 1, 255, 256, 257, 299):
+        assert bytes(files[i]) == opng.encode_png(maps[i]), i
+    tall = np.repeat(rng.integers(0, 19, (2, 70, 1)), 8, 1).astype(np.uint8)          # W = 8 -> R = 256 rows; use W = 3000
+    tall = np.repeat(rng.integers(0, 19, (2, 90, 30)), 100, 2).astype(np.uint8)       # [2, 90, 3000]: 24 chunks/row, R = 10, S = 9
+    wide = np.repeat(rng.integers(0, 19, (1, 700, 40)), 100, 2).astype(np.uint8)      # [1, 700, 4000]: 32 chunks/row, R = 8, S = 88
+    for arr in (tall, wide):
+        n, H, W = arr.shape
+        files = PngEncoder(H, W, n).encode_to_host(torch.from_numpy(arr).cuda())
+        for i in range(n):
+            assert bytes(files[i]) == opng.encode_png(arr[i])
