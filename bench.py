@@ -464,7 +464,7 @@ def measure_e2e(args, device, rank, world, barrier):
     assert n_files == steps * WINDOW
     png = {'value': steps * WINDOW * world / secs, 'unit': UNIT, 'steps': steps, 'files_written': n_files,
            'mean_file_bytes': n_bytes / max(1, n_files), 'd2h_bytes_per_step': n_bytes / steps + WINDOW * C * 8,
-           'api': 'same call with the PNG files written (device encoder, %d writer threads, double-buffered)' % 8}
+           'api': 'same call with the PNG files written (device encoder, one native hiast_write_files call per window with %d POSIX writers, double-buffered)' % 8}
     if rank == 0:                                   # the reference's writer (cv2.imwrite on host label maps) beside it
         n_host_png = WINDOW
         t0 = time.perf_counter()

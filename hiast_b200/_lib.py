@@ -55,6 +55,7 @@ _SIGNATURES = {
     'hiast_png_workspace_bytes': (_sz, [_i, _i, _i]),
     'hiast_png_max_bytes': (_sz, [_i, _i]),
     'hiast_png_segments': (_i, [_i, _i]),
+    'hiast_write_files': (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     'hiast_png_encode': (_i, [_vp, _i, _i, _i, _vp, _sz, _vp, _vp, _sz, _vp]),
     'hiast_resize_nearest_u8': (_i, [_vp, _i, _i, _i, _vp, _i, _i, _d, _d, _vp]),
     'hiast_softmax_flip_sum': (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),

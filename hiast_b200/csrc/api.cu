@@ -1,5 +1,12 @@
 // Library-level entry points, device queries and host-side test hooks.
+#include <fcntl.h>
+#include <unistd.h>
+
+#include <atomic>
+#include <cerrno>
 #include <mutex>
+#include <thread>
+#include <vector>
 
 #include "common.cuh"
 #include "scan_math.h"
@@ -31,6 +38,7 @@ extern "C" const char* hiast_status_string(int status) {
     case HIAST_ERR_UNSUPPORTED: return "unsupported configuration";
     case HIAST_ERR_CUDA: return "CUDA error (see hiast_last_cuda_error)";
     case HIAST_ERR_WORKSPACE: return "workspace too small";
+    case HIAST_ERR_IO: return "file I/O error (errno in errno_out)";
     default: return "unknown status";
   }
 }
@@ -57,4 +65,52 @@ extern "C" double hiast_testhook_threshold_step(const uint32_t* prefix_row_host,
   if (temp_out) *temp_out = temp;
   if (error_out) *error_out = err;
   return r;
+}
+
+// ---- host-side file writer of the device PNG path -------------------------------------------------------------------
+// pseudo_label_generator.py:43-46 ends in a file per image.  With the files encoded on the device the remaining host work is
+// open / write / close; done from Python threads it is throttled by the interpreter lock (every call boundary re-acquires it
+// while the main thread is busy launching the next window).  One foreign call writes all files of a window with n_threads
+// plain POSIX writers; ctypes releases the lock for the duration.
+extern "C" int hiast_write_files(const char* const* paths, const uint8_t* blob, const int64_t* offsets, int n_files,
+                                 int n_threads, int* errno_out) {
+  if (!paths || !blob || !offsets || n_files < 0) return HIAST_ERR_INVALID_ARG;
+  if (n_files == 0) return HIAST_OK;
+  n_threads = std::max(1, std::min(n_threads, n_files));
+  std::atomic<int> next(0), first_errno(0);
+  auto worker = [&]() {
+    for (;;) {
+      const int i = next.fetch_add(1);
+      if (i >= n_files) return;
+      const int fd = ::open(paths[i], O_WRONLY | O_CREAT | O_TRUNC, 0644);
+      int err = 0;
+      if (fd < 0) {
+        err = errno;
+      } else {
+        const uint8_t* p = blob + offsets[i];
+        int64_t left = offsets[i + 1] - offsets[i];
+        while (left > 0) {
+          const ssize_t w = ::write(fd, p, static_cast<size_t>(left));
+          if (w < 0) {
+            if (errno == EINTR) continue;
+            err = errno;
+            break;
+          }
+          p += w;
+          left -= w;
+        }
+        if (::close(fd) != 0 && err == 0) err = errno;
+      }
+      if (err != 0) {
+        int expected = 0;
+        first_errno.compare_exchange_strong(expected, err);
+      }
+    }
+  };
+  std::vector<std::thread> pool;
+  for (int t = 1; t < n_threads; ++t) pool.emplace_back(worker);
+  worker();
+  for (auto& th : pool) th.join();
+  if (errno_out) *errno_out = first_errno.load();
+  return first_errno.load() == 0 ? HIAST_OK : HIAST_ERR_IO;
 }

@@ -7,6 +7,7 @@ Shapes / dtypes follow include/hiast_b200.h.  No CPU path exists: CPU tensors ra
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -17,7 +18,7 @@ from ._lib import IGNORE, KEY_ONE, REGION, TERM_CE, TERM_CST, TERM_ENT, TERM_KLD
 __all__ = [
     'ias_key_lo', 'ias_num_bins', 'ias_row_stride', 'ias_new_hist', 'ias_softmax_hist', 'ias_upsample_softmax_hist', 'ias_conf_hist', 'ias_threshold_scan',
     'ias_select', 'ias_meanprob_scan', 'ias_fused_window', 'UNSUPPORTED', 'cbst_sample_hist', 'cbst_quantile', 'copy_paste', 'hard_lut', 'st_loss_fwd', 'st_loss_bwd',
-    'confusion_matrix', 'confusion_from_logits', 'iou_from_confusion', 'PngEncoder', 'resize_nearest_u8', 'softmax_flip_sum', 'probs_upsample_argmax', 'ce_general_fwd', 'ce_general_bwd',
+    'confusion_matrix', 'confusion_from_logits', 'iou_from_confusion', 'PngEncoder', 'resize_nearest_u8', 'softmax_flip_sum', 'probs_upsample_argmax', 'ce_general_fwd', 'ce_general_bwd', 'write_files',
 ]
 
 
@@ -381,6 +382,7 @@ class PngEncoder:
         self._blob = torch.empty(cap, dtype=torch.uint8, device=self.device)
         self._offsets = torch.empty(self.max_images + 1, dtype=torch.int64, device=self.device)
         self._host = {}
+        self._last_offsets = {}
         self._host_off = torch.empty(self.max_images + 1, dtype=torch.int64).pin_memory()
 
     def _launch(self, labels):
@@ -404,6 +406,10 @@ class PngEncoder:
             self._launch(labels)
         return self._blob[:total], self._offsets[:n + 1], self._host_off[:n + 1]
 
+    def host_blob(self, slot=0):
+        """(pinned uint8 numpy blob, n+1 offsets) of the last ``encode_to_host(..., slot)``: what ``write_files`` takes."""
+        return self._host[slot].numpy(), self._last_offsets[slot]
+
     def encode_to_host(self, labels, slot=0):
         """List of numpy uint8 arrays, one PNG file each: views of the pinned buffer `slot`, valid until the next call
         with the same slot (two slots let a writer thread pool drain one window while the next is encoded)."""
@@ -416,6 +422,7 @@ class PngEncoder:
         torch.cuda.current_stream(self.device).synchronize()
         h = host.numpy()
         o = off.tolist()
+        self._last_offsets[slot] = o
         return [h[o[i]:o[i + 1]] for i in range(len(o) - 1)]
 
 
@@ -499,3 +506,17 @@ def ce_general_bwd(z, labels, weights, refer_labels, region, ignore_index, scale
     check(lib().hiast_ce_general_bwd(*head, int(ignore_index), b, c, hw, ptr(scale), ptr(grad), stream_ptr(z.device)),
           'hiast_ce_general_bwd')
     return grad
+
+
+def write_files(paths, blob_host, offsets, n_threads=8):
+    """Write file i = blob_host[offsets[i]:offsets[i+1]] to paths[i] with native POSIX writer threads (one foreign call,
+    the interpreter lock is released for its duration).  blob_host: contiguous uint8 numpy array."""
+    n = len(paths)
+    assert len(offsets) == n + 1 and blob_host.dtype == np.uint8 and blob_host.flags['C_CONTIGUOUS']
+    arr = (C.c_char_p * n)(*[os.fsencode(p) for p in paths])
+    off = (C.c_int64 * (n + 1))(*[int(o) for o in offsets])
+    err = C.c_int(0)
+    status = lib().hiast_write_files(C.cast(arr, C.c_void_p), C.c_void_p(blob_host.ctypes.data), C.cast(off, C.c_void_p), n,
+                                     int(n_threads), C.cast(C.pointer(err), C.c_void_p))
+    if status != 0:
+        raise OSError(err.value, 'hiast_write_files: %s' % os.strerror(err.value) if err.value else 'hiast_write_files failed')

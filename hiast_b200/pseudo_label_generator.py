@@ -59,6 +59,7 @@ class BasePseudoGenerator:
         self.window_batches = int(window_batches)
         self._model_arg, self._loader_arg, self._len_arg, self._save_dir_arg = model, loader, dataset_len, save_dir
         self._png_pool = ThreadPoolExecutor(max_workers=png_workers) if png_workers > 0 else None
+        self._png_workers = max(1, int(png_workers))
         self._png_jobs = []
         self._png_slot_jobs = [[], []]              # device PNG path: writers of the two pinned blob buffers
         self._png_slot = 0
@@ -97,10 +98,15 @@ class BasePseudoGenerator:
         plbl_save_path = os.path.join(self.pseudo_label_save_dir, '{}_pseudo_label.png'.format(img_name))
         cv2.imwrite(plbl_save_path, plbl.astype(np.uint8))
 
-    def save_pseudo_label_file(self, png_bytes, img_path):
-        """:43-46 with the file already encoded on the device: same name, same decoded pixels."""
+    def _pseudo_label_path(self, img_path):
+        """:44-45"""
         img_name = os.path.splitext(os.path.basename(img_path))[0]
-        plbl_save_path = os.path.join(self.pseudo_label_save_dir, '{}_pseudo_label.png'.format(img_name))
+        return os.path.join(self.pseudo_label_save_dir, '{}_pseudo_label.png'.format(img_name))
+
+    def save_pseudo_label_file(self, png_bytes, img_path):
+        """:43-46 with the file already encoded on the device: same name, same decoded pixels.  (Hook: when a subclass
+        overrides it, files are handed over one by one; otherwise a window is written by one hiast_write_files call.)"""
+        plbl_save_path = self._pseudo_label_path(img_path)
         with open(plbl_save_path, 'wb') as f:
             f.write(png_bytes)
 
@@ -262,7 +268,15 @@ def _flush_window(gen, engine, paths, n_images, scan):
         counts_h = cpin.numpy().copy()
         for i in range(n_images):
             gen._record_image(counts_h[i], paths[i])
-            gen._save_file_async(files[i], paths[i], slot)
+        if type(gen).save_pseudo_label_file is BasePseudoGenerator.save_pseudo_label_file and gen._png_pool is not None:
+            # one native call writes the whole window (POSIX writer threads, no interpreter lock)
+            blob_host, offsets = enc.host_blob(slot)
+            targets = [gen._pseudo_label_path(p) for p in paths[:n_images]]
+            gen._png_slot_jobs[slot].append(gen._png_pool.submit(ops.write_files, targets, blob_host, offsets,
+                                                                 gen._png_workers))
+        else:
+            for i in range(n_images):
+                gen._save_file_async(files[i], paths[i], slot)
         return                                        # the files are written while the next window is computed
     pins = getattr(gen, '_pinned', None)
     if pins is None or pins[0].shape[0] < engine.max_images or pins[0].shape[1:] != engine.plbl.shape[1:]:

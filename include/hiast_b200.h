@@ -39,6 +39,7 @@ extern "C" {
 #define HIAST_ERR_UNSUPPORTED   -2
 #define HIAST_ERR_CUDA          -3
 #define HIAST_ERR_WORKSPACE     -4
+#define HIAST_ERR_IO            -5
 
 #define HIAST_IGNORE_LABEL      255
 #define HIAST_KEY_ONE           0x3C00  /* fp16 bit pattern of 1.0: the largest histogram key      */
@@ -237,6 +238,11 @@ HIAST_API size_t hiast_png_max_bytes(int H, int W);
 HIAST_API int hiast_png_segments(int H, int W);
 HIAST_API int hiast_png_encode(const uint8_t* labels, int n_images, int H, int W, uint8_t* out, size_t out_capacity,
                      int64_t* offsets, void* workspace, size_t workspace_bytes, void* stream);
+/* HOST function: writes file i = blob_host[offsets_host[i] .. offsets_host[i+1]) to paths_host[i] (create / truncate,
+ * mode 0644) for i < n_files with n_threads POSIX writer threads; *errno_out = first errno (0 if none).  All pointers are
+ * host memory (the blob is the pinned copy of hiast_png_encode's output).  Returns HIAST_ERR_IO if any file failed.     */
+HIAST_API int hiast_write_files(const char* const* paths_host, const uint8_t* blob_host, const int64_t* offsets_host,
+                      int n_files, int n_threads, int* errno_out);
 
 /* ---- pseudo-label reader side (8f rank 2)  sseg/datasets/loader/base_dataset.py:176 --------- */
 /* `cv2.resize(lbl, (Wd, Hd), interpolation=cv2.INTER_NEAREST)` for n uint8 label maps [n,Hs,Ws] -> [n,Hd,Wd]:

@@ -77,3 +77,20 @@ def test_product_path_has_no_cpu_fallback(built_lib):
     assert l.hiast_ema_update(None, None, None, 1, 1024, 0.9, 0.1, None) == -1
     assert l.hiast_ias_fused_window(None, 1, 19, 4, 4, 2, 0, 0.5, 0.9, 8.0, None, None, None, None, None, None, None, None, None,
                                     None, None, 0, 0, None) == -1
+
+
+def test_native_file_writer_is_a_host_function(built_lib, tmp_path):
+    """hiast_write_files (the writer behind the device PNG path) needs no GPU: contents, empty files, error reporting."""
+    import numpy as np
+    from hiast_b200 import ops
+    blob = np.frombuffer(os.urandom(20000), dtype=np.uint8).copy()
+    offs = [0, 7, 7, 9000, 20000]
+    paths = [str(tmp_path / ('f%d_pseudo_label.png' % i)) for i in range(4)]
+    ops.write_files(paths, blob, offs, n_threads=3)
+    for i, p in enumerate(paths):
+        assert open(p, 'rb').read() == blob[offs[i]:offs[i + 1]].tobytes()
+    ops.write_files(paths[:1], blob, [5, 6], n_threads=8)                 # truncates an existing file
+    assert open(paths[0], 'rb').read() == blob[5:6].tobytes()
+    with pytest.raises(OSError) as e:
+        ops.write_files([str(tmp_path / 'missing_dir' / 'x.png')], blob, [0, 4])
+    assert e.value.errno == 2
