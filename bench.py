@@ -454,16 +454,16 @@ def measure_e2e(args, device, rank, world, barrier):
     run_png(WINDOW, 'device')
     barrier()
     t0 = time.perf_counter()
-    n_files, n_bytes = run_png(steps * WINDOW, 'device')
+    n_files, n_bytes = run_png(steps_lr * WINDOW, 'device')
     torch.cuda.synchronize()
     secs = time.perf_counter() - t0
     if world > 1:
         t = torch.tensor([secs], dtype=torch.float64, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         secs = float(t[0])
-    assert n_files == steps * WINDOW
-    png = {'value': steps * WINDOW * world / secs, 'unit': UNIT, 'steps': steps, 'files_written': n_files,
-           'mean_file_bytes': n_bytes / max(1, n_files), 'd2h_bytes_per_step': n_bytes / steps + WINDOW * C * 8,
+    assert n_files == steps_lr * WINDOW
+    png = {'value': steps_lr * WINDOW * world / secs, 'unit': UNIT, 'steps': steps_lr, 'files_written': n_files,
+           'mean_file_bytes': n_bytes / max(1, n_files), 'd2h_bytes_per_step': n_bytes / steps_lr + WINDOW * C * 8,
            'api': 'same call with the PNG files written (device encoder, one native hiast_write_files call per window with %d POSIX writers, double-buffered)' % 8}
     if rank == 0:                                   # the reference's writer (cv2.imwrite on host label maps) beside it
         n_host_png = WINDOW
