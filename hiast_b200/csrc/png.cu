@@ -256,9 +256,14 @@ __device__ __forceinline__ void chunk_masks(const Chunk& c, u128* E3, u128* G) {
   uint32_t e[4] = {0, 0, 0, 0}, g[4] = {0, 0, 0, 0};
 #pragma unroll
   for (int k = 0; k < 32; ++k) {
+    // SWAR byte tests (the __vcmp*4 intrinsics are emulated with more instructions on sm_100):
+    //   byte == 0 of x:  ~(((x & 0x7F..) + 0x7F..) | x) & 0x80..      byte >= 0x90 of w:  ((w & 0x7F..) + 0x70..) & w & 0x80..
     const uint32_t left = (c.w[k] << 8) | (k == 0 ? static_cast<uint32_t>(c.prev & 0xFF) : (c.w[k - 1] >> 24));
-    e[k >> 3] |= byte_mask_to_nibble(__vcmpeq4(c.w[k], left)) << (4 * (k & 7));
-    g[k >> 3] |= byte_mask_to_nibble(__vcmpgeu4(c.w[k], 0x90909090u)) << (4 * (k & 7));
+    const uint32_t x = c.w[k] ^ left;
+    const uint32_t eq = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u;
+    const uint32_t ge = ((c.w[k] & 0x7F7F7F7Fu) + 0x70707070u) & c.w[k] & 0x80808080u;
+    e[k >> 3] |= ((((eq >> 7) * 0x01020408u) >> 24) & 0xFu) << (4 * (k & 7));
+    g[k >> 3] |= ((((ge >> 7) * 0x01020408u) >> 24) & 0xFu) << (4 * (k & 7));
   }
   u128 E = make128(e[0], e[1], e[2], e[3]);
   if (c.prev < 0) E.lo &= ~1ull;
@@ -367,12 +372,14 @@ __device__ uint32_t crc32_bitwise(const uint8_t* p, int n) {
   return c ^ 0xFFFFFFFFu;
 }
 
-__global__ void __launch_bounds__(kPngThreads) k_png_offsets(PngGeom g, int n_images, PngWorkspace ws, uint8_t* out,
+constexpr int kOffsetsThreads = 1024;  // one CTA; a warp per image, 32 images in flight
+
+__global__ void __launch_bounds__(kOffsetsThreads) k_png_offsets(PngGeom g, int n_images, PngWorkspace ws, uint8_t* out,
                                                              unsigned long long capacity, long long* offsets) {
   // one warp per image, lanes over its segments: sizes and modes, chunk offsets by a warp scan, the Adler-32 state of every
   // segment start from the prefix sums of the byte sums (A_s = 1 + sum_{k<s} s1_k; B = sum_s (L_s * A_s + s2_s), all mod 65521)
   const int lane = lane_id(), warp = threadIdx.x >> 5;
-  for (int img = warp; img < n_images; img += kPngThreads / 32) {
+  for (int img = warp; img < n_images; img += kOffsetsThreads / 32) {
     uint32_t pos = 8 + 25;
     unsigned long long a_run = 1, b_acc = 0;
     for (int s0 = 0; s0 < g.S; s0 += 32) {
@@ -417,15 +424,15 @@ __global__ void __launch_bounds__(kPngThreads) k_png_offsets(PngGeom g, int n_im
     }
   }
   __syncthreads();
-  {  // inclusive scan of the file sizes over the images, 256 at a time
-    __shared__ long long s_scan[kPngThreads / 32];
+  {  // inclusive scan of the file sizes over the images, 1024 at a time
+    __shared__ long long s_scan[kOffsetsThreads / 32];
     __shared__ long long s_carry;
     if (threadIdx.x == 0) {
       s_carry = 0;
       offsets[0] = 0;
     }
     __syncthreads();
-    for (int base = 0; base < n_images; base += kPngThreads) {
+    for (int base = 0; base < n_images; base += kOffsetsThreads) {
       const int i = base + threadIdx.x;
       long long v = i < n_images ? offsets[i + 1] : 0;
 #pragma unroll
@@ -440,7 +447,7 @@ __global__ void __launch_bounds__(kPngThreads) k_png_offsets(PngGeom g, int n_im
       v += add;
       if (i < n_images) offsets[i + 1] = v;
       __syncthreads();
-      if (threadIdx.x == kPngThreads - 1) s_carry = v;
+      if (threadIdx.x == kOffsetsThreads - 1) s_carry = v;
       __syncthreads();
     }
   }
@@ -751,7 +758,7 @@ extern "C" int hiast_png_encode(const uint8_t* labels, int n_images, int H, int 
   const int n_seg = n_images * g.S;
   k_png_count<<<n_seg, kPngThreads, 0, st>>>(labels, g, vec, ws);
   HIAST_CHECK_LAUNCH();
-  k_png_offsets<<<1, kPngThreads, 0, st>>>(g, n_images, ws, out, static_cast<unsigned long long>(out_capacity),
+  k_png_offsets<<<1, kOffsetsThreads, 0, st>>>(g, n_images, ws, out, static_cast<unsigned long long>(out_capacity),
                                           reinterpret_cast<long long*>(offsets));
   HIAST_CHECK_LAUNCH();
   const size_t smem = (static_cast<size_t>(g.Lmax) + 5 + 3 + 12 + 2 + 6 + 15) / 16 * 16;
