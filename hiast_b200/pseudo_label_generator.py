@@ -438,3 +438,164 @@ class IASPseudoGenerator(BasePseudoGenerator):
         self.threshold_trace.append(engine.thr_groups[:g].cpu().numpy().copy())
         self.class_threshold = engine.thr_state.cpu().numpy()
         self.class_mean_probs = engine.mean_state.cpu().numpy()
+
+
+def striped_batch_order(n_images_total, window_images, batch_size, rank, world_size):
+    """Dataset indices, batch by batch, that rank ``rank`` processes (windows w = rank, rank + R, ... in the pinned global
+    order; each window cut into batches of ``batch_size``).  Feed it to a ``DataLoader(batch_sampler=...)``."""
+    from .sharded import local_windows, window_images as _win
+    n_windows = (n_images_total + window_images - 1) // window_images
+    batches = []
+    for w in local_windows(n_windows, rank, world_size):
+        i0, n = _win(w, window_images, n_images_total)
+        for k in range(0, n, batch_size):
+            batches.append(list(range(i0 + k, i0 + min(n, k + batch_size))))
+    return batches
+
+
+@PSEUDO_POLICY.register('IAS_SHARDED')
+class ShardedIASPseudoGenerator(IASPseudoGenerator):
+    """IAS pseudo-labelling over R ranks (one process per GPU, ``torch.distributed`` initialised), behind the same
+    ``PSEUDO_POLICY[...](cfg).run()`` call.  New: the reference runs this stage in one process.
+
+    The pinned global order of the target set is cut into windows of ``window_batches`` batches; window w belongs to
+    rank w mod R and **the injected loader yields only this rank's batches, in order** (``striped_batch_order`` gives the
+    batch sampler).  Per owned window: phase A of the NEXT window is issued batch by batch as the model produces logits,
+    then the 19-double threshold state is received from rank r-1 (NCCL / gloo recv), the window is scanned, the state is
+    sent on to rank r+1, and the window is masked, PNG-encoded on the device and written.  At the end the per-group sums
+    are all-gathered and every rank replays the mean-probability EMA, the statistics lists are gathered in global order,
+    and rank 0 writes ``save_data``'s files.  Results are bit-identical to the single-process generator
+    (tests/test_sharded_gloo.py with a host stand-in engine, tests/test_sharded_gpu.py with NCCL)."""
+
+    def __init__(self, cfg, *args, engine_factory=None, process_group=None, **kw):
+        import torch.distributed as dist
+        self._engine_factory = engine_factory
+        self._pg = process_group
+        super().__init__(cfg, *args, **kw)
+        if dist.is_available() and dist.is_initialized():
+            dist.barrier(group=process_group)          # every rank has seen the empty save dir before anyone writes
+
+    def _make_engine(self, logits, alpha=0.0, beta=0.0, gamma=1.0):
+        b, c, h, w = logits.shape
+        group = max(int(_cfg_get(self.cfg, 'pseudo_policy.batch_size', b) or b), b)
+        n = 2 * group * self.window_batches                       # two windows: the next one's phase A runs ahead
+        if self._engine_factory is not None:
+            return self._engine_factory(c, h, w, group, alpha, beta, gamma, self._cp_gamma(), n)
+        return IASEngine(c, h, w, group, alpha, beta, gamma, self._cp_gamma(), n, device=self.device)
+
+    def run(self):
+        import torch.distributed as dist
+        from .sharded import ShardedIAS, window_images
+        if self._already_done():
+            print('%% pseudo labels have existed')
+            return
+        if self.t_dataset is None:
+            raise RuntimeError('the sharded generator needs dataset_len (the size of the whole target set)')
+        C = self.cfg.dataset.num_classes
+        ias = self.cfg.pseudo_policy.ias
+        self.class_threshold = 0.9 * np.ones(C)                                            # :185
+        n_total = len(self.t_dataset)
+        it = self._iterate_logits()
+        engine = drv = None
+        pending = None
+        per_window = {}                                   # global window -> (sample_stats rows, thr_groups)
+        first = next(it, None)
+        if first is not None:
+            engine = self._engine = self._make_engine(first[0], ias.alpha, ias.beta, ias.gamma)
+            engine.thr_state.copy_(torch.from_numpy(self.class_threshold))
+            window = engine.max_images // 2
+            drv = ShardedIAS(engine, window, n_total, process_group=self._pg)
+            drv._stash = []
+            for j, w in enumerate(drv.my_windows):
+                _, n = window_images(w, window, n_total)
+                slot, filled, paths = drv._slot(j), 0, []
+                while filled < n:                          # phase A of window j, batch by batch
+                    logits, p = first if first is not None else next(it)
+                    first = None
+                    _phase_a(engine, logits, slot + filled)
+                    filled += logits.shape[0]
+                    paths += p
+                if filled != n:
+                    raise ValueError('window %d must hold %d images, the loader delivered %d' % (w, n, filled))
+                if pending is not None:                    # ... while the previous window waits for its thresholds
+                    self._finish_sharded_window(drv, per_window, *pending)
+                pending = (w, j, paths, n)
+            if pending is not None:
+                self._finish_sharded_window(drv, per_window, *pending)
+        self._wait_png()
+        self._gather_state(drv, per_window, n_total)
+        rank = dist.get_rank(self._pg) if dist.is_available() and dist.is_initialized() else 0
+        if rank == 0:
+            self.save_data()
+
+    def _finish_sharded_window(self, drv, per_window, w, j, paths, n):
+        import torch.distributed as dist
+        e = drv.engine
+        slot = drv._slot(j)
+        if w > 0 and drv.world > 1:
+            dist.recv(e.thr_state, src=drv._global((drv.rank - 1) % drv.world), group=drv.pg)
+        e.phase_b(slot, n)
+        if w < drv.n_windows_total - 1 and drv.world > 1:
+            dist.send(e.thr_state, dst=drv._global((drv.rank + 1) % drv.world), group=drv.pg)
+        e.phase_c(slot, n)
+        g0, g = slot // e.B, (n + e.B - 1) // e.B
+        drv._stash.append(torch.stack([torch.as_tensor(e.confsum[g0:g0 + g]), e.group_counts(slot, n)], dim=1).clone())
+        plbl, counts = e.plbl[slot:slot + n], torch.as_tensor(e.counts[slot:slot + n])
+        rows_before = len(self.sample_stats)
+        if torch.is_tensor(plbl) and plbl.is_cuda and self._device_png():
+            enc = self._png_encoder
+            if enc is None or (enc.H, enc.W) != tuple(plbl.shape[1:]) or enc.max_images < n:
+                enc = self._png_encoder = ops.PngEncoder(plbl.shape[1], plbl.shape[2], e.max_images // 2, device=e.device)
+            pslot = self._png_slot = 1 - self._png_slot
+            self._wait_png_slot(pslot)
+            enc.encode_to_host(plbl, pslot)
+            counts_h = counts.cpu().numpy()
+            blob_host, offsets = enc.host_blob(pslot)
+            targets = [self._pseudo_label_path(p) for p in paths]
+            if self._png_pool is not None:
+                self._png_slot_jobs[pslot].append(self._png_pool.submit(ops.write_files, targets, blob_host, offsets,
+                                                                        self._png_workers))
+            else:
+                ops.write_files(targets, blob_host, offsets, self._png_workers)
+        else:
+            plbl_h = plbl.cpu().numpy() if torch.is_tensor(plbl) else np.asarray(plbl)
+            counts_h = counts.cpu().numpy()
+            for i in range(n):
+                self._save_async(plbl_h[i].copy(), paths[i])
+            self._wait_png()
+        for i in range(n):
+            self._record_image(counts_h[i], paths[i])
+        thr_groups = torch.as_tensor(e.thr_groups[g0:g0 + g]).cpu().numpy().copy()
+        per_window[w] = (self.sample_stats[rows_before:], thr_groups)
+
+    def _gather_state(self, drv, per_window, n_total):
+        """Global results on every rank: thresholds / mean probabilities / class totals from the driver, the per-image
+        statistics lists re-assembled in the global image order."""
+        import torch.distributed as dist
+        C = self.cfg.dataset.num_classes
+        if drv is None:
+            return
+        thr, mean, statics = drv.finish_state()
+        self.class_threshold = thr.cpu().numpy().copy()
+        self.class_mean_probs = mean.cpu().numpy().copy()
+        self.pow_rounding_certified = drv.engine.check_errors() if hasattr(drv.engine, 'check_errors') else True
+        parts = [per_window]
+        if drv.world > 1:
+            parts = [None] * drv.world
+            dist.all_gather_object(parts, per_window, group=drv.pg)
+        merged = {}
+        for p in parts:
+            merged.update(p)
+        self.sample_stats, self.threshold_trace = [], []
+        self.samples_class = {i: [] for i in range(C)}
+        self.statics_class = np.array([0] * C)
+        for w in sorted(merged):
+            rows, thr_groups = merged[w]
+            self.threshold_trace.append(thr_groups)
+            for row in rows:
+                self.sample_stats.append(row)
+                for k, v in row.items():
+                    if k != 'file':
+                        self.samples_class[k].append([row['file'], v])
+                        self.statics_class[k] += v
+        assert np.array_equal(self.statics_class, statics.cpu().numpy()), 'gathered statistics disagree with the device sums'

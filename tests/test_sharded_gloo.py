@@ -87,3 +87,84 @@ def test_sharded_equals_unsharded_equals_oracle(world, tmp_path):
     assert np.array_equal(plbl, np.stack(oracle.labels))
     thr_groups = np.concatenate([by_window[w][1] for w in range(n_win)])
     assert np.array_equal(thr_groups, np.stack(oracle.threshold_trace))
+
+
+# ----------------------------------------------------------------- the reference-facing sharded generator
+def _cfg(s):
+    from types import SimpleNamespace
+    return SimpleNamespace(
+        dataset=SimpleNamespace(num_classes=s['C']),
+        pseudo_policy=SimpleNamespace(type='IAS_SHARDED', batch_size=s['B'],
+                                      ias=SimpleNamespace(alpha=s['alpha'], beta=s['beta'], gamma=s['gamma'])),
+        preprocessor=SimpleNamespace(copy_paste=SimpleNamespace(gamma=s['cp_gamma'])))
+
+
+class _Identity:
+    def __call__(self, x):
+        return {'logits': x}
+
+
+def _gen_worker(rank, world, port, out_dir):
+    import json
+    import sys
+    sys.path.insert(0, os.path.dirname(__file__))
+    from host_engine import HostEngine
+    import hiast_b200
+    hiast_b200.register_all()
+    from hiast_b200 import PSEUDO_POLICY
+    from hiast_b200.pseudo_label_generator import striped_batch_order
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        s = SPEC
+        batches = gi.ias_batches(s)                         # global order, batch k = images 2k, 2k+1
+        window_batches = 2
+        order = striped_batch_order(s['N'], window_batches * s['B'], s['B'], rank, world)
+        loader = [{'images': batches[idx[0] // s['B']][0], 'image_paths': batches[idx[0] // s['B']][1]} for idx in order]
+        assert all(len(idx) == len(b['image_paths']) for idx, b in zip(order, loader))
+        gen = PSEUDO_POLICY['IAS_SHARDED'](_cfg(s), model=_Identity(), loader=loader, dataset_len=s['N'],
+                                           save_dir=os.path.join(out_dir, 'run', 'pseudo_labels'),
+                                           window_batches=window_batches, device='cpu', engine_factory=HostEngine)
+        gen.run()
+        np.savez(os.path.join(out_dir, 'gen_rank%d.npz' % rank), thr=gen.class_threshold, mean=gen.class_mean_probs,
+                 statics=gen.statics_class, trace=np.concatenate(gen.threshold_trace),
+                 stats=np.array(json.dumps(gen.sample_stats)), samples=np.array(json.dumps(gen.samples_class)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world', [2, 3])
+def test_sharded_generator_equals_oracle_and_writes_the_reference_files(world, tmp_path):
+    import json
+    cv2 = pytest.importorskip('cv2')
+    port = _free_port()
+    mp.spawn(_gen_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    s = SPEC
+    oracle = oias.IASOracle(s['C'], s['alpha'], s['beta'], s['gamma'], s['cp_gamma'])
+    batches = gi.ias_batches(s)
+    oracle.run(batches)
+    for r in range(world):                                  # every rank holds the same global results
+        got = np.load(os.path.join(str(tmp_path), 'gen_rank%d.npz' % r))
+        assert np.array_equal(got['thr'], oracle.class_threshold)
+        assert np.array_equal(got['statics'], oracle.statics_class)
+        assert np.array_equal(got['trace'], np.stack(oracle.threshold_trace))
+        np.testing.assert_allclose(got['mean'], oracle.class_mean_probs, rtol=1e-6)
+        assert json.loads(str(got['stats'])) == json.loads(json.dumps(oracle.sample_stats))
+        assert json.loads(str(got['samples'])) == json.loads(json.dumps(oracle.samples_class))
+    save_dir = os.path.join(str(tmp_path), 'run', 'pseudo_labels')
+    paths = [p for _, ps in batches for p in ps]
+    assert len(os.listdir(save_dir)) == len(paths)
+    for i, p in enumerate(paths):
+        png = cv2.imread(os.path.join(save_dir, os.path.splitext(p)[0] + '_pseudo_label.png'), cv2.IMREAD_UNCHANGED)
+        assert np.array_equal(png, oracle.labels[i])
+    root = os.path.join(save_dir, '..')                     # written once, by rank 0
+    assert np.array_equal(np.load(os.path.join(root, 'class_threshold.npy')), oracle.class_threshold)
+    assert json.load(open(os.path.join(root, 'samples_with_class.json'))) == json.loads(json.dumps(oracle.samples_class))
+
+
+def test_striped_batch_order():
+    from hiast_b200.pseudo_label_generator import striped_batch_order
+    assert striped_batch_order(9, 4, 2, 0, 2) == [[0, 1], [2, 3], [8]]
+    assert striped_batch_order(9, 4, 2, 1, 2) == [[4, 5], [6, 7]]
+    assert striped_batch_order(3, 4, 2, 1, 2) == []
