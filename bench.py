@@ -334,7 +334,7 @@ def measure_e2e(args, device, rank, world, barrier):
     """IASPseudoGenerator.run() on pinned host logits: H2D per batch + D2H per label map inside the timed region."""
     import torch
     from types import SimpleNamespace
-    from hiast_b200.pseudo_label_generator import IASPseudoGenerator
+    from hiast_b200.pseudo_label_generator import IASPseudoGenerator, ShardedIASPseudoGenerator
     import shutil
     import tempfile
     import torch.distributed as dist
@@ -361,7 +361,14 @@ def measure_e2e(args, device, rank, world, barrier):
         pseudo_policy=SimpleNamespace(type='IAS', batch_size=GROUP, ias=SimpleNamespace(alpha=ALPHA, beta=BETA, gamma=GAMMA)),
         preprocessor=SimpleNamespace(copy_paste=SimpleNamespace(gamma=CP_GAMMA)))
 
-    class Gen(IASPseudoGenerator):
+    # N > 1: the same call through PSEUDO_POLICY['IAS_SHARDED'] -- every rank feeds its own windows of one global job of
+    # n_images * world images, the threshold state travels rank to rank (NCCL) exactly as in the device-resident run.
+    Base = ShardedIASPseudoGenerator if world > 1 else IASPseudoGenerator
+
+    def total(n_images):
+        return n_images * world if world > 1 else None
+
+    class Gen(Base):
         def save_pseudo_label(self, plbl, img_path):      # PNG encode/write excluded, as in the CPU baseline
             self.last = plbl
 
@@ -369,7 +376,7 @@ def measure_e2e(args, device, rank, world, barrier):
             pass
 
     def run(n_images):
-        gen = Gen(cfg, model=Identity(), loader=loader(n_images), dataset_len=None, save_dir=tempfile.mkdtemp(),
+        gen = Gen(cfg, model=Identity(), loader=loader(n_images), dataset_len=total(n_images), save_dir=tempfile.mkdtemp(),
                   window_batches=WINDOW // GROUP, device=device)
         gen.run()
         return gen
@@ -392,8 +399,9 @@ def measure_e2e(args, device, rank, world, barrier):
     res = {'value': steps * WINDOW * world / secs, 'unit': UNIT, 'steps': steps,
            'h2d_bytes_per_step': WINDOW * C * H * W * 4,
            'd2h_bytes_per_step': WINDOW * (H * W + C * 8) + (WINDOW // GROUP) * C * 8,
-           'api': "PSEUDO_POLICY['IAS'](cfg).run() on pinned host logits, identity model, PNG write stubbed; "
-                  "N>1: independent replicas of the call, one per GPU"}
+           'api': ("PSEUDO_POLICY['IAS'](cfg).run() on pinned host logits, identity model, PNG write stubbed" if world == 1 else
+                   "PSEUDO_POLICY['IAS_SHARDED'](cfg).run() on pinned host logits (one global job, windows striped over the "
+                   "ranks, NCCL threshold hand-off), identity model, PNG write stubbed")}
 
     # Same call fed with what the network actually produces: stride-8 logits [19,129,257] (2.5 MB per image instead of
     # 159 MB); the bilinear up-sampling of self_training_segmentor.py:27 is fused into phase A.
@@ -412,7 +420,7 @@ def measure_e2e(args, device, rank, world, barrier):
             yield {'images': host_lr[j:j + GROUP], 'image_paths': ['img_%06d.png' % (i + k) for k in range(GROUP)]}
 
     def run_lr(n_images):
-        gen = Gen(cfg, model=LowRes(), loader=loader_lr(n_images), dataset_len=None, save_dir=tempfile.mkdtemp(),
+        gen = Gen(cfg, model=LowRes(), loader=loader_lr(n_images), dataset_len=total(n_images), save_dir=tempfile.mkdtemp(),
                   window_batches=WINDOW // GROUP, device=device)
         gen.run()
         return gen
@@ -436,15 +444,21 @@ def measure_e2e(args, device, rank, world, barrier):
 
     # ... and with the on-disk output of the reference (pseudo_label_generator.py:43-46) INCLUDED: the label maps are
     # encoded as PNG files on the device (hiast_png_encode), only the files cross PCIe, a thread pool writes them.
-    class GenPng(IASPseudoGenerator):
+    class GenPng(Base):
+        def save_data(self):
+            pass
+
+    class GenPngHost(IASPseudoGenerator):               # rank 0 alone, for the reference writer beside it
         def save_data(self):
             pass
 
     def run_png(n_images, mode):
         d = tempfile.mkdtemp()
         try:
-            gen = GenPng(cfg, model=LowRes(), loader=loader_lr(n_images), dataset_len=None, save_dir=os.path.join(d, 'pl'),
-                         window_batches=WINDOW // GROUP, device=device, png=mode)
+            cls = GenPng if mode == 'device' else GenPngHost
+            gen = cls(cfg, model=LowRes(), loader=loader_lr(n_images), save_dir=os.path.join(d, 'pl'),
+                      dataset_len=total(n_images) if mode == 'device' else None,
+                      window_batches=WINDOW // GROUP, device=device, png=mode)
             gen.run()
             files = os.listdir(os.path.join(d, 'pl'))
             return len(files), sum(os.path.getsize(os.path.join(d, 'pl', f)) for f in files)

@@ -245,27 +245,43 @@ def _phase_a(engine, logits, first_image):
 
 
 def _flush_window(gen, engine, paths, n_images, scan):
-    """Phases B/C for the images in the window, then D2H of labels + counts (pinned buffers, one sync per
-    window) and the host bookkeeping."""
+    """Phases B/C for the images in the window, then the outputs (``_emit_window``)."""
     if n_images == 0:
         return
     if scan:
         engine.phase_b(0, n_images)
     engine.phase_c(0, n_images)
     engine.mean_prob(0, n_images)
+    _emit_window(gen, engine, paths, 0, n_images)
+
+
+def _emit_window(gen, engine, paths, first, n_images):
+    """Outputs of the masked window engine.plbl[first:first+n]: PNG files + per-image statistics.
+
+    Device path (default): the label maps are encoded as PNG files on the device, one D2H copy moves the finished files to a
+    pinned blob (two blobs alternate) and ONE native call writes them while the next window is computed.  Host path
+    (``png='host'`` or a hooked ``save_pseudo_label``): uint8 label maps come back at 1 B/px through a pinned buffer (one
+    sync per window) and go to the hook / ``cv2.imwrite``."""
+    plbl, counts = engine.plbl[first:first + n_images], engine.counts[first:first + n_images]
+    if not torch.is_tensor(plbl):                     # a host stand-in engine (CPU tests of the orchestration)
+        plbl_h, counts_h = np.asarray(plbl), torch.as_tensor(counts).numpy()
+        for i in range(n_images):
+            gen._record_image(counts_h[i], paths[i])
+            gen._save_async(plbl_h[i].copy(), paths[i])
+        gen._wait_png()
+        return
     if gen._device_png():
         cpin = getattr(gen, '_pinned_counts', None)
-        if cpin is None or cpin.shape != engine.counts.shape:
+        if cpin is None or cpin.shape[0] < n_images or cpin.shape[1:] != counts.shape[1:]:
             cpin = gen._pinned_counts = torch.empty(engine.counts.shape, dtype=torch.int64).pin_memory()
-        cpin[:n_images].copy_(engine.counts[:n_images], non_blocking=True)
+        cpin[:n_images].copy_(counts, non_blocking=True)
         enc = gen._png_encoder
-        if enc is None or (enc.H, enc.W) != tuple(engine.plbl.shape[1:]) or enc.max_images < engine.max_images:
-            enc = gen._png_encoder = ops.PngEncoder(engine.plbl.shape[1], engine.plbl.shape[2], engine.max_images,
-                                                    device=engine.device)
+        if enc is None or (enc.H, enc.W) != tuple(plbl.shape[1:]) or enc.max_images < n_images:
+            enc = gen._png_encoder = ops.PngEncoder(plbl.shape[1], plbl.shape[2], engine.max_images, device=engine.device)
         slot = gen._png_slot = 1 - gen._png_slot
         gen._wait_png_slot(slot)                      # the writers of two windows ago still read this pinned blob
-        files = enc.encode_to_host(engine.plbl[:n_images], slot)     # finished PNG files; syncs the stream once
-        counts_h = cpin.numpy().copy()
+        files = enc.encode_to_host(plbl, slot)        # finished PNG files; syncs the stream once
+        counts_h = cpin.numpy()[:n_images].copy()
         for i in range(n_images):
             gen._record_image(counts_h[i], paths[i])
         if type(gen).save_pseudo_label_file is BasePseudoGenerator.save_pseudo_label_file and gen._png_pool is not None:
@@ -279,11 +295,11 @@ def _flush_window(gen, engine, paths, n_images, scan):
                 gen._save_file_async(files[i], paths[i], slot)
         return                                        # the files are written while the next window is computed
     pins = getattr(gen, '_pinned', None)
-    if pins is None or pins[0].shape[0] < engine.max_images or pins[0].shape[1:] != engine.plbl.shape[1:]:
+    if pins is None or pins[0].shape[0] < n_images or pins[0].shape[1:] != plbl.shape[1:]:
         pins = gen._pinned = (torch.empty(engine.plbl.shape, dtype=torch.uint8).pin_memory(),
                               torch.empty(engine.counts.shape, dtype=torch.int64).pin_memory())
-    pins[0][:n_images].copy_(engine.plbl[:n_images], non_blocking=True)   # host PNG path: 1 B/px back
-    pins[1][:n_images].copy_(engine.counts[:n_images], non_blocking=True)
+    pins[0][:n_images].copy_(plbl, non_blocking=True)   # host PNG path: 1 B/px back
+    pins[1][:n_images].copy_(counts, non_blocking=True)
     torch.cuda.current_stream(engine.device).synchronize()
     gen._wait_png()                                   # the previous window's encoders still read the pinned buffer
     plbl_h, counts_h = pins[0].numpy(), pins[1].numpy()
@@ -540,31 +556,8 @@ class ShardedIASPseudoGenerator(IASPseudoGenerator):
         e.phase_c(slot, n)
         g0, g = slot // e.B, (n + e.B - 1) // e.B
         drv._stash.append(torch.stack([torch.as_tensor(e.confsum[g0:g0 + g]), e.group_counts(slot, n)], dim=1).clone())
-        plbl, counts = e.plbl[slot:slot + n], torch.as_tensor(e.counts[slot:slot + n])
         rows_before = len(self.sample_stats)
-        if torch.is_tensor(plbl) and plbl.is_cuda and self._device_png():
-            enc = self._png_encoder
-            if enc is None or (enc.H, enc.W) != tuple(plbl.shape[1:]) or enc.max_images < n:
-                enc = self._png_encoder = ops.PngEncoder(plbl.shape[1], plbl.shape[2], e.max_images // 2, device=e.device)
-            pslot = self._png_slot = 1 - self._png_slot
-            self._wait_png_slot(pslot)
-            enc.encode_to_host(plbl, pslot)
-            counts_h = counts.cpu().numpy()
-            blob_host, offsets = enc.host_blob(pslot)
-            targets = [self._pseudo_label_path(p) for p in paths]
-            if self._png_pool is not None:
-                self._png_slot_jobs[pslot].append(self._png_pool.submit(ops.write_files, targets, blob_host, offsets,
-                                                                        self._png_workers))
-            else:
-                ops.write_files(targets, blob_host, offsets, self._png_workers)
-        else:
-            plbl_h = plbl.cpu().numpy() if torch.is_tensor(plbl) else np.asarray(plbl)
-            counts_h = counts.cpu().numpy()
-            for i in range(n):
-                self._save_async(plbl_h[i].copy(), paths[i])
-            self._wait_png()
-        for i in range(n):
-            self._record_image(counts_h[i], paths[i])
+        _emit_window(self, e, paths, slot, n)
         thr_groups = torch.as_tensor(e.thr_groups[g0:g0 + g]).cpu().numpy().copy()
         per_window[w] = (self.sample_stats[rows_before:], thr_groups)
 
