@@ -270,6 +270,8 @@ def _emit_window(gen, engine, paths, first, n_images):
             gen._save_async(plbl_h[i].copy(), paths[i])
         gen._wait_png()
         return
+    if gen._device_png() and plbl.shape[2] > 128 * 256:
+        gen.png = 'host'                              # wider than the device writer's 32768-pixel rows: the reference's writer
     if gen._device_png():
         cpin = getattr(gen, '_pinned_counts', None)
         if cpin is None or cpin.shape[0] < n_images or cpin.shape[1:] != counts.shape[1:]:
