@@ -307,11 +307,13 @@ def gpu_arm(args):
                        'images_per_step_per_gpu': WINDOW, 'images_total': images, 'alpha': ALPHA, 'beta': BETA,
                        'gamma': GAMMA, 'distribution': args.dist, 'resident_pool_maps': WINDOW,
                        'l2': 'inputs exceed L2 (10.2 GB streamed per step)',
-                       'parallelism': ('one rank: fused A+B+C kernel per window, no collective' if world == 1 else
+                       'parallelism': (('one rank: fused A+B+C kernel per window, no collective' if fused_used else
+                                        'one rank: phases A, B (prefix + scan), C and the mean-prob scan per window, no collective')
+                                       if world == 1 else
                                        'windows striped over %d ranks; 19-double threshold state via NCCL send/recv' % world)},
             'hbm_frac_of_peak': ALG_BYTES_PER_IMAGE * value / world / 1e9 / peak,
             'roofline': {'kernel': 'k_ias_fused (phases A+B+C in one persistent kernel; the events also cover its 4 memsets)'
-                                   if fused_used else 'k_softmax_hist_gr (phase A)', 'bound': 'hbm', 'achieved': achieved, 'peak': peak,
+                                   if fused_used else 'k_softmax_hist_grs (phase A)', 'bound': 'hbm', 'achieved': achieved, 'peak': peak,
                          'unit': 'GB/s', 'frac': achieved / peak, 'traffic': ncu_traffic(), 'peak_source': peak_src,
                          'algorithmic_bytes_per_launch': ALG_BYTES_PER_IMAGE * WINDOW, 'launch_ms': a_ms,
                          'share_of_step': a_ms / (ms / K)},
