@@ -45,10 +45,23 @@ def _cfg_get(node, path, default=None):
     return node
 
 
+_COPY_STREAMS = {}
+
+
+def _copy_stream(device):
+    """One host-to-device copy stream per device for the life of the process: the caching allocator keeps a block pool per
+    stream, so a fresh stream per run() would cudaMalloc every batch again (measured: 260 us per batch instead of 23)."""
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    st = _COPY_STREAMS.get(key)
+    if st is None:
+        st = _COPY_STREAMS[key] = torch.cuda.Stream(device)
+    return st
+
+
 class BasePseudoGenerator:
 
     def __init__(self, cfg, model=None, loader=None, dataset_len=None, save_dir=None, window_batches=8,
-                 device='cuda', png_workers=8, png='device'):
+                 device='cuda', png_workers=8, png='device', prefetch=None):
         self.cfg = cfg
         self.statics_class = np.array([0] * self.cfg.dataset.num_classes)                # :18
         self.sample_stats = []                                                           # :19
@@ -57,6 +70,7 @@ class BasePseudoGenerator:
         self.class_threshold = None
         self.device = torch.device(device)
         self.window_batches = int(window_batches)
+        self.prefetch = None if prefetch is None else int(prefetch)   # H2D copies issued this many batches ahead (None: auto, 0: inline)
         self._model_arg, self._loader_arg, self._len_arg, self._save_dir_arg = model, loader, dataset_len, save_dir
         self._png_pool = ThreadPoolExecutor(max_workers=png_workers) if png_workers > 0 else None
         self._png_workers = max(1, int(png_workers))
@@ -202,24 +216,81 @@ class BasePseudoGenerator:
         return IASEngine(c, h, w, group, alpha, beta, gamma, self._cp_gamma(), group * self.window_batches,
                          device=self.device)
 
+    def _device_batches(self):
+        """(images on the device, image_paths) for every loader batch.  With ``prefetch > 0`` a producer thread walks the loader
+        and issues the host-to-device copies on its own stream, up to ``prefetch`` batches ahead, so the copies of the next window
+        run while the main thread sits in the stream sync at the end of the current one (the consumer waits on each batch's event)."""
+        depth = getattr(self, 'prefetch', 0)
+        if (depth is not None and depth <= 0) or self.device.type != 'cuda':
+            for data in self.t_loader:
+                yield data['images'].to(self.device, non_blocking=True), list(data['image_paths'])
+            return
+        import queue
+        import threading
+        q = queue.Queue()
+        copy_stream = _copy_stream(self.device)
+        stop = threading.Event()
+        slots = []                                # semaphore, created by the producer once the batch size is known
+
+        def producer():
+            try:
+                with torch.cuda.stream(copy_stream):
+                    for data in self.t_loader:
+                        if not slots:
+                            nbytes = max(1, data['images'].numel() * data['images'].element_size())
+                            # None: about 1.5 GB of batches in flight, at most one window (full-resolution logits: 4 batches;
+                            # images or stride-8 logits: the whole next window)
+                            n = depth if depth is not None else max(2, min(self.window_batches, int(1.5e9 // nbytes)))
+                            slots.append(threading.Semaphore(n))
+                        while not slots[0].acquire(timeout=0.05):
+                            if stop.is_set():
+                                return
+                        if stop.is_set():
+                            return
+                        imgs = data['images'].to(self.device, non_blocking=True)
+                        ev = torch.cuda.Event()
+                        ev.record(copy_stream)
+                        q.put((imgs, ev, list(data['image_paths'])))
+                q.put(None)
+            except BaseException as exc:          # surfaces in the consumer
+                q.put(exc)
+
+        t = threading.Thread(target=producer, name='hiast-h2d', daemon=True)
+        t.start()
+        try:
+            while True:
+                item = q.get()
+                if item is None:
+                    break
+                if isinstance(item, BaseException):
+                    raise item
+                imgs, ev, paths = item
+                slots[0].release()
+                main = torch.cuda.current_stream(self.device)
+                main.wait_event(ev)
+                imgs.record_stream(main)
+                yield imgs, paths
+        finally:
+            stop.set()
+            t.join(timeout=5.0)
+
     def _iterate_logits(self):
         """Yields (logits [B,C,H,W] on the device, image_paths) exactly as :189-192 produces them."""
         self.model.eval() if hasattr(self.model, 'eval') else None
         with torch.no_grad():
-            for data in self.t_loader:
-                imgs = data['images'].to(self.device, non_blocking=True)
+            for imgs, image_paths in self._device_batches():
                 out = self.model(imgs)
                 if 'logits' not in out and 'logits_lr' in out:
                     # the network's own (stride-8) output: the bilinear up-sampling of
                     # self_training_segmentor.py:27 is fused into phase A (SURVEY 8f rank 1)
                     lr = out['logits_lr']
                     lr = lr.float() if lr.dtype != torch.float32 else lr
-                    yield LowResLogits(lr.contiguous(), tuple(out.get('size', imgs.shape[2:]))), list(data['image_paths'])
+                    yield LowResLogits(lr.contiguous(), tuple(out.get('size', imgs.shape[2:]))), image_paths
                     continue
                 logits = out['logits']
                 if logits.dtype != torch.float32:
                     logits = logits.float()
-                yield logits.contiguous(), list(data['image_paths'])
+                yield logits.contiguous(), image_paths
 
     def _already_done(self):
         return self.t_dataset is not None and len(os.listdir(self.pseudo_label_save_dir)) >= len(self.t_dataset)
