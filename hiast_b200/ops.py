@@ -363,8 +363,9 @@ def iou_from_confusion(cm, K):
 class PngEncoder:
     """Device PNG writer for uint8 label maps [N,H,W] (pseudo_label_generator.py:43-46 `cv2.imwrite`).
 
-    ``encode(labels)`` launches the three kernels on the current stream and returns ``(blob, offsets)``: device uint8
-    blob and device int64 [N+1] offsets; file i is ``blob[offsets[i]:offsets[i+1]]``.  ``encode_to_host(labels)`` also
+    ``encode(labels)`` launches the three kernels on the current stream and returns ``(blob, offsets, host_offsets)``:
+    device uint8 blob, device int64 [N+1] offsets and their pinned host copy (one sync); file i is
+    ``blob[offsets[i]:offsets[i+1]]``.  ``encode_to_host(labels)`` also
     copies the used part of the blob to pinned host memory (one sync) and returns a list of ``memoryview``-able numpy
     slices.  The blob is sized for ``expect_ratio`` x compression and grown (to the worst case) if a batch does not fit."""
 
