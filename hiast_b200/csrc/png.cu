@@ -505,7 +505,7 @@ struct BitWriter {
 
 // VAR 0: per-lane token loop with an inner literal loop (lanes diverge); VAR 1 (default): one token per iteration, branch-free body.
 template <int VAR>
-__global__ void __launch_bounds__(kPngThreads) k_png_emit(const uint8_t* __restrict__ labels, PngGeom g, int vec,
+__global__ void __launch_bounds__(kPngThreads, 4) k_png_emit(const uint8_t* __restrict__ labels, PngGeom g, int vec,
                                                           PngWorkspace ws, uint8_t* __restrict__ out,
                                                           unsigned long long capacity,
                                                           const long long* __restrict__ offsets, int n_images) {
