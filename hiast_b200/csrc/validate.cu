@@ -324,18 +324,19 @@ __global__ void __launch_bounds__(kValThreads) k_probs_upsample_argmax_staged(Sc
       const float* src = sc.p[s] + (static_cast<int64_t>(b) * C + c0) * plane_sz + static_cast<int64_t>(row0[s]) * ws + col0[s];
       float* dst = stage + static_cast<size_t>(sg.base[s]) * sg.cg;
       const int pitch = sg.nc_max[s], cstride = sg.nr_max[s] * pitch;
-      if (sg.vec16) {
-        const int q = ncols[s] >> 2, per_c = nrows[s] * q, total = nc * per_c;
-        for (int i = threadIdx.x; i < total; i += kValThreads) {
-          const int c = i / per_c, rem = i - c * per_c, r = rem / q, k = rem - r * q;
-          cp_async16(dst + c * cstride + r * pitch + 4 * k, src + c * plane_sz + static_cast<int64_t>(r) * ws + 4 * k);
-        }
-      } else {
-        const int cols = min(ncols[s], ws - col0[s]);
-        const int per_c = nrows[s] * cols, total = nc * per_c;
-        for (int i = threadIdx.x; i < total; i += kValThreads) {
-          const int c = i / per_c, rem = i - c * per_c, r = rem / cols, k = rem - r * cols;
-          cp_async4(dst + c * cstride + r * pitch + k, src + c * plane_sz + static_cast<int64_t>(r) * ws + k);
+      // a warp per (channel, row) of the window, lanes along the row: one division per row instead of two per element
+      // (the first version spent as many instructions on this index arithmetic as on the taps)
+      const int lane = lane_id(), warp = threadIdx.x >> 5;
+      const int n_rows_total = nc * nrows[s];
+      const int cols = min(ncols[s], ws - col0[s]);
+      for (int rr = warp; rr < n_rows_total; rr += kValThreads / 32) {
+        const int c = rr / nrows[s], r = rr - c * nrows[s];
+        const float* src_row = src + c * plane_sz + static_cast<int64_t>(r) * ws;
+        float* dst_row = dst + c * cstride + r * pitch;
+        if (sg.vec16) {
+          for (int k = 4 * lane; k < ncols[s]; k += 128) cp_async16(dst_row + k, src_row + k);
+        } else {
+          for (int k = lane; k < cols; k += 32) cp_async4(dst_row + k, src_row + k);
         }
       }
     }
