@@ -320,3 +320,34 @@ def test_generators_from_stride8_logits_equal_the_interpolated_path(ptype, tmp_p
     assert np.array_equal(res['full'][2], res['low'][2])
     for a, b in zip(res['full'][3], res['low'][3]):
         assert a is not None and np.array_equal(a, b)
+
+
+@pytest.mark.parametrize('prefetch', [0, 1, None])
+def test_h2d_prefetch_thread_does_not_change_results(prefetch, tmp_path):
+    """The producer thread that issues the host-to-device copies ahead (prefetch > 0 / None = auto) is pure plumbing:
+    thresholds, statistics and files equal the inline path and the oracle; a loader error surfaces in run()."""
+    import hiast_b200
+    hiast_b200.register_all()
+    from hiast_b200 import PSEUDO_POLICY
+    spec = gi.IAS_SPECS['ias_small']
+    batches = gi.ias_batches(spec)
+    pinned = [(lg.pin_memory(), p) for lg, p in batches]
+    save_dir = str(tmp_path / 'run' / 'pseudo_labels')
+    gen = PSEUDO_POLICY['IAS'](make_cfg(spec), model=Identity(), loader=loader_of(pinned), dataset_len=spec['N'],
+                               save_dir=save_dir, window_batches=2, prefetch=prefetch)
+    gen.run()
+    oracle = oias.IASOracle(spec['C'], spec['alpha'], spec['beta'], spec['gamma'], spec['cp_gamma'])
+    oracle.run([(lg.cuda(), p) for lg, p in batches])
+    assert np.array_equal(gen.class_threshold, oracle.class_threshold)
+    assert np.array_equal(gen.statics_class, oracle.statics_class)
+    assert gen.sample_stats == oracle.sample_stats
+    assert len(os.listdir(save_dir)) == spec['N']
+
+    def broken():
+        yield {'images': pinned[0][0], 'image_paths': pinned[0][1]}
+        raise OSError('disk gone')
+
+    gen2 = PSEUDO_POLICY['IAS'](make_cfg(spec), model=Identity(), loader=broken(), dataset_len=spec['N'],
+                                save_dir=str(tmp_path / 'run2' / 'pseudo_labels'), window_batches=2, prefetch=prefetch)
+    with pytest.raises(OSError):
+        gen2.run()
