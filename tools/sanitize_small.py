@@ -53,5 +53,20 @@ probs = [ops.softmax_flip_sum(a, a.flip(3).contiguous()) for a in zs]
 ops.probs_upsample_argmax(probs, (32, 64))
 ops.probs_upsample_argmax(probs[:1], (32, 64))
 ops.probs_upsample_argmax(probs + probs[:1], (33, 65))
+# general CE (class weights / refer_labels), forward + backward
+wts = torch.rand(C, generator=g).cuda()
+lab = torch.randint(0, C, (2, 32, 64), generator=g).cuda()
+for refer in (None, y):
+    sums, cnt = ops.ce_general_fwd(z, lab, wts, refer, 'ignored', 255)
+    ops.ce_general_bwd(z, lab, wts, refer, 'ignored', 255, torch.ones(1, device='cuda'))
+# PNG writer: both emit variants, many images (offset scan rounds), >32 segments per image
+from hiast_b200._lib import lib  # noqa: E402
+many = torch.from_numpy(rng.integers(0, 4, (300, 6, 10)).astype(np.uint8)).cuda()
+wide = torch.from_numpy(np.repeat(rng.integers(0, 19, (1, 300, 40)), 100, 2).astype(np.uint8)).cuda()
+for v in (0, 1):
+    lib().hiast_debug_png_variant(v)
+    ops.PngEncoder(6, 10, 300).encode_to_host(many)
+    ops.PngEncoder(300, 4000, 1).encode_to_host(wide)
+lib().hiast_debug_png_variant(1)
 torch.cuda.synchronize()
 print('sanitize_small ok')
