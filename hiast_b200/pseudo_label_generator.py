@@ -61,7 +61,7 @@ def _copy_stream(device):
 class BasePseudoGenerator:
 
     def __init__(self, cfg, model=None, loader=None, dataset_len=None, save_dir=None, window_batches=8,
-                 device='cuda', png_workers=8, png='device', prefetch=None):
+                 device='cuda', png_workers=8, png='device', prefetch=None, defer_sync=True):
         self.cfg = cfg
         self.statics_class = np.array([0] * self.cfg.dataset.num_classes)                # :18
         self.sample_stats = []                                                           # :19
@@ -70,6 +70,7 @@ class BasePseudoGenerator:
         self.class_threshold = None
         self.device = torch.device(device)
         self.window_batches = int(window_batches)
+        self.defer_sync = bool(defer_sync)            # complete a window's outputs while the next one is computed
         self.prefetch = None if prefetch is None else int(prefetch)   # H2D copies issued this many batches ahead (None: auto, 0: inline)
         self._model_arg, self._loader_arg, self._len_arg, self._save_dir_arg = model, loader, dataset_len, save_dir
         self._png_pool = ThreadPoolExecutor(max_workers=png_workers) if png_workers > 0 else None
@@ -145,7 +146,25 @@ class BasePseudoGenerator:
         else:
             self._png_jobs.append(self._png_pool.submit(self.save_pseudo_label, plbl, img_path))
 
+    def _finish_pending_emit(self):
+        """Complete the window whose outputs were queued by ``_emit_window(..., defer=True)``: wait for ITS event (the GPU is
+        one window further by now), do the per-image bookkeeping, hand the finished files to the native writer."""
+        p = getattr(self, '_pending_emit', None)
+        if p is None:
+            return
+        self._pending_emit = None
+        blob_host, offsets = p['enc'].finish(p['handle'])
+        counts_h = p['counts'].numpy()[:p['n']].copy()
+        for i in range(p['n']):
+            self._record_image(counts_h[i], p['paths'][i])
+        targets = [self._pseudo_label_path(q) for q in p['paths']]
+        self._png_slot_jobs[p['slot']].append(self._png_pool.submit(ops.write_files, targets, blob_host, offsets,
+                                                                    self._png_workers))
+        if p.get('after') is not None:
+            p['after']()
+
     def _wait_png(self):
+        self._finish_pending_emit()
         for job in self._png_jobs:
             job.result()
         self._png_jobs = []
@@ -337,8 +356,9 @@ def _flush_lowres(engine):
     engine.phase_a_lowres(lr, pend[0][1])
 
 
-def _flush_window(gen, engine, paths, n_images, scan):
-    """Phases B/C for the images in the window, then the outputs (``_emit_window``)."""
+def _flush_window(gen, engine, paths, n_images, scan, before_emit=None):
+    """Phases B/C for the images in the window, then the outputs (``_emit_window``, deferred when possible).
+    ``before_emit()`` may queue more copies on the stream and returns the completion callback."""
     if n_images == 0:
         return
     _flush_lowres(engine)
@@ -346,10 +366,47 @@ def _flush_window(gen, engine, paths, n_images, scan):
         engine.phase_b(0, n_images)
     engine.phase_c(0, n_images)
     engine.mean_prob(0, n_images)
-    _emit_window(gen, engine, paths, 0, n_images)
+    after = before_emit() if before_emit is not None else None
+    _emit_window(gen, engine, paths, 0, n_images, defer=True, after=after)
 
 
-def _emit_window(gen, engine, paths, first, n_images):
+def _can_defer(gen, engine):
+    """Deferred completion needs the device PNG writer with the native file writer and a CUDA engine."""
+    return (getattr(gen, 'defer_sync', True) and gen._device_png() and gen._png_pool is not None
+            and type(gen).save_pseudo_label_file is BasePseudoGenerator.save_pseudo_label_file
+            and torch.is_tensor(engine.plbl) and engine.plbl.is_cuda and engine.plbl.shape[2] <= 128 * 256)
+
+
+def _emit_window(gen, engine, paths, first, n_images, defer=False, after=None):
+    """Outputs of the masked window engine.plbl[first:first+n] (PNG files + per-image statistics).  ``defer=True`` (single-GPU
+    generators): everything is only QUEUED on the stream -- encoder, copies of the offset table / predicted blob bytes / counts,
+    an event -- and completed when the next window is emitted (``_finish_pending_emit``), so the host never waits for the GPU
+    at the end of a window and phase A of the next window is issued behind this one without a gap.  ``after`` runs on
+    completion (the IAS generator reads its threshold copies there)."""
+    if defer and _can_defer(gen, engine):
+        plbl, counts = engine.plbl[first:first + n_images], engine.counts[first:first + n_images]
+        gen._finish_pending_emit()                    # the previous window (its event is long past)
+        enc = gen._png_encoder
+        if enc is None or (enc.H, enc.W) != tuple(plbl.shape[1:]) or enc.max_images < n_images:
+            enc = gen._png_encoder = ops.PngEncoder(plbl.shape[1], plbl.shape[2], engine.max_images, device=engine.device)
+        slot = gen._png_slot = 1 - gen._png_slot
+        gen._wait_png_slot(slot)                      # the writers of two windows ago still read this pinned blob
+        cpins = gen.__dict__.setdefault('_pinned_counts2', {})
+        cpin = cpins.get(slot)
+        if cpin is None or cpin.shape[0] < n_images or cpin.shape[1:] != counts.shape[1:]:
+            cpin = cpins[slot] = torch.empty(engine.counts.shape, dtype=torch.int64).pin_memory()
+        cpin[:n_images].copy_(counts, non_blocking=True)
+        handle = enc.encode_async(plbl, slot)
+        gen._pending_emit = dict(enc=enc, handle=handle, slot=slot, paths=list(paths[:n_images]), n=n_images, counts=cpin,
+                                 after=after)
+        return
+    gen._finish_pending_emit()
+    _emit_window_sync(gen, engine, paths, first, n_images)
+    if after is not None:
+        after()
+
+
+def _emit_window_sync(gen, engine, paths, first, n_images):
     """Outputs of the masked window engine.plbl[first:first+n]: PNG files + per-image statistics.
 
     Device path (default): the label maps are encoded as PNG files on the device, one D2H copy moves the finished files to a
@@ -366,6 +423,7 @@ def _emit_window(gen, engine, paths, first, n_images):
         return
     if gen._device_png() and plbl.shape[2] > 128 * 256:
         gen.png = 'host'                              # wider than the device writer's 32768-pixel rows: the reference's writer
+    native = (type(gen).save_pseudo_label_file is BasePseudoGenerator.save_pseudo_label_file and gen._png_pool is not None)
     if gen._device_png():
         cpin = getattr(gen, '_pinned_counts', None)
         if cpin is None or cpin.shape[0] < n_images or cpin.shape[1:] != counts.shape[1:]:
@@ -380,7 +438,7 @@ def _emit_window(gen, engine, paths, first, n_images):
         counts_h = cpin.numpy()[:n_images].copy()
         for i in range(n_images):
             gen._record_image(counts_h[i], paths[i])
-        if type(gen).save_pseudo_label_file is BasePseudoGenerator.save_pseudo_label_file and gen._png_pool is not None:
+        if native:
             # one native call writes the whole window (POSIX writer threads, no interpreter lock)
             blob_host, offsets = enc.host_blob(slot)
             targets = [gen._pseudo_label_path(p) for p in paths[:n_images]]
@@ -545,11 +603,34 @@ class IASPseudoGenerator(BasePseudoGenerator):
     def _finish_window(self, engine, paths, n):
         if n == 0:
             return
-        _flush_window(self, engine, paths, n, scan=True)
         g = engine._groups(n)
-        self.threshold_trace.append(engine.thr_groups[:g].cpu().numpy().copy())
-        self.class_threshold = engine.thr_state.cpu().numpy()
-        self.class_mean_probs = engine.mean_state.cpu().numpy()
+
+        def before_emit():
+            # per-window host copies of the thresholds: queued into pinned buffers (one set per PNG slot), read on completion
+            if not _can_defer(self, engine):
+                def read_now():
+                    self.threshold_trace.append(engine.thr_groups[:g].cpu().numpy().copy())
+                    self.class_threshold = engine.thr_state.cpu().numpy()
+                    self.class_mean_probs = engine.mean_state.cpu().numpy()
+                return read_now
+            pins = self.__dict__.setdefault('_thr_pins', {})
+            slot = 1 - self._png_slot                  # the slot _emit_window is about to take
+            buf = pins.get(slot)
+            if buf is None or buf[0].shape != engine.thr_groups.shape:
+                buf = pins[slot] = (torch.empty(engine.thr_groups.shape, dtype=torch.float64).pin_memory(),
+                                    torch.empty(engine.thr_state.shape, dtype=torch.float64).pin_memory(),
+                                    torch.empty(engine.mean_state.shape, dtype=torch.float64).pin_memory())
+            buf[0][:g].copy_(engine.thr_groups[:g], non_blocking=True)
+            buf[1].copy_(engine.thr_state, non_blocking=True)
+            buf[2].copy_(engine.mean_state, non_blocking=True)
+
+            def read_later():
+                self.threshold_trace.append(buf[0][:g].numpy().copy())
+                self.class_threshold = buf[1].numpy().copy()
+                self.class_mean_probs = buf[2].numpy().copy()
+            return read_later
+
+        _flush_window(self, engine, paths, n, scan=True, before_emit=before_emit)
 
 
 def striped_batch_order(n_images_total, window_images, batch_size, rank, world_size):
