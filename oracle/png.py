@@ -66,8 +66,6 @@ def _rev(code, n):
 
 
 _LIT = [(_rev(0x30 + b, 8), 8) if b < 144 else (_rev(0x190 + b - 144, 9), 9) for b in range(256)]
-_LIT_VAL = np.array([v for v, _ in _LIT], dtype=np.int64)
-_LIT_NB = np.array([n for _, n in _LIT], dtype=np.int64)
 
 
 def _match_token(run):

@@ -121,7 +121,6 @@ def test_many_small_images_and_tall_images():
     assert len(files) == 300
     for i in (0, 1, 255, 256, 257, 299):
         assert bytes(files[i]) == opng.encode_png(maps[i]), i
-    tall = np.repeat(rng.integers(0, 19, (2, 70, 1)), 8, 1).astype(np.uint8)          # W = 8 -> R = 256 rows; use W = 3000
     tall = np.repeat(rng.integers(0, 19, (2, 90, 30)), 100, 2).astype(np.uint8)       # [2, 90, 3000]: 24 chunks/row, R = 10, S = 9
     wide = np.repeat(rng.integers(0, 19, (1, 700, 40)), 100, 2).astype(np.uint8)      # [1, 700, 4000]: 32 chunks/row, R = 8, S = 88
     for arr in (tall, wide):
