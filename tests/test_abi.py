@@ -70,11 +70,34 @@ def test_product_path_has_no_cpu_fallback(built_lib):
         ops.confusion_matrix(torch.zeros(4, dtype=torch.int64), torch.zeros(4, dtype=torch.int64), 19)
     with pytest.raises(_lib.HiastError):
         ops.ias_upsample_softmax_hist(torch.zeros(1, 19, 3, 3), (8, 8), 2)
+    with pytest.raises(_lib.HiastError):                       # round-1 widening: no host path either
+        ops.resize_nearest_u8(torch.zeros(2, 4, 4, dtype=torch.uint8), (8, 8))
+    with pytest.raises(_lib.HiastError):
+        ops.softmax_flip_sum(torch.zeros(1, 19, 4, 4))
+    with pytest.raises(_lib.HiastError):
+        ops.probs_upsample_argmax([torch.zeros(1, 19, 4, 4)], (8, 8))
+    with pytest.raises(_lib.HiastError):
+        ops.ce_general_fwd(torch.zeros(1, 19, 4, 4), torch.zeros(1, 4, 4, dtype=torch.int64))
+    from hiast_b200.losses import ce
+    with pytest.raises(_lib.HiastError):
+        ce(torch.zeros(1, 19, 4, 4), torch.zeros(1, 4, 4, dtype=torch.int64), weights=torch.ones(19))
+    from hiast_b200.validator import Validator
+    from types import SimpleNamespace
+    cfg = SimpleNamespace(dataset=SimpleNamespace(num_classes=19, source=SimpleNamespace(type='GTA5')),
+                          validate=SimpleNamespace(resize_sizes=[[4, 4]], is_flip=False, color_mask_dir_path=None))
+    with pytest.raises(_lib.HiastError):
+        Validator(cfg, model=lambda x: {'logits': torch.zeros(1, 19, 4, 4)}, loader=[], device='cpu').predict(torch.zeros(1, 3, 4, 4))
     from hiast_b200.ema import update_ema_model
     with pytest.raises(_lib.HiastError):                       # CPU models: no host path for the EMA update either
         update_ema_model(torch.nn.Linear(3, 2), torch.nn.Linear(3, 2), 0.99)
     l = _lib.lib()
     assert l.hiast_ema_update(None, None, None, 1, 1024, 0.9, 0.1, None) == -1
+    assert l.hiast_png_encode(None, 1, 4, 4, None, 0, None, None, 0, None) == -1
+    assert l.hiast_resize_nearest_u8(None, 1, 4, 4, None, 8, 8, 1.0, 1.0, None) == -1
+    assert l.hiast_softmax_flip_sum(None, None, 1, 19, 4, 4, None, None) == -1
+    assert l.hiast_probs_upsample_argmax(None, None, None, 1, 1, 19, 4, 4, None, None) == -1
+    assert l.hiast_ce_general_fwd(None, None, 8, None, None, 0, 1, 255, 1, 19, 16, None, None, None, 0, None) == -1
+    assert l.hiast_write_files(None, None, None, 1, 1, None) == -1
     assert l.hiast_ias_fused_window(None, 1, 19, 4, 4, 2, 0, 0.5, 0.9, 8.0, None, None, None, None, None, None, None, None, None,
                                     None, None, 0, 0, None) == -1
 
