@@ -4,6 +4,7 @@
 
 #include <atomic>
 #include <cerrno>
+#include <map>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -25,6 +26,20 @@ int sm_count() {
     cached[dev] = n;
   }
   return cached[dev];
+}
+
+int ensure_dyn_smem_impl(const void* kernel, size_t bytes) {
+  if (bytes <= 48 * 1024) return HIAST_OK;           // the default limit needs no opt-in
+  static std::mutex mu;
+  static std::map<std::pair<int, const void*>, size_t> granted;
+  int dev = 0;
+  HIAST_CUDA_TRY(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  size_t& have = granted[std::make_pair(dev, kernel)];
+  if (have >= bytes) return HIAST_OK;
+  HIAST_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)));
+  have = bytes;
+  return HIAST_OK;
 }
 
 }  // namespace hiast

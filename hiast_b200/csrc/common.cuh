@@ -29,6 +29,17 @@ inline cudaStream_t as_stream(void* s) { return static_cast<cudaStream_t>(s); }
 // SM count / max resident CTAs of the current device, cached per device.
 int sm_count();
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute of a kernel: remember, per (device, kernel), the largest
+// size already granted and call cudaFuncSetAttribute only when a launch needs more.  Returns a HIAST status.
+int ensure_dyn_smem_impl(const void* kernel, size_t bytes);
+template <typename K>
+inline int ensure_dyn_smem(K kernel, size_t bytes) { return ensure_dyn_smem_impl(reinterpret_cast<const void*>(kernel), bytes); }
+#define HIAST_TRY(expr)                \
+  do {                                 \
+    const int _rc = (expr);            \
+    if (_rc != HIAST_OK) return _rc;   \
+  } while (0)
+
 template <typename K>
 inline int resident_grid(K kernel, int threads, size_t dyn_smem) {
   int occ = 0;

@@ -70,8 +70,8 @@ __device__ __forceinline__ void cm_flush(const unsigned* s_cm, int cells, int us
 __device__ __forceinline__ int clamp_class(long long v, int K) { return (v >= 0 && v < K) ? static_cast<int>(v) : K; }
 
 template <typename T>
-__global__ void __launch_bounds__(kThreadsM) k_confusion(const T* __restrict__ pred, const T* __restrict__ target,
-                                                         long long n, int K, int ignore_index, T* __restrict__ pred_out,
+__global__ void __launch_bounds__(kThreadsM) k_confusion(const T* pred, const T* __restrict__ target,
+                                                         long long n, int K, int ignore_index, T* pred_out,
                                                          long long* __restrict__ cm, int use_shared) {
   extern __shared__ unsigned s_cm[];
   const int cells = (K + 1) * (K + 1);

@@ -251,11 +251,7 @@ __global__ void __launch_bounds__(kThreadsG, 1) k_ias_fused(FusedArgs f) {
             } else if (bin >= hi0) {
               const int k = bin - hi0;
               const unsigned sh = (k & 1) * 16;
-              const uint32_t old = atomicAdd(s_tab + l * words + (k >> 1), 1u << sh);
-              if (((old >> sh) & 0xffffu) == 0xffffu) {
-                if (sh == 0) atomicSub(s_tab + l * words + (k >> 1), 1u << 16);
-                atomicAdd(g_hist + static_cast<size_t>(l) * nbs + bin, 65536u);
-              }
+              tab16_add(s_tab + l * words + (k >> 1), sh, g_hist + static_cast<size_t>(l) * nbs + bin);
             } else {
               atomicAdd(g_hist + static_cast<size_t>(l) * nbs + bin, 1u);
             }
@@ -535,11 +531,7 @@ int launch_fused(FusedArgs f, int groups_in_flight, cudaStream_t st) {
   slices = static_cast<int>(std::max<long long>(1, std::min<long long>(slices, tiles_per_group / 4)));
   f.ga.slices = slices;
   f.ga.n_units = f.n_groups * slices;
-  static thread_local bool configured = false;
-  if (!configured) {
-    HIAST_CUDA_TRY(cudaFuncSetAttribute(k_ias_fused<C, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kBudget)));
-    configured = true;
-  }
+  HIAST_TRY(ensure_dyn_smem(k_ias_fused<C, 1>, kBudget));
   const size_t smem = kStage + sizeof(uint32_t) * C * words;
   const int grid = std::min(sms, f.ga.n_units);
   k_ias_fused<C, 1><<<grid, kThreadsG, smem, st>>>(f);

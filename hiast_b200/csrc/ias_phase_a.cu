@@ -433,11 +433,7 @@ __global__ void __launch_bounds__(kThreadsG, 1) k_softmax_hist_gr(GroupArgs ga) 
           } else if (bin >= hi0) {
             const int idx = bin - hi0;
             const unsigned sh = (idx & 1) * 16;
-            const uint32_t old = atomicAdd(s_tab + l * words + (idx >> 1), 1u << sh);
-            if (((old >> sh) & 0xffffu) == 0xffffu) {   // this 16-bit counter wrapped: move 65536 to the global row
-              if (sh == 0) atomicSub(s_tab + l * words + (idx >> 1), 1u << 16);   // undo the carry into the neighbour
-              atomicAdd(g_hist + static_cast<size_t>(l) * nbs + bin, 65536u);
-            }
+            tab16_add(s_tab + l * words + (idx >> 1), sh, g_hist + static_cast<size_t>(l) * nbs + bin);
           } else {
             atomicAdd(g_hist + static_cast<size_t>(l) * nbs + bin, 1u);
           }
@@ -602,11 +598,7 @@ __global__ void __launch_bounds__(kThreadsG, 1) k_softmax_hist_grs(GroupArgs ga)
           } else if (bin >= hi0) {
             const int idx = bin - hi0;
             const unsigned sh = (idx & 1) * 16;
-            const uint32_t old = atomicAdd(s_tab + l * words + (idx >> 1), 1u << sh);
-            if (((old >> sh) & 0xffffu) == 0xffffu) {   // this 16-bit counter wrapped: move 65536 to the global row
-              if (sh == 0) atomicSub(s_tab + l * words + (idx >> 1), 1u << 16);   // undo the carry into the neighbour
-              atomicAdd(g_hist + static_cast<size_t>(l) * nbs + bin, 65536u);
-            }
+            tab16_add(s_tab + l * words + (idx >> 1), sh, g_hist + static_cast<size_t>(l) * nbs + bin);
           } else {
             atomicAdd(g_hist + static_cast<size_t>(l) * nbs + bin, 1u);
           }
@@ -847,12 +839,17 @@ constexpr int kSchedSlots = 1024;
 __device__ unsigned g_sched_slots[kSchedSlots];
 
 int next_sched_slot(unsigned** out, cudaStream_t st) {
-  static unsigned* base = nullptr;
+  static std::atomic<unsigned*> bases[64];        // a __device__ symbol has one address PER DEVICE
   static std::atomic<unsigned> next{0};
+  int dev = 0;
+  HIAST_CUDA_TRY(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return HIAST_ERR_UNSUPPORTED;
+  unsigned* base = bases[dev].load(std::memory_order_acquire);
   if (!base) {
     void* p = nullptr;
     HIAST_CUDA_TRY(cudaGetSymbolAddress(&p, g_sched_slots));
     base = static_cast<unsigned*>(p);
+    bases[dev].store(base, std::memory_order_release);
   }
   unsigned* slot = base + (next.fetch_add(1) % kSchedSlots);
   HIAST_CUDA_TRY(cudaMemsetAsync(slot, 0, sizeof(unsigned), st));
@@ -866,12 +863,7 @@ namespace {
 template <int C, int MODE>
 int launch_phase_a_tma(PhaseAArgs a, cudaStream_t st) {
   constexpr size_t smem = tma_smem_bytes<C>();
-  static thread_local bool configured = false;
-  if (!configured) {
-    HIAST_CUDA_TRY(cudaFuncSetAttribute(k_softmax_hist_tma<C, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        static_cast<int>(smem)));
-    configured = true;
-  }
+  HIAST_TRY(ensure_dyn_smem(k_softmax_hist_tma<C, MODE>, smem));
   a.tiles_per_image = static_cast<int>((a.HW + kTileT - 1) / kTileT);
   a.n_tiles = static_cast<long long>(a.tiles_per_image) * a.n_images;
   int grid = sm_count();
@@ -888,12 +880,7 @@ int launch_phase_a_sp(PhaseAArgs a, cudaStream_t st) {
   a.tiles_per_image = static_cast<int>((vecs + kThreadsA - 1) / kThreadsA);
   a.n_tiles = static_cast<long long>(a.tiles_per_image) * a.n_images;
   constexpr size_t smem = sizeof(float) * PX * C * kThreadsA;
-  static thread_local bool configured = false;
-  if (!configured) {
-    HIAST_CUDA_TRY(cudaFuncSetAttribute(k_softmax_hist_sp<C, MODE, PX, MATH, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        static_cast<int>(smem)));
-    configured = true;
-  }
+  HIAST_TRY(ensure_dyn_smem(k_softmax_hist_sp<C, MODE, PX, MATH, OCC>, smem));
   int grid = resident_grid(k_softmax_hist_sp<C, MODE, PX, MATH, OCC>, kThreadsA, smem);
   const long long n_chunks = (a.n_tiles + kChunkTiles - 1) / kChunkTiles;
   if (grid > n_chunks) grid = static_cast<int>(n_chunks);
@@ -955,19 +942,9 @@ int launch_phase_a_gr(PhaseAArgs a, cudaStream_t st) {
   ga.slices = best;
   ga.n_units = n_groups * best;
   const size_t smem = kStage + sizeof(uint32_t) * C * words;
-  static thread_local bool configured = false;
-  if (!configured) {
-    HIAST_CUDA_TRY(cudaFuncSetAttribute(k_softmax_hist_gr<C, HINT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        static_cast<int>(kBudget)));
-    configured = true;
-  }
+  HIAST_TRY(ensure_dyn_smem(k_softmax_hist_gr<C, HINT>, kBudget));
   if (STATIC) {
-    static thread_local bool configured_s = false;
-    if (!configured_s) {
-      HIAST_CUDA_TRY(cudaFuncSetAttribute(k_softmax_hist_grs<C, HINT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          static_cast<int>(kBudget)));
-      configured_s = true;
-    }
+    HIAST_TRY(ensure_dyn_smem(k_softmax_hist_grs<C, HINT>, kBudget));
     ga.a = a;
     const int grid_s = static_cast<int>(std::min<long long>(sms, a.n_tiles));
     k_softmax_hist_grs<C, HINT><<<grid_s, kThreadsG, smem, st>>>(ga);

@@ -403,11 +403,7 @@ extern "C" int hiast_ias_threshold_scan(uint32_t* hist, int n_groups, int C, int
   k_hist_prefix<<<n_groups * C, kThreadsP, 0, st>>>(hist, nb);
   HIAST_CHECK_LAUNCH();
   const size_t smem = 2 * static_cast<size_t>(row_stride(nb)) * sizeof(uint32_t);
-  static thread_local size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    HIAST_CUDA_TRY(cudaFuncSetAttribute(k_threshold_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    configured = smem;
-  }
+  HIAST_TRY(ensure_dyn_smem(k_threshold_scan, smem));
   k_threshold_scan<<<C, kThreadsS, smem, st>>>(hist, n_groups, C, key_lo, nb, alpha, beta, gamma, thr_state, thr_groups,
                                                temp_groups, error_flag);
   HIAST_CHECK_LAUNCH();
@@ -430,11 +426,7 @@ extern "C" int hiast_ias_select(const float* conf, const uint8_t* label, const d
     const int tiles_pi = static_cast<int>((HW + px_per_tile * kSubC - 1) / (px_per_tile * kSubC));
     const long long ntl = static_cast<long long>(tiles_pi) * n_images;
     const size_t smem = static_cast<size_t>(C) * kThreadsC * sizeof(unsigned long long);
-    static thread_local size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-      HIAST_CUDA_TRY(cudaFuncSetAttribute(k_select_private, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-      configured = smem;
-    }
+    HIAST_TRY(ensure_dyn_smem(k_select_private, smem));
     // contiguous tile ranges (image-level flushes stay rare), 4x more CTAs than fit at once so that the hardware
     // scheduler evens out the tail (dynamic chunking was measured slower here: every chunk pays an image flush)
     int grid = resident_grid(k_select_private, kThreadsC, smem) * 4;

@@ -377,11 +377,7 @@ __global__ void __launch_bounds__(kThreadsU2, 1) k_upsample_softmax_hist_v2(UpAr
             } else if (bin >= hi0) {
               const int kk = bin - hi0;
               const unsigned sh = (kk & 1) * 16;
-              const uint32_t old = atomicAdd(s_tab + l * words + (kk >> 1), 1u << sh);
-              if (((old >> sh) & 0xffffu) == 0xffffu) {
-                if (sh == 0) atomicSub(s_tab + l * words + (kk >> 1), 1u << 16);
-                atomicAdd(g_hist + static_cast<size_t>(l) * nbs + bin, 65536u);
-              }
+              tab16_add(s_tab + l * words + (kk >> 1), sh, g_hist + static_cast<size_t>(l) * nbs + bin);
             } else {
               atomicAdd(g_hist + static_cast<size_t>(l) * nbs + bin, 1u);
             }
@@ -453,18 +449,10 @@ extern "C" int hiast_ias_upsample_softmax_hist(const float* logits_lr, int n_ima
         const size_t smem = stage + sizeof(uint32_t) * C * words;
         const int grid = static_cast<int>(std::min<long long>(sm_count(), v.a.n_tiles));
         if (C == 19) {
-          static thread_local bool configured = false;
-          if (!configured) {
-            HIAST_CUDA_TRY(cudaFuncSetAttribute(k_upsample_softmax_hist_v2<19>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kBudget)));
-            configured = true;
-          }
+          HIAST_TRY(ensure_dyn_smem(k_upsample_softmax_hist_v2<19>, kBudget));
           k_upsample_softmax_hist_v2<19><<<grid, kThreadsU2, smem, st>>>(ua);
         } else {
-          static thread_local bool configured = false;
-          if (!configured) {
-            HIAST_CUDA_TRY(cudaFuncSetAttribute(k_upsample_softmax_hist_v2<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kBudget)));
-            configured = true;
-          }
+          HIAST_TRY(ensure_dyn_smem(k_upsample_softmax_hist_v2<16>, kBudget));
           k_upsample_softmax_hist_v2<16><<<grid, kThreadsU2, smem, st>>>(ua);
         }
         HIAST_CHECK_LAUNCH();
@@ -485,20 +473,12 @@ extern "C" int hiast_ias_upsample_softmax_hist(const float* logits_lr, int n_ima
   if (rc != HIAST_OK) return rc;
   const long long n_chunks = (u.a.n_tiles + kChunkTiles - 1) / kChunkTiles;
   if (C == 19) {
-    static thread_local size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-      HIAST_CUDA_TRY(cudaFuncSetAttribute(k_upsample_softmax_hist<19, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-      configured = smem;
-    }
+    HIAST_TRY(ensure_dyn_smem(k_upsample_softmax_hist<19, 6>, smem));
     int grid = resident_grid(k_upsample_softmax_hist<19, 6>, kThreadsA, smem);
     if (grid > n_chunks) grid = static_cast<int>(n_chunks);
     k_upsample_softmax_hist<19, 6><<<grid, kThreadsA, smem, st>>>(u);
   } else {
-    static thread_local size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-      HIAST_CUDA_TRY(cudaFuncSetAttribute(k_upsample_softmax_hist<16, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-      configured = smem;
-    }
+    HIAST_TRY(ensure_dyn_smem(k_upsample_softmax_hist<16, 6>, smem));
     int grid = resident_grid(k_upsample_softmax_hist<16, 6>, kThreadsA, smem);
     if (grid > n_chunks) grid = static_cast<int>(n_chunks);
     k_upsample_softmax_hist<16, 6><<<grid, kThreadsA, smem, st>>>(u);

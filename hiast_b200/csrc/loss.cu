@@ -803,24 +803,19 @@ bool loss_vector_ok(const LossArgs& a, const void* extra) {
 
 size_t loss_stage_bytes(int C) { return sizeof(float2) * 2 * C * kThreadsL; }
 
-cudaError_t loss_configure_smem(int C, size_t smem) {
-  static thread_local bool done19 = false, done16 = false;
-  bool& done = (C == 19) ? done19 : done16;
-  if (done) return cudaSuccess;
-  cudaError_t e;
+int loss_configure_smem(int C, size_t smem) {
   if (C == 19) {
-    e = cudaFuncSetAttribute(k_loss_fwd<19>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_loss_bwd<19>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_loss_fwd_pk<19>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_loss_bwd_pk<19>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    HIAST_TRY(ensure_dyn_smem(k_loss_fwd<19>, smem));
+    HIAST_TRY(ensure_dyn_smem(k_loss_bwd<19>, smem));
+    HIAST_TRY(ensure_dyn_smem(k_loss_fwd_pk<19>, smem));
+    HIAST_TRY(ensure_dyn_smem(k_loss_bwd_pk<19>, smem));
   } else {
-    e = cudaFuncSetAttribute(k_loss_fwd<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_loss_bwd<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_loss_fwd_pk<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_loss_bwd_pk<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    HIAST_TRY(ensure_dyn_smem(k_loss_fwd<16>, smem));
+    HIAST_TRY(ensure_dyn_smem(k_loss_bwd<16>, smem));
+    HIAST_TRY(ensure_dyn_smem(k_loss_fwd_pk<16>, smem));
+    HIAST_TRY(ensure_dyn_smem(k_loss_bwd_pk<16>, smem));
   }
-  done = (e == cudaSuccess);
-  return e;
+  return HIAST_OK;
 }
 
 inline int cst_kind_host(int terms) { return terms & HIAST_CST_SOFTCE_LOGITS; }
@@ -866,7 +861,7 @@ extern "C" int hiast_st_loss_fwd(const float* z, const float* t, const void* plb
   if (loss_vector_ok(a, nullptr)) {
     grid = std::min(grid, sm_count() * 2);   // persistent: one resident wave, every thread pipelines its own sequence
     const size_t smem = loss_stage_bytes(C);
-    HIAST_CUDA_TRY(loss_configure_smem(C, smem));
+    HIAST_TRY(loss_configure_smem(C, smem));
     const bool packed = cst_kind_host(terms) == HIAST_CST_SOFTCE && !g_loss_scalar;
     if (packed) {
       if (C == 19) k_loss_fwd_pk<19><<<grid, kThreadsL, smem, st>>>(a, parts);
@@ -896,7 +891,7 @@ extern "C" int hiast_st_loss_bwd(const float* z, const float* t, const void* plb
   if (loss_vector_ok(a, grad_z)) {
     grid = std::min(grid, sm_count() * 2);
     const size_t smem = loss_stage_bytes(C);
-    HIAST_CUDA_TRY(loss_configure_smem(C, smem));
+    HIAST_TRY(loss_configure_smem(C, smem));
     const bool packed = cst_kind_host(terms) == HIAST_CST_SOFTCE && !g_loss_scalar;
     if (packed) {
       if (C == 19) k_loss_bwd_pk<19><<<grid, kThreadsL, smem, st>>>(a, scales, grad_z);

@@ -376,8 +376,7 @@ __global__ void __launch_bounds__(kValThreads) k_probs_upsample_argmax_staged(Sc
 template <int NS>
 int launch_staged(const ScaleSet& sc, const StageGeom& sg, size_t smem, int B, int C, int H, int W, uint8_t* label,
                   cudaStream_t st) {
-  HIAST_CUDA_TRY(cudaFuncSetAttribute(k_probs_upsample_argmax_staged<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      static_cast<int>(smem)));
+  HIAST_TRY(ensure_dyn_smem(k_probs_upsample_argmax_staged<NS>, smem));
   const long long tiles = static_cast<long long>(B) * ((H + kRowsV - 1) / kRowsV) * ((W + kValThreads - 1) / kValThreads);
   if (tiles > 0x7FFFFFFFll) return HIAST_ERR_UNSUPPORTED;
   k_probs_upsample_argmax_staged<NS><<<static_cast<int>(tiles), kValThreads, smem, st>>>(sc, sg, B, C, H, W, label);

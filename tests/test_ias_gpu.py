@@ -253,6 +253,60 @@ def test_full_resolution_hist_variants_match_plain_red(mode):
         assert int(hist.sum()) == 5 * H * W
 
 
+def _two_hot_neighbour_keys_logits(n, C, H, W, cls=5):
+    """Maps whose confidences alternate, pixel by pixel in raster order, between the fp16 keys 0x3BFE and 0x3BFF of ONE class:
+    the two 16-bit counters of one shared-memory word of the group-resident kernels, both driven far beyond 65 535."""
+    logits = torch.full((n, C, H, W), -100.0, device='cuda')
+    logits[:, cls] = 0.0
+    gap = torch.tensor([6.930, 7.624], device='cuda')            # 1 / (1 + e^-gap) = 1 - 2^-10, 1 - 2^-11
+    logits[:, cls + 1] = -gap[torch.arange(W, device='cuda') % 2]
+    probe = torch.softmax(logits[:1, :, :1, :2], dim=1).max(dim=1)[0].half().view(torch.int16).flatten().tolist()
+    assert probe == [0x3BFE, 0x3BFF], [hex(k) for k in probe]
+    return logits
+
+
+def test_shared_table_counters_with_two_hot_adjacent_keys():
+    """32 full-size maps put ~226 k pixels per CTA slice into EACH of two adjacent keys of one class (the
+    low and the high half of one packed shared-memory word).  Fifty repetitions of the default kernel must reproduce the
+    plain one-RED-per-pixel histogram every time (the half-range drain leaves no window in which a neighbour's increment
+    can observe a carry)."""
+    o = ops()
+    C, H, W, n = 19, 1024, 2048, 32
+    logits = _two_hot_neighbour_keys_logits(n, C, H, W)
+    _, _, want = o.ias_softmax_hist(logits, group_size=2, hist_mode=1)
+    key_lo = o.ias_key_lo(C)
+    assert int(want[:, 5, 0x3BFE - key_lo].sum()) == n * H * W // 2 and int(want[:, 5, 0x3BFF - key_lo].sum()) == n * H * W // 2
+    conf = torch.empty((n, H, W), device='cuda')
+    label = torch.empty((n, H, W), dtype=torch.uint8, device='cuda')
+    hist = torch.empty_like(want)
+    for rep in range(50):
+        o.ias_softmax_hist(logits, 2, key_lo, conf, label, hist, hist_mode=0)
+        assert torch.equal(hist, want), 'repetition %d' % rep
+    for B in (1, 3, 32):                                          # other flush patterns: a flush per image, ragged groups, one group
+        _, _, w1 = o.ias_softmax_hist(logits, group_size=B, hist_mode=1)
+        for rep in range(5):
+            _, _, h0 = o.ias_softmax_hist(logits, group_size=B, hist_mode=0)
+            assert torch.equal(h0, w1)
+
+
+def test_upsample_kernel_counters_drain_beyond_16_bits():
+    """The fused up-sampling kernel shares the packed shared-memory table: constant low-resolution maps put a whole CTA slice
+    into one counter (image k -> key 0x3BFE or 0x3BFF of one class)."""
+    o = ops()
+    C, H, W, n = 19, 1024, 2048, 8
+    lr = torch.full((n, C, 129, 257), -100.0, device='cuda')
+    lr[:, 5] = 0.0
+    lr[0::2, 6] = -6.930
+    lr[1::2, 6] = -7.624
+    full = torch.nn.functional.interpolate(lr, size=(H, W), mode='bilinear', align_corners=True)
+    _, _, want = o.ias_softmax_hist(full, group_size=2, hist_mode=1)
+    for rep in range(10):
+        _, _, hist = o.ias_upsample_softmax_hist(lr, (H, W), 2)
+        assert torch.equal(hist, want)
+    key_lo = o.ias_key_lo(C)
+    assert int(want[:, 5, 0x3BFE - key_lo].sum()) == n // 2 * H * W
+
+
 def test_empty_and_single_image():
     o = ops()
     logits = torch.randn(1, 19, 8, 16, device='cuda')
