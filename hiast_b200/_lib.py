@@ -23,6 +23,17 @@ IGNORE = 255
 
 _vp, _i, _i64, _sz, _d = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_double
 
+
+
+class WindowEmit(C.Structure):
+    """HiastWindowEmit of include/hiast_b200.h (argument block of hiast_ias_emit_window)."""
+    _fields_ = [(n, _vp) for n in ('conf', 'label', 'thr_groups', 'plbl', 'counts', 'confsum', 'mean_state', 'blob_dev',
+                                   'offsets_dev', 'png_ws', 'blob_host', 'offsets_host', 'plbl_host', 'counts_host',
+                                   'confsum_host', 'thr_groups_host')] + \
+               [('blob_capacity', _sz), ('png_ws_bytes', _sz), ('blob_copy_bytes', _sz), ('cp_gamma', _d)] + \
+               [(n, C.c_int32) for n in ('n_images', 'H', 'W', 'C', 'group_size', 'reserved')]
+
+
 _SIGNATURES = {
     'hiast_version': (_i, []),
     'hiast_status_string': (C.c_char_p, [_i]),
@@ -56,6 +67,16 @@ _SIGNATURES = {
     'hiast_png_max_bytes': (_sz, [_i, _i]),
     'hiast_png_segments': (_i, [_i, _i]),
     'hiast_write_files': (_i, [_vp, _vp, _vp, _i, _i, _vp]),
+    'hiast_stager_create': (_i, [_i, C.POINTER(_vp)]),
+    'hiast_stager_destroy': (_i, [_vp]),
+    'hiast_stager_push': (_i, [_vp, _i, _vp, _vp, _sz, _vp, _vp]),
+    'hiast_stager_release': (_i, [_vp, _i, _i, _vp]),
+    'hiast_ias_emit_window': (_i, [C.POINTER(WindowEmit), _vp]),
+    'hiast_writer_create': (_i, [_i, C.POINTER(_vp)]),
+    'hiast_writer_destroy': (_i, [_vp]),
+    'hiast_writer_submit': (_i64, [_vp, _vp, _i, _vp, _sz, _vp, _sz, _vp, _vp]),
+    'hiast_writer_wait': (_i, [_vp, _i64, C.POINTER(_i)]),
+    'hiast_dev_variants': (_i, []),
     'hiast_png_encode': (_i, [_vp, _i, _i, _i, _vp, _sz, _vp, _vp, _sz, _vp]),
     'hiast_resize_nearest_u8': (_i, [_vp, _i, _i, _i, _vp, _i, _i, _d, _d, _vp]),
     'hiast_softmax_flip_sum': (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp]),

@@ -16,8 +16,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libhiast_b200.so')
-SOURCES = ['api.cu', 'ias_phase_a.cu', 'ias_upsample.cu', 'ias_scan_select.cu', 'ias_fused.cu', 'cbst.cu', 'loss.cu', 'confusion.cu', 'copy_paste.cu', 'ema.cu', 'png.cu', 'resize.cu', 'validate.cu', 'ce_general.cu']
-HEADERS = ['common.cuh', 'ias_common.cuh', 'packed_math.cuh', 'scan_math.h', os.path.join('..', '..', 'include', 'hiast_b200.h')]
+SOURCES = ['api.cu', 'ias_phase_a.cu', 'ias_upsample.cu', 'ias_scan_select.cu', 'ias_fused.cu', 'cbst.cu', 'loss.cu', 'confusion.cu', 'copy_paste.cu', 'ema.cu', 'png.cu', 'resize.cu', 'validate.cu', 'ce_general.cu', 'host_pipeline.cu']
+HEADERS = ['common.cuh', 'ias_common.cuh', 'packed_math.cuh', 'scan_math.h', os.path.join('..', '..', 'include', 'hiast_b200.h'),
+           os.path.join('..', '..', 'include', 'hiast_b200_dev.h')]
 
 NVCC_FLAGS = [
     '-O3', '-std=c++17',
@@ -43,8 +44,17 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def _dev_flag():
+    """HIAST_DEV_VARIANTS=1 in the environment compiles the measured-and-dropped kernel variants (phase-A hist_modes other than
+    1 / 83, the TMA-staged kernel, the fused persistent window kernel) into the library; the product build leaves them out."""
+    return os.environ.get('HIAST_DEV_VARIANTS', '0') not in ('', '0')
+
+
 def build(force=False, verbose=False):
-    if not force and not _stale():
+    stamp = os.path.join(HERE, 'build', 'flavour')
+    want = 'dev' if _dev_flag() else 'product'
+    have = open(stamp).read().strip() if os.path.exists(stamp) else None
+    if not force and not _stale() and have == want:
         return LIB
     nvcc = find_nvcc()
     objdir = os.path.join(HERE, 'build')
@@ -54,7 +64,7 @@ def build(force=False, verbose=False):
     for src in SOURCES:
         obj = os.path.join(objdir, src.replace('.cu', '.o'))
         objs.append(obj)
-        cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', os.path.join(CSRC, src), '-o', obj]
+        cmd = [nvcc] + NVCC_FLAGS + (['-DHIAST_DEV_VARIANTS'] if _dev_flag() else []) + (['-Xptxas', '-v'] if verbose else []) + ['-c', os.path.join(CSRC, src), '-o', obj]
         procs.append((src, cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False
     for src, cmd, p in procs:
@@ -70,6 +80,8 @@ def build(force=False, verbose=False):
                                                          '-gencode', 'arch=compute_100a,code=sm_100a']
     subprocess.check_call(link)
     os.replace(LIB + '.tmp', LIB)
+    with open(stamp, 'w') as f:
+        f.write(want)
     return LIB
 
 

@@ -44,7 +44,15 @@ int ensure_dyn_smem_impl(const void* kernel, size_t bytes) {
 
 }  // namespace hiast
 
-extern "C" int hiast_version(void) { return 1000 * 0 + 1; }
+extern "C" int hiast_dev_variants(void) {
+#ifdef HIAST_DEV_VARIANTS
+  return 1;
+#else
+  return 0;
+#endif
+}
+
+extern "C" int hiast_version(void) { return 1000 * 0 + 2; }
 
 extern "C" const char* hiast_status_string(int status) {
   switch (status) {

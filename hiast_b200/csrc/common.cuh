@@ -6,6 +6,7 @@
 #include <stdint.h>
 
 #include "../../include/hiast_b200.h"
+#include "../../include/hiast_b200_dev.h"
 
 namespace hiast {
 

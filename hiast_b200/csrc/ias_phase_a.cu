@@ -942,22 +942,22 @@ int launch_phase_a_gr(PhaseAArgs a, cudaStream_t st) {
   ga.slices = best;
   ga.n_units = n_groups * best;
   const size_t smem = kStage + sizeof(uint32_t) * C * words;
-  HIAST_TRY(ensure_dyn_smem(k_softmax_hist_gr<C, HINT>, kBudget));
-  if (STATIC) {
+  ga.a = a;
+  if constexpr (STATIC) {
     HIAST_TRY(ensure_dyn_smem(k_softmax_hist_grs<C, HINT>, kBudget));
-    ga.a = a;
     const int grid_s = static_cast<int>(std::min<long long>(sms, a.n_tiles));
     k_softmax_hist_grs<C, HINT><<<grid_s, kThreadsG, smem, st>>>(ga);
     HIAST_CHECK_LAUNCH();
     return HIAST_OK;
+  } else {
+    HIAST_TRY(ensure_dyn_smem(k_softmax_hist_gr<C, HINT>, kBudget));
+    const int grid = std::min(sms, ga.n_units);
+    const int rc = next_sched_slot(&ga.a.sched, st);
+    if (rc != HIAST_OK) return rc;
+    k_softmax_hist_gr<C, HINT><<<grid, kThreadsG, smem, st>>>(ga);
+    HIAST_CHECK_LAUNCH();
+    return HIAST_OK;
   }
-  const int grid = std::min(sms, ga.n_units);
-  const int rc = next_sched_slot(&a.sched, st);
-  if (rc != HIAST_OK) return rc;
-  ga.a = a;
-  k_softmax_hist_gr<C, HINT><<<grid, kThreadsG, smem, st>>>(ga);
-  HIAST_CHECK_LAUNCH();
-  return HIAST_OK;
 }
 
 // hist_mode = 10 * pipeline + sink.  pipeline 0: 128-bit LDG, 4 px/thread; 1: TMA-staged; 2: 64-bit LDG, 2 px/thread;
@@ -974,7 +974,10 @@ template <int C>
 int launch_phase_a(const PhaseAArgs& a, int mode, cudaStream_t st) {
   if (mode == 0) mode = kDefaultHistMode;
   switch (mode) {
-    case 1: return launch_phase_a_ldg<C, 1, 4>(a, st);
+    case 1: return launch_phase_a_ldg<C, 1, 4>(a, st);        // plain kernel, one global RED per pixel: the cross-check
+    case 83: return launch_phase_a_gr<C, 0, 1>(a, st);        // the product kernel
+#ifdef HIAST_DEV_VARIANTS
+    // measured and dropped (profiles/): compiled only into the development build
     case 2: return launch_phase_a_ldg<C, 2, 4>(a, st);
     case 3: return launch_phase_a_ldg<C, 3, 4>(a, st);
     case 4: return launch_phase_a_ldg<C, 4, 4>(a, st);
@@ -992,13 +995,15 @@ int launch_phase_a(const PhaseAArgs& a, int mode, cudaStream_t st) {
     case 66: return launch_phase_a_sp<C, 6, 2, 1>(a, st);
     case 80: return launch_phase_a_gr<C, 0>(a, st);
     case 81: return launch_phase_a_gr<C, 1>(a, st);
-    case 83: return launch_phase_a_gr<C, 0, 1>(a, st);
     case 71: return launch_phase_a_sp<C, 1, 2, 1, 4>(a, st);
     case 76: return launch_phase_a_sp<C, 6, 2, 1, 4>(a, st);
     case 21: return launch_phase_a_ldg<C, 1, 2>(a, st);
     case 25: return launch_phase_a_ldg<C, 5, 2>(a, st);
     case 26: return launch_phase_a_ldg<C, 6, 2>(a, st);
     default: return HIAST_ERR_INVALID_ARG;
+#else
+    default: return HIAST_ERR_UNSUPPORTED;                    // a development variant: build with HIAST_DEV_VARIANTS=1
+#endif
   }
 }
 

@@ -12,6 +12,8 @@ place (the reference re-binds ``param_k.data`` to a fresh tensor; the values are
 
 from __future__ import annotations
 
+import weakref
+
 import numpy as np
 import torch
 
@@ -19,7 +21,9 @@ from ._lib import HiastError, check, lib, ptr, stream_ptr
 
 CHUNK_ELEMS = 1 << 15
 CHUNK_BYTES = 1 << 18
-_cache = {}
+# ema_model -> {id(model): entry}; entries hold a weak reference to ``model`` and die with either module, so a recycled
+# ``id()`` can never hit a stale entry and dead models' parameters are not kept alive
+_cache = weakref.WeakKeyDictionary()
 
 
 class _Tables:
@@ -43,7 +47,8 @@ def reset():
     """Forget the cached parameter lists / pointer tables (call after replacing Parameter objects in a model: the
     module trees are walked only on the first call for a given (ema_model, model) pair; re-allocated ``.data`` is
     detected automatically)."""
-    _cache.clear()
+    for k in list(_cache.keys()):
+        del _cache[k]
 
 
 def _validate(params, buffers):
@@ -61,12 +66,24 @@ def _validate(params, buffers):
 
 def update_ema_model(ema_model, model, gamma):
     """utils/utils.py:115-123.  Returns ``ema_model`` like the reference."""
-    key = (id(ema_model), id(model))
-    ent = _cache.get(key)
+    per_teacher = _cache.get(ema_model)
+    if per_teacher is None:
+        per_teacher = _cache[ema_model] = {}
+    ent = per_teacher.get(id(model))
+    if ent is not None:
+        # same objects as when the trees were walked?  (weak reference still alive and pointing at THIS model; the first
+        # Parameter of both trees unchanged -- replacing other Parameter objects needs reset(), see its docstring)
+        first_q, first_k = next(model.parameters(), None), next(ema_model.parameters(), None)
+        stale = ent['model']() is not model or (ent['params'] and (ent['params'][0][1] is not first_q or ent['params'][0][0] is not first_k))
+        if stale:
+            ent = None
     if ent is None:
         # the module trees are walked once; later calls only re-read the data pointers of the cached tensors
-        ent = _cache[key] = {'params': [(k, q) for q, k in zip(model.parameters(), ema_model.parameters())],
-                             'buffers': [(k, q) for q, k in zip(model.buffers(), ema_model.buffers())], 'ptrs': None}
+        for dead in [k for k, e in per_teacher.items() if e['model']() is None]:
+            del per_teacher[dead]
+        ent = per_teacher[id(model)] = {'model': weakref.ref(model),
+                                        'params': [(k, q) for q, k in zip(model.parameters(), ema_model.parameters())],
+                                        'buffers': [(k, q) for q, k in zip(model.buffers(), ema_model.buffers())], 'ptrs': None}
     params, buffers = ent['params'], ent['buffers']
     if not params and not buffers:
         return ema_model

@@ -277,33 +277,65 @@ HIAST_API int hiast_ce_general_bwd(const float* logits, const void* labels, int 
                          const void* refer_labels, int refer_bytes, int region, int ignore_index, int B, int C,
                          int64_t HW, const float* scale, float* grad_logits, void* stream);
 
-/* ---- host-side test hooks (no GPU needed; used by tests only) --------------------------- */
-/* x^n by double-double repeated squaring, the integer-gamma power used by the scan.          */
-HIAST_API double hiast_testhook_powi(double x, int n);
-/* One class, one group of hiast_ias_threshold_scan on the HOST from an inclusive-prefix
- * histogram row; returns the new threshold, *temp_out = the float32 quantile.               */
-HIAST_API double hiast_testhook_threshold_step(const uint32_t* prefix_row_host, int key_lo,
-                                     double thr, double alpha, double beta, double gamma,
-                                     float* temp_out, int* error_out);
+/* ---- host side of the pseudo-labelling loop  workflows/pseudo_label_generator.py:189-211 ------------------------
+ * HOST functions (they enqueue CUDA work but are not kernels).  What the reference does per batch with
+ * `data['images'].cuda()` (:190), per image with cv2.imwrite (:43-46) and per batch with numpy bookkeeping (:82-105)
+ * becomes a handful of foreign calls per WINDOW of batches; the interpreter never waits for the GPU.              */
 
-/* ---- development hooks -------------------------------------------------------------------- */
-/* Per-unit timeline of the next hiast_ias_fused_window launches: dev_buffer = u64 [n_SMs][256][6]
- * (kind << 32 | unit, begin, end, closer: wait begin, wait end, published; %globaltimer ns), zeroed by the caller;
- * NULL switches tracing off.                                                                   */
-HIAST_API int hiast_debug_validate_direct(int on);   /* 1: hiast_probs_upsample_argmax always takes the direct (unstaged) kernel */
-HIAST_API int hiast_debug_png_variant(int v);         /* emit kernel token loop: 0 nested (divergent), 1 (default) one token per iteration */
-HIAST_API int hiast_debug_set_fused_trace(void* dev_buffer);
-/* on != 0: hiast_st_loss_fwd / _bwd use the scalar vector kernels instead of the packed-pair (f32x2) ones for
- * the SoftCE consistency kind (A/B measurements and cross-checks).                               */
-HIAST_API int hiast_debug_loss_scalar(int on);
-/* on != 0: hiast_ias_upsample_softmax_hist uses its first kernel (4 horizontally adjacent pixels per thread).   */
-HIAST_API int hiast_debug_upsample_v1(int on);
+/* H2D staging ring.  Slot s is a caller-owned device buffer; two events per slot order the copy stream against the
+ * consumer stream: push = [copy_stream waits until the slot's previous contents were consumed] cudaMemcpyAsync on
+ * copy_stream, [consumer_stream waits for the copy]; release = "everything queued on consumer_stream so far has
+ * consumed slots first .. first+n-1".  A slot must be released before it is pushed again.                          */
+HIAST_API int hiast_stager_create(int n_slots, void** handle_out);
+HIAST_API int hiast_stager_destroy(void* handle);
+HIAST_API int hiast_stager_push(void* handle, int slot, void* dst_device, const void* src_host, size_t nbytes,
+                      void* copy_stream, void* consumer_stream);
+HIAST_API int hiast_stager_release(void* handle, int first_slot, int n_slots, void* consumer_stream);
 
-/* ---- device-side self test (needs a GPU; used by tests only) ---------------------------- */
-/* Sweeps EVERY non-positive float (bit patterns 0x80000000..0xFF800000 and +0) through the packed
- * (f32x2) exponential used by phase A and compares it bit for bit with CUDA's expf();
- * *mismatches_dev (device u64) receives the number of differing inputs.                      */
-HIAST_API int hiast_selftest_packed_expf(unsigned long long* mismatches_dev, void* stream);
+/* Everything a window of n_images owes the host after its thresholds are known, queued by ONE call on `stream`:
+ * zero counts / confsum, hiast_ias_select (:71-89), optionally hiast_ias_meanprob_scan (:95-105; mean_state NULL =
+ * skip), then either hiast_png_encode (:43-46; blob_dev != NULL) with the copies of the offset table and of the first
+ * blob_copy_bytes of the blob to pinned host memory, or (blob_dev NULL, plbl_host != NULL) the copy of the uint8
+ * label maps themselves; and the copies of counts / confsum / thr_groups (each nullable).  Host pointers must stay
+ * valid and untouched until the stream reaches this point (use an event or hiast_writer_submit's ticket).        */
+typedef struct HiastWindowEmit {
+  const float*   conf;            /* f32 [n,H,W]   phase A output                                   */
+  const uint8_t* label;           /* u8  [n,H,W]                                                    */
+  const double*  thr_groups;      /* f64 [g,C]     thresholds in force per group (phase B output)   */
+  uint8_t*       plbl;            /* u8  [n,H,W]   out                                              */
+  int64_t*       counts;          /* i64 [n,C]     out (zeroed here)                                */
+  uint64_t*      confsum;         /* u64 [g,C]     out (zeroed here)                                */
+  double*        mean_state;      /* f64 [C]       in/out, nullable                                 */
+  uint8_t*       blob_dev;        /* PNG blob on the device, nullable                               */
+  int64_t*       offsets_dev;     /* i64 [n+1]                                                      */
+  void*          png_ws;          /* hiast_png_workspace_bytes(n, H, W)                             */
+  uint8_t*       blob_host;       /* pinned                                                         */
+  int64_t*       offsets_host;    /* pinned i64 [n+1]                                               */
+  uint8_t*       plbl_host;       /* pinned u8 [n,H,W], used when blob_dev == NULL                  */
+  int64_t*       counts_host;     /* pinned, nullable                                               */
+  uint64_t*      confsum_host;    /* pinned, nullable                                               */
+  double*        thr_groups_host; /* pinned, nullable                                               */
+  size_t         blob_capacity;   /* bytes of blob_dev                                              */
+  size_t         png_ws_bytes;
+  size_t         blob_copy_bytes; /* predicted size of the window's files: copied with the window   */
+  double         cp_gamma;
+  int32_t        n_images, H, W, C, group_size, reserved;
+} HiastWindowEmit;
+HIAST_API int hiast_ias_emit_window(const HiastWindowEmit* args, void* stream);
+
+/* Asynchronous file writer (:43-46 without the interpreter).  submit records an event on `stream` (behind
+ * hiast_ias_emit_window's copies) and returns a ticket > 0 at once; a dispatcher thread sleeps on the event, then
+ * reads offsets_host[n_files] = the true size of the window's files, fetches blob_dev[bytes_copied .. total) if the
+ * predicted copy was short (blob_host_capacity must cover it) and the pool's POSIX writer threads create file i =
+ * blob_host[offsets_host[i] .. offsets_host[i+1]) at paths_host[i] (paths are copied by submit).  wait blocks until
+ * every ticket <= `ticket` is on disk; an I/O or CUDA failure is sticky (HIAST_ERR_IO / _CUDA, *errno_out).
+ * destroy drains the queue.  Negative return of submit = HIAST_ERR_*.                                            */
+HIAST_API int     hiast_writer_create(int n_threads, void** handle_out);
+HIAST_API int     hiast_writer_destroy(void* handle);
+HIAST_API int64_t hiast_writer_submit(void* handle, const char* const* paths_host, int n_files, const uint8_t* blob_host,
+                            size_t blob_host_capacity, const int64_t* offsets_host, size_t bytes_copied,
+                            const uint8_t* blob_dev, void* stream);
+HIAST_API int     hiast_writer_wait(void* handle, int64_t ticket, int* errno_out);
 
 #ifdef __cplusplus
 }

@@ -1,4 +1,5 @@
-"""The C-ABI library loads without a GPU and exports every symbol include/hiast_b200.h declares."""
+"""The C-ABI library loads without a GPU and exports every symbol include/hiast_b200.h (the drop-in boundary) and
+include/hiast_b200_dev.h (test hooks / A-B toggles) declare."""
 
 import ctypes
 import os
@@ -8,6 +9,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HEADER = os.path.join(ROOT, 'include', 'hiast_b200.h')
+DEV_HEADER = os.path.join(ROOT, 'include', 'hiast_b200_dev.h')
 
 
 @pytest.fixture(scope='module')
@@ -18,11 +20,20 @@ def built_lib():
     return path
 
 
-def declared_functions():
-    text = open(HEADER).read()
-    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
-    names = re.findall(r'\b(hiast_[a-z0-9_]+)\s*\(', text)
+def declared_functions(headers=(HEADER, DEV_HEADER)):
+    names = []
+    for h in headers:
+        text = open(h).read()
+        text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+        names += re.findall(r'\b(hiast_[a-z0-9_]+)\s*\(', text)
     return sorted(set(names))
+
+
+def test_public_header_holds_no_debug_or_test_symbols():
+    public = declared_functions((HEADER,))
+    assert not [n for n in public if 'debug' in n or 'testhook' in n or 'selftest' in n or n.startswith('hiast_dev_')]
+    dev = set(declared_functions((DEV_HEADER,))) - set(public)
+    assert all('debug' in n or 'testhook' in n or 'selftest' in n or n.startswith('hiast_dev_') for n in dev), dev
 
 
 def test_header_declares_the_expected_surface():

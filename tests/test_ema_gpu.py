@@ -74,3 +74,36 @@ def test_ema_update_rejects_cpu_models():
     from hiast_b200._lib import HiastError
     with pytest.raises(HiastError):
         update_ema_model(small_net(), small_net(), 0.99)
+
+
+def test_ema_cache_follows_the_modules_not_their_ids():
+    """the table cache is keyed by weak references -- a student that is dropped and replaced (possibly at the
+    same id()) is walked again, and entries die with their modules."""
+    import gc
+    from hiast_b200 import ema
+    ema.reset()
+    teacher = small_net().cuda()
+    for rep in range(4):
+        student = small_net().cuda()
+        with torch.no_grad():
+            for p in student.parameters():
+                p.fill_(float(rep + 1))
+            for p in teacher.parameters():
+                p.zero_()
+        ema.update_ema_model(teacher, student, 0.5)
+        for p in teacher.parameters():
+            assert torch.all(p == 0.5 * (rep + 1)), rep
+        del student
+        gc.collect()
+    assert len(ema._cache) == 1
+    # a replaced FIRST Parameter object is noticed without reset()
+    student = small_net().cuda()
+    ema.update_ema_model(teacher, student, 0.5)
+    student[0].weight = torch.nn.Parameter(torch.full_like(student[0].weight, 8.0))
+    with torch.no_grad():
+        teacher[0].weight.zero_()
+    ema.update_ema_model(teacher, student, 0.5)
+    assert torch.all(teacher[0].weight == 4.0)
+    del teacher
+    gc.collect()
+    assert len(ema._cache) == 0

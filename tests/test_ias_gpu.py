@@ -22,6 +22,28 @@ def ops():
     return o
 
 
+ALL_MODES = [1, 2, 3, 4, 5, 6, 11, 16, 21, 25, 26, 31, 36, 41, 46, 51, 56, 61, 66, 71, 76, 80, 81, 83]
+PRODUCT_MODES = [1, 83]
+
+
+def modes(wanted=ALL_MODES):
+    """The product library ships the plain kernel (1) and the group-resident kernel (83 = default 0); the measured-and-dropped
+    variants exist only in a development build (HIAST_DEV_VARIANTS=1 python -m hiast_b200.build --force)."""
+    from hiast_b200 import _lib
+    dev = bool(_lib.lib().hiast_dev_variants())
+    return [m for m in wanted if dev or m in (0, 1, 83)]
+
+
+def test_development_variants_are_not_in_the_product_library():
+    from hiast_b200 import _lib
+    o = ops()
+    x = torch.randn(1, 19, 8, 16, device='cuda')
+    if _lib.lib().hiast_dev_variants():
+        pytest.skip('development build')
+    with pytest.raises(_lib.HiastError, match='unsupported'):
+        o.ias_softmax_hist(x, group_size=2, hist_mode=56)
+
+
 def torch_softmax_max(logits):
     """The reference's own CUDA path for a1 (pseudo_label_generator.py:192-193)."""
     probs = torch.softmax(logits, dim=1)
@@ -29,9 +51,11 @@ def torch_softmax_max(logits):
 
 
 @pytest.mark.parametrize('shape', [(2, 19, 64, 128), (3, 19, 33, 52), (1, 16, 40, 64), (2, 7, 31, 51), (1, 40, 9, 13)])
-@pytest.mark.parametrize('mode', [1, 2, 3, 4, 5, 6, 11, 16, 21, 25, 26, 31, 36, 41, 46, 51, 56, 61, 66, 71, 76, 80, 81, 83])
+@pytest.mark.parametrize('mode', ALL_MODES)
 def test_phase_a_bit_exact_vs_torch_cuda(shape, mode):
     o = ops()
+    if mode not in modes():
+        pytest.skip('development variant (not in the product library)')
     g = torch.Generator().manual_seed(sum(shape) + mode)
     n, c, h, w = shape
     logits = torch.cat([gi.diffuse_logits(g, 1, c, h, w), gi.peaked_logits(g, n - 1, c, h, w)] if n > 1
@@ -51,7 +75,7 @@ def test_phase_a_bit_exact_vs_torch_cuda(shape, mode):
 
 
 def test_packed_expf_is_expf_for_every_non_positive_float():
-    """The f32x2 exponential of phase A (modes 51/56) against CUDA's expf(), all 2^31 - 2^23 + 2 inputs."""
+    """The f32x2 exponential of phase A (the product kernel and the loss kernels) against CUDA's expf(), all 2^31 - 2^23 + 2 inputs."""
     import ctypes
     from hiast_b200 import _lib
     bad = torch.ones(1, dtype=torch.int64, device='cuda')
@@ -83,7 +107,7 @@ def test_phase_a_randomised_stress_vs_torch_cuda(seed):
     x[:, 0] = torch.where(torch.isinf(x).all(dim=1), torch.zeros(()), x[:, 0])      # no all -inf pixel (NaN in torch too)
     x = x.cuda()
     want_conf, want_label = torch_softmax_max(x)
-    for mode in (56, 80, 83):
+    for mode in modes((56, 80, 83)):
         conf, label, hist = o.ias_softmax_hist(x, group_size=2, hist_mode=mode)
         assert torch.equal(conf, want_conf), (seed, mode)
         assert torch.equal(label.long(), want_label), (seed, mode)
@@ -110,7 +134,7 @@ def test_phase_a_ties_and_near_ties():
     x = torch.cat([x, x[:2] * 1e-6, x[:2] * 300.0])         # tiny logits: every channel a near tie; huge gaps
     x = x.cuda()
     want_conf, want_label = torch_softmax_max(x)
-    for mode in (0, 1, 6, 16, 26, 36, 46, 51, 56, 66, 76, 80, 81, 83):
+    for mode in modes((0, 1, 6, 16, 26, 36, 46, 51, 56, 66, 76, 80, 81, 83)):
         conf, label, _ = o.ias_softmax_hist(x, group_size=2, hist_mode=mode)
         assert torch.equal(conf, want_conf), mode
         assert torch.equal(label.long(), want_label), mode
@@ -178,7 +202,7 @@ def test_config0_vs_oracle():
     logits = torch.cat([lg for lg, _ in batches]).cuda()
     oracle = oias.IASOracle(C, spec['alpha'], spec['beta'], spec['gamma'], spec['cp_gamma'])
     oracle.run([(lg.cuda(), p) for lg, p in batches])
-    for mode in (1, 2, 3, 4, 5, 6, 11, 16, 21, 25, 26, 31, 36, 41, 46, 51, 56, 61, 66, 71, 76, 80, 81, 83):
+    for mode in modes():
         conf, label, hist = o.ias_softmax_hist(logits, group_size=B, hist_mode=mode)
         thr_state = torch.full((C,), 0.9, dtype=torch.float64, device='cuda')
         flag = torch.zeros(1, dtype=torch.int32, device='cuda')
@@ -230,6 +254,12 @@ def test_full_resolution_properties():
 
 @pytest.mark.parametrize('mode', [56, 80, 81, 83])
 def test_full_resolution_hist_variants_match_plain_red(mode):
+    if mode not in modes():
+        pytest.skip('development variant (not in the product library)')
+    _full_resolution_hist_variants_match_plain_red(mode)
+
+
+def _full_resolution_hist_variants_match_plain_red(mode):
     """Full-size maps through the packed-math / group-resident kernels == the plain one-RED-per-pixel kernel, on
     diffuse, peaked, saturated and CONSTANT maps (one (class, key) bin receives 2M pixels: exercises the 16-bit
     wrap of the shared-memory table), odd group sizes and a trailing 1-image group."""
