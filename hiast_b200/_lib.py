@@ -98,7 +98,7 @@ _lib = None
 
 
 class HiastError(RuntimeError):
-    pass
+    status = None          # the HIAST_ERR_* code when the error came from a C-ABI call
 
 
 def lib():
@@ -127,7 +127,9 @@ def check(status, what):
         msg = l.hiast_status_string(status).decode()
         if status == -3:
             msg += ' [cudaError %d]' % l.hiast_last_cuda_error()
-        raise HiastError('%s failed: %s' % (what, msg))
+        err = HiastError('%s failed: %s' % (what, msg))
+        err.status = status
+        raise err
 
 
 def ptr(t):

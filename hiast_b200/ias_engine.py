@@ -78,9 +78,20 @@ class IASEngine:
         if first_image % self.B or first_image + n > self.max_images:
             raise ValueError('bad window')
         g0 = first_image // self.B
-        ops.ias_upsample_softmax_hist(logits_lr, (self.H, self.W), self.B, self.key_lo,
-                                      self.conf[first_image:first_image + n], self.label[first_image:first_image + n],
-                                      self.hist[g0:g0 + self._groups(n)], accumulate=False)
+        try:
+            ops.ias_upsample_softmax_hist(logits_lr, (self.H, self.W), self.B, self.key_lo,
+                                          self.conf[first_image:first_image + n], self.label[first_image:first_image + n],
+                                          self.hist[g0:g0 + self._groups(n)], accumulate=False)
+        except ops._lib.HiastError as err:
+            if err.status != ops.UNSUPPORTED:
+                raise
+            # a shape the fused kernel does not cover (C not in {16, 19}, W % 4 != 0, down-sampling): the reference's own
+            # F.interpolate (self_training_segmentor.py:27), group by group to bound the full-resolution scratch, then the
+            # generic phase A -- same results, no fusion
+            for k in range(0, n, self.B):
+                full = torch.nn.functional.interpolate(logits_lr[k:k + self.B], size=(self.H, self.W), mode='bilinear',
+                                                       align_corners=True)
+                self.phase_a(full, first_image + k)
 
     def phase_a_from_conf(self, conf, label, first_image=0):
         """Same, from caller-provided conf f32 [n,H,W] / label (u8|i64) [n,H,W]; the engine's key range must

@@ -19,6 +19,7 @@ __all__ = [
     'ias_key_lo', 'ias_num_bins', 'ias_row_stride', 'ias_new_hist', 'ias_softmax_hist', 'ias_upsample_softmax_hist', 'ias_conf_hist', 'ias_threshold_scan',
     'ias_select', 'ias_meanprob_scan', 'ias_fused_window', 'UNSUPPORTED', 'cbst_sample_hist', 'cbst_quantile', 'copy_paste', 'hard_lut', 'st_loss_fwd', 'st_loss_bwd',
     'confusion_matrix', 'confusion_from_logits', 'iou_from_confusion', 'PngEncoder', 'resize_nearest_u8', 'softmax_flip_sum', 'probs_upsample_argmax', 'ce_general_fwd', 'ce_general_bwd', 'write_files',
+    'Stager', 'FileWriter', 'WindowEmitter',
 ]
 
 
@@ -572,3 +573,171 @@ def write_files(paths, blob_host, offsets, n_threads=8):
                                      int(n_threads), C.cast(C.pointer(err), C.c_void_p))
     if status != 0:
         raise OSError(err.value, 'hiast_write_files: %s' % os.strerror(err.value) if err.value else 'hiast_write_files failed')
+
+
+# ------------------------------------------------------------ host pipeline (csrc/host_pipeline.cu)
+class Stager:
+    """Host-to-device staging ring (``hiast_stager_*``): ``n_slots`` device slots of ``slot_bytes`` carved from one uint8 buffer,
+    filled by ``cudaMemcpyAsync`` on a copy stream.  ``push`` returns a device view (same dtype / shape as the host tensor) that
+    the consumer stream may use at once -- the ordering events are queued, the host never waits.  ``release`` marks slots as
+    consumed by everything queued on the consumer stream so far; a slot must be released before it is pushed again."""
+
+    def __init__(self, n_slots, slot_bytes, device, copy_stream):
+        self.n_slots, self.device, self.copy_stream = int(n_slots), torch.device(device), copy_stream
+        self.slot_bytes = (int(slot_bytes) + 255) // 256 * 256
+        self.ring = torch.empty(self.n_slots * self.slot_bytes, dtype=torch.uint8, device=self.device)
+        self._busy = [False] * self.n_slots
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(lib().hiast_stager_create(self.n_slots, C.byref(h)), 'hiast_stager_create')
+        self._h = h
+        self._push, self._release = lib().hiast_stager_push, lib().hiast_stager_release
+        self._base = self.ring.data_ptr()
+        self._cs = C.c_void_p(copy_stream.cuda_stream)
+
+    def busy(self, slot):
+        return self._busy[slot]
+
+    def push(self, slot, host_tensor, consumer_stream_ptr):
+        if self._busy[slot]:
+            raise _lib.HiastError('staging slot %d pushed again before it was released' % slot)
+        t = host_tensor if host_tensor.is_contiguous() else host_tensor.contiguous()
+        nbytes = t.numel() * t.element_size()
+        if nbytes > self.slot_bytes:
+            raise _lib.HiastError('batch of %d bytes does not fit a %d-byte staging slot' % (nbytes, self.slot_bytes))
+        off = slot * self.slot_bytes
+        check(self._push(self._h, slot, C.c_void_p(self._base + off), C.c_void_p(t.data_ptr()), nbytes, self._cs,
+                         consumer_stream_ptr), 'hiast_stager_push')
+        self._busy[slot] = True
+        return self.ring[off:off + nbytes].view(t.dtype).view(t.shape)
+
+    def release(self, first_slot, n_slots, consumer_stream_ptr):
+        check(self._release(self._h, first_slot, n_slots, consumer_stream_ptr), 'hiast_stager_release')
+        for k in range(first_slot, first_slot + n_slots):
+            self._busy[k] = False
+
+    def view_of(self, first_ptr, nbytes, dtype, shape):
+        """A tensor over ring memory [first_ptr, first_ptr + nbytes) (consecutive slots of one window), else None."""
+        off = first_ptr - self._base
+        if off < 0 or off + nbytes > self.ring.numel():
+            return None
+        return self.ring[off:off + nbytes].view(dtype).view(shape)
+
+    def close(self):
+        if self._h is not None:
+            lib().hiast_stager_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class FileWriter:
+    """Persistent native writer pool (``hiast_writer_*``).  ``submit`` returns a ticket immediately; the files are on disk
+    when ``wait(ticket)`` returns (foreign call, interpreter lock released)."""
+
+    def __init__(self, n_threads, device):
+        self.device = torch.device(device)
+        h = C.c_void_p()
+        check(lib().hiast_writer_create(max(1, int(n_threads)), C.byref(h)), 'hiast_writer_create')
+        self._h = h
+        self.n_threads = max(1, int(n_threads))
+
+    def submit(self, paths, blob_host, offsets_host, bytes_copied, blob_dev, stream_ptr_):
+        n = len(paths)
+        arr = (C.c_char_p * n)(*[os.fsencode(p) for p in paths])
+        t = lib().hiast_writer_submit(self._h, C.cast(arr, C.c_void_p), n, C.c_void_p(blob_host.data_ptr()), blob_host.numel(),
+                                      C.c_void_p(offsets_host.data_ptr()), int(bytes_copied), C.c_void_p(blob_dev.data_ptr()),
+                                      stream_ptr_)
+        if t <= 0:
+            check(int(t) if t < 0 else -1, 'hiast_writer_submit')
+        return int(t)
+
+    def wait(self, ticket):
+        err = C.c_int(0)
+        status = lib().hiast_writer_wait(self._h, int(ticket), C.byref(err))
+        if status == -5:
+            raise OSError(err.value, 'pseudo-label file writer: %s' % os.strerror(err.value))
+        check(status, 'hiast_writer_wait')
+
+    def close(self):
+        if self._h is not None:
+            lib().hiast_writer_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class WindowEmitter:
+    """Per-window outputs through ONE foreign call (``hiast_ias_emit_window``): phase C, optional mean-prob EMA, the PNG
+    encoder (``png=True``) or the raw uint8 label maps (``png=False``), and every device-to-host copy, into the pinned
+    buffers of one of ``n_slots`` emit slots.  The caller orders reuse of a slot (writer ticket or event)."""
+
+    def __init__(self, engine, window_images, n_slots=3, png=True):
+        e = self.engine = engine
+        self.window, self.n_slots, self.png = int(window_images), int(n_slots), bool(png)
+        self.device = e.device
+        n, g, c, hw = self.window, (self.window + e.B - 1) // e.B, e.C, e.H * e.W
+        l = lib()
+        self.slots = []
+        self.max_file = l.hiast_png_max_bytes(e.H, e.W) if png else 0
+        if png and self.max_file == 0:
+            raise _lib.HiastError('unsupported PNG size %dx%d' % (e.H, e.W))
+        ws_bytes = l.hiast_png_workspace_bytes(n, e.H, e.W) if png else 0
+        self._png_ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=self.device) if png else None
+        cap = self.max_file * n + 4096
+        self.predicted = cap // 4 + 4096                    # bytes of a window's files; refined from every finished window
+        for _ in range(self.n_slots):
+            s = dict(counts_host=torch.empty((n, c), dtype=torch.int64).pin_memory(),
+                     confsum_host=torch.empty((g, c), dtype=torch.int64).pin_memory(),
+                     thr_host=torch.empty((g, c), dtype=torch.float64).pin_memory())
+            if png:
+                s.update(blob_dev=torch.empty(cap, dtype=torch.uint8, device=self.device),
+                         offsets_dev=torch.empty(n + 1, dtype=torch.int64, device=self.device),
+                         blob_host=torch.empty(cap, dtype=torch.uint8).pin_memory(),
+                         offsets_host=torch.zeros(n + 1, dtype=torch.int64).pin_memory())
+            else:
+                s.update(plbl_host=torch.empty((n, e.H, e.W), dtype=torch.uint8).pin_memory())
+            a = _lib.WindowEmit()
+            a.H, a.W, a.C, a.group_size, a.cp_gamma = e.H, e.W, e.C, e.B, e.cp_gamma
+            a.counts_host, a.confsum_host, a.thr_groups_host = (s['counts_host'].data_ptr(), s['confsum_host'].data_ptr(),
+                                                                s['thr_host'].data_ptr())
+            if png:
+                a.blob_dev, a.offsets_dev, a.png_ws = s['blob_dev'].data_ptr(), s['offsets_dev'].data_ptr(), self._png_ws.data_ptr()
+                a.blob_host, a.offsets_host = s['blob_host'].data_ptr(), s['offsets_host'].data_ptr()
+                a.blob_capacity, a.png_ws_bytes = cap, self._png_ws.numel()
+            else:
+                a.plbl_host = s['plbl_host'].data_ptr()
+            s['args'] = a
+            self.slots.append(s)
+        self._emit = l.hiast_ias_emit_window
+
+    def emit(self, slot, first_image, n_images, with_mean_prob=False):
+        """Queue the outputs of engine images [first_image, first_image + n) into emit slot ``slot`` on the current stream."""
+        e, s = self.engine, self.slots[slot]
+        a = s['args']
+        g0 = first_image // e.B
+        a.conf = e.conf.data_ptr() + first_image * e.H * e.W * 4
+        a.label = e.label.data_ptr() + first_image * e.H * e.W
+        a.plbl = e.plbl.data_ptr() + first_image * e.H * e.W
+        a.thr_groups = e.thr_groups.data_ptr() + g0 * e.C * 8
+        a.counts = e.counts.data_ptr() + first_image * e.C * 8
+        a.confsum = e.confsum.data_ptr() + g0 * e.C * 8
+        a.mean_state = e.mean_state.data_ptr() if with_mean_prob else None
+        a.n_images = n_images
+        copied = 0
+        if self.png:
+            copied = a.blob_copy_bytes = min(self.predicted, s['blob_dev'].numel())
+        check(self._emit(C.byref(a), stream_ptr(self.device)), 'hiast_ias_emit_window')
+        return copied
+
+    def learn(self, total_bytes):
+        """Feed back the size of a finished window's files (the next windows copy 1.25 x that with their results)."""
+        self.predicted = int(total_bytes) + int(total_bytes) // 4 + 65536

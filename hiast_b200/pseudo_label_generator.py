@@ -2,25 +2,36 @@
 
 Mirrors ``workflows/pseudo_label_generator.py`` (reference, /root/reference/code):
 ``BasePseudoGenerator`` :14-106, ``ConstantThresholdPseudoGenerator`` ('CT') :109-132,
-``NoThresholdPseudoGenerator`` ('NT') :135-139, ``IASPseudoGenerator`` ('IAS') :168-213.  Same
-constructor (``PSEUDO_POLICY[type](cfg)``), same attributes (``class_threshold``, ``class_mean_probs``,
-``statics_class``, ``sample_stats``, ``samples_class``), same methods and the same files written by
-``save_pseudo_label`` / ``save_data``.
+``NoThresholdPseudoGenerator`` ('NT') :135-139, ``CBSTPseudoGenerator`` ('CBST') :142-165,
+``IASPseudoGenerator`` ('IAS') :168-213.  Same constructor (``PSEUDO_POLICY[type](cfg)``), same attributes
+(``class_threshold``, ``class_mean_probs``, ``statics_class``, ``sample_stats``, ``samples_class``), same methods and the
+same files written by ``save_pseudo_label`` / ``save_data``.
 
-What changes is where the work happens.  The reference copies conf (f32) + label (int64) of every
-batch to the host (12 B/px) and runs numpy / Python loops there; here logits never leave the GPU:
-each batch goes through phase A as it arrives, a window of batches is then scanned (phase B) and
-masked (phase C) on the device and ENCODED AS PNG FILES on the device (``hiast_png_encode``); only the finished
-files (typically 2-5 % of the label bytes), the per-image class counts and the thresholds come back, and a small
-thread pool writes the files.  ``png='host'`` (or an overridden ``save_pseudo_label`` hook) keeps the reference's
-``cv2.imwrite`` on uint8 label maps copied back at 1 B/px.
+What changes is where the work happens.  The reference copies conf (f32) + label (int64) of every batch to the host
+(12 B/px) and runs numpy / Python loops there.  Here the logits never leave the GPU and the interpreter never waits for it:
 
-The backbone and the datasets are outside this package: ``initialize`` takes an
-injected ``model`` / ``loader`` (any callable returning ``{'logits': [B,C,H,W]}``; any iterable of
-``{'images', 'image_paths'}``).  Inside a reference checkout, bind the reference's own
-``initialize`` instead (INTEGRATION.md).
+    host loop (one thread)        per batch: one foreign call stages the batch into a device ring over a copy stream
+                                  (``hiast_stager_push``), the model runs, phase A is launched (full-resolution logits) or the
+                                  stride-8 logits are queued for ONE fused up-sampling launch per window;
+    window j closes               phase A(j) is complete on the main stream; the threshold chain of window j-1 (token receive,
+                                  scan, token send) is queued on a high-priority side stream behind A(j), so that it runs in the
+                                  shadow of phase C / the PNG encoder of window j-2, which are queued on the main stream next
+                                  (``hiast_ias_emit_window``: one call for mask, counts, encoder and every device-to-host copy);
+    completion                    a native writer pool sleeps on the window's event and puts the files on disk
+                                  (``hiast_writer_*``); the interpreter picks up counts / thresholds from pinned buffers when it
+                                  is about to reuse them, three windows later.
 
-``CBSTPseudoGenerator`` ('CBST') :142-165 is implemented on the device as well (two passes over the loader).
+``png='host'`` (or an overridden ``save_pseudo_label`` hook) keeps the reference's per-image ``cv2.imwrite`` on uint8 label maps
+copied back at 1 B/px, through the same deferred completion.
+
+``initialize`` takes an injected ``model`` / ``loader`` (any callable returning ``{'logits': [B,C,H,W]}`` or the network's own
+``{'logits_lr': stride-8 logits, 'size': (H, W)}``; any iterable of ``{'images', 'image_paths'}``).  Without them it does what the
+reference's ``initialize`` (:25-41) does through the registries: ``MODEL[cfg.model.type](cfg)`` + checkpoint from
+``cfg.pseudo_policy.resume_from``, ``DATASET[cfg.dataset.target.type](...)`` in a shuffled ``DataLoader`` -- the backbone and the
+datasets themselves are outside this package and have to be registered by the host project.
+
+``IAS_SHARDED`` runs the same pipeline over R ranks (one process per GPU): windows are striped over the ranks and the 19-double
+threshold state is handed rank to rank (NCCL send / recv) inside the side-stream chain.
 """
 
 from __future__ import annotations
@@ -33,8 +44,9 @@ import numpy as np
 import torch
 
 from . import ops
+from ._lib import HiastError, stream_ptr
 from .ias_engine import IASEngine
-from .registry import PSEUDO_POLICY
+from .registry import DATASET, MODEL, PSEUDO_POLICY
 
 
 def _cfg_get(node, path, default=None):
@@ -45,23 +57,27 @@ def _cfg_get(node, path, default=None):
     return node
 
 
-_COPY_STREAMS = {}
+def _stream(device, kind):
+    from .sharded import device_stream
+    return device_stream(device, kind)
 
 
-def _copy_stream(device):
-    """One host-to-device copy stream per device for the life of the process: the caching allocator keeps a block pool per
-    stream, so a fresh stream per run() would cudaMalloc every batch again (measured: 260 us per batch instead of 23)."""
-    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
-    st = _COPY_STREAMS.get(key)
-    if st is None:
-        st = _COPY_STREAMS[key] = torch.cuda.Stream(device)
-    return st
+class LowResLogits:
+    """Stride-8 logits [B,C,h,w] together with the size they are to be up-sampled to (bilinear, align_corners=True)."""
+
+    def __init__(self, logits_lr, size):
+        self.logits_lr, self.size = logits_lr, (int(size[0]), int(size[1]))
+
+    @property
+    def shape(self):
+        b, c = self.logits_lr.shape[:2]
+        return (b, c, self.size[0], self.size[1])
 
 
 class BasePseudoGenerator:
 
     def __init__(self, cfg, model=None, loader=None, dataset_len=None, save_dir=None, window_batches=8,
-                 device='cuda', png_workers=8, png='device', prefetch=None, defer_sync=True):
+                 device='cuda', png_workers=None, png='device', prefetch=None, defer_sync=True, stage_bytes=3 << 30):
         self.cfg = cfg
         self.statics_class = np.array([0] * self.cfg.dataset.num_classes)                # :18
         self.sample_stats = []                                                           # :19
@@ -70,40 +86,91 @@ class BasePseudoGenerator:
         self.class_threshold = None
         self.device = torch.device(device)
         self.window_batches = int(window_batches)
-        self.defer_sync = bool(defer_sync)            # complete a window's outputs while the next one is computed
-        self.prefetch = None if prefetch is None else int(prefetch)   # H2D copies issued this many batches ahead (None: auto, 0: inline)
+        self.defer_sync = bool(defer_sync)            # False: complete every window before the next one starts (debugging)
+        self.prefetch = None if prefetch is None else int(prefetch)   # 0: plain .to(device) on the main stream, no staging ring
+        self.stage_bytes = int(stage_bytes)           # device memory of the host-to-device staging ring
         self._model_arg, self._loader_arg, self._len_arg, self._save_dir_arg = model, loader, dataset_len, save_dir
+        if png_workers is None:
+            png_workers = self._default_workers()
         self._png_pool = ThreadPoolExecutor(max_workers=png_workers) if png_workers > 0 else None
         self._png_workers = max(1, int(png_workers))
         self._png_jobs = []
-        self._png_slot_jobs = [[], []]              # device PNG path: writers of the two pinned blob buffers
-        self._png_slot = 0
         if png not in ('device', 'host'):
             raise ValueError("png must be 'device' or 'host'")
         self.png = png
-        self._png_encoder = None
         self._engine = None
+        self._stager = None
+        self._writer = None
         self.pow_rounding_certified = True
         self.initialize()
 
+    @staticmethod
+    def _default_workers():
+        """File-writer threads: the host cores this rank may use (cores / ranks on the node) minus the interpreter's own,
+        at most 8 -- eight ranks with eight writers each on a 32-core host only fight each other."""
+        local = int(os.environ.get('LOCAL_WORLD_SIZE', os.environ.get('WORLD_SIZE', '1')) or 1)
+        try:
+            cores = len(os.sched_getaffinity(0))
+        except (AttributeError, OSError):
+            cores = os.cpu_count() or 1
+        return max(1, min(8, cores // max(1, local) - 1))
+
     # ------------------------------------------------------------------ set-up
     def initialize(self):
-        """:25-41.  The reference builds the segmentation model and the target DataLoader from cfg; both are
-        outside this package, so they are injected.  The save-dir contract (:38-41) is kept."""
-        if self._model_arg is None or self._loader_arg is None:
-            raise RuntimeError('hiast_b200 pseudo-label generators need model= and loader= (the DeepLabv2 backbone and '
-                               'the dataset loaders are not part of this package; see INTEGRATION.md)')
-        self.model = self._model_arg
-        self.t_loader = self._loader_arg
-        n = self._len_arg
-        if n is None:
-            ds = getattr(self.t_loader, 'dataset', None)
-            n = len(ds) if ds is not None else None
-        self.t_dataset = range(n) if n is not None else None
-        self.pseudo_label_save_dir = self._save_dir_arg or _cfg_get(self.cfg, 'pseudo_policy.save_dir')
+        """:25-41.  Injected ``model`` / ``loader`` are used as they are; otherwise both are built from cfg through the
+        registries exactly like the reference (model: ``utils.load_model``, utils/utils.py:68-89; loader: :29-36)."""
+        cfg = self.cfg
+        if self._model_arg is not None:
+            self.model = self._model_arg
+        else:
+            self.model = self._load_model(_cfg_get(cfg, 'pseudo_policy.resume_from'))
+        if self._loader_arg is not None:
+            self.t_loader = self._loader_arg
+            n = self._len_arg
+            if n is None:
+                ds = getattr(self.t_loader, 'dataset', None)
+                n = len(ds) if ds is not None else None
+            self.t_dataset = range(n) if n is not None else None
+        else:
+            self.t_dataset, self.t_loader = self._build_target_loader()
+        self.pseudo_label_save_dir = self._save_dir_arg or _cfg_get(cfg, 'pseudo_policy.save_dir')
         assert self.pseudo_label_save_dir is not None and \
             (not os.path.exists(self.pseudo_label_save_dir) or len(os.listdir(self.pseudo_label_save_dir)) == 0)
         os.makedirs(self.pseudo_label_save_dir, exist_ok=True)
+
+    def _load_model(self, resume_from):
+        """utils/utils.py:68-89 ``load_model(cfg, resume_from)`` + ``.cuda()`` (:27)."""
+        mtype = _cfg_get(self.cfg, 'model.type')
+        if mtype not in MODEL:
+            raise RuntimeError("PSEUDO_POLICY[...](cfg) without model=: MODEL[%r] is not registered.  The backbone is outside "
+                               "hiast_b200: register the host project's segmentor (INTEGRATION.md section 1) or pass model=" % (mtype,))
+        model = MODEL[mtype](self.cfg)
+        if resume_from is not None:
+            own = model.state_dict()
+            loaded = torch.load(resume_from, map_location='cpu')
+            strip = 7 if 'module' in list(loaded.keys())[0] else 0          # saved from DistributedDataParallel (:78-79)
+            own.update({k[strip:]: v for k, v in loaded.items() if k[strip:] in own})
+            model.load_state_dict(own)
+            print('%% load model from {}'.format(resume_from))
+        else:
+            import warnings
+            warnings.warn('not load model')
+        return model.to(self.device)
+
+    def _build_target_loader(self):
+        """:29-36  target dataset at ``pseudo_policy.resize_size`` in a shuffled DataLoader."""
+        from torch.utils.data import DataLoader
+        cfg = self.cfg
+        ttype = _cfg_get(cfg, 'dataset.target.type')
+        if ttype not in DATASET:
+            raise RuntimeError("PSEUDO_POLICY[...](cfg) without loader=: DATASET[%r] is not registered.  The datasets are outside "
+                               "hiast_b200: register the host project's dataset class or pass loader=" % (ttype,))
+        rs = cfg.pseudo_policy.resize_size
+        aug_type = ['PRS-{}-{}'.format(rs[0], rs[1])]
+        ds = DATASET[ttype](cfg, cfg.dataset.target.json_path, cfg.dataset.target.image_dir, aug_type=aug_type,
+                            num_classes=cfg.dataset.num_classes)
+        loader = DataLoader(ds, cfg.pseudo_policy.batch_size, shuffle=True, num_workers=cfg.dataset.num_workers, pin_memory=True)
+        return ds, loader
 
     # ------------------------------------------------------------------ outputs
     def save_pseudo_label(self, plbl, img_path):
@@ -120,7 +187,7 @@ class BasePseudoGenerator:
 
     def save_pseudo_label_file(self, png_bytes, img_path):
         """:43-46 with the file already encoded on the device: same name, same decoded pixels.  (Hook: when a subclass
-        overrides it, files are handed over one by one; otherwise a window is written by one hiast_write_files call.)"""
+        overrides it, files are handed over one by one; otherwise the native writer pool puts a window on disk.)"""
         plbl_save_path = self._pseudo_label_path(img_path)
         with open(plbl_save_path, 'wb') as f:
             f.write(png_bytes)
@@ -129,47 +196,22 @@ class BasePseudoGenerator:
         """The device writer is used unless the caller asked for the host one or hooked save_pseudo_label."""
         return self.png == 'device' and type(self).save_pseudo_label is BasePseudoGenerator.save_pseudo_label
 
-    def _save_file_async(self, png_bytes, img_path, slot):
-        if self._png_pool is None:
-            self.save_pseudo_label_file(png_bytes, img_path)
-        else:
-            self._png_slot_jobs[slot].append(self._png_pool.submit(self.save_pseudo_label_file, png_bytes, img_path))
-
-    def _wait_png_slot(self, slot):
-        for job in self._png_slot_jobs[slot]:
-            job.result()
-        self._png_slot_jobs[slot] = []
+    def _native_files(self):
+        return type(self).save_pseudo_label_file is BasePseudoGenerator.save_pseudo_label_file
 
     def _save_async(self, plbl, img_path):
+        """One label map to ``save_pseudo_label``: overridden hooks inline and in order, cv2.imwrite on the thread pool."""
         if self._png_pool is None or type(self).save_pseudo_label is not BasePseudoGenerator.save_pseudo_label:
-            self.save_pseudo_label(plbl, img_path)       # overridden hooks are called inline, in order
-        else:
-            self._png_jobs.append(self._png_pool.submit(self.save_pseudo_label, plbl, img_path))
-
-    def _finish_pending_emit(self):
-        """Complete the window whose outputs were queued by ``_emit_window(..., defer=True)``: wait for ITS event (the GPU is
-        one window further by now), do the per-image bookkeeping, hand the finished files to the native writer."""
-        p = getattr(self, '_pending_emit', None)
-        if p is None:
-            return
-        self._pending_emit = None
-        blob_host, offsets = p['enc'].finish(p['handle'])
-        counts_h = p['counts'].numpy()[:p['n']].copy()
-        for i in range(p['n']):
-            self._record_image(counts_h[i], p['paths'][i])
-        targets = [self._pseudo_label_path(q) for q in p['paths']]
-        self._png_slot_jobs[p['slot']].append(self._png_pool.submit(ops.write_files, targets, blob_host, offsets,
-                                                                    self._png_workers))
-        if p.get('after') is not None:
-            p['after']()
+            self.save_pseudo_label(plbl, img_path)
+            return None
+        job = self._png_pool.submit(self.save_pseudo_label, plbl, img_path)
+        self._png_jobs.append(job)
+        return job
 
     def _wait_png(self):
-        self._finish_pending_emit()
         for job in self._png_jobs:
             job.result()
         self._png_jobs = []
-        self._wait_png_slot(0)
-        self._wait_png_slot(1)
 
     def save_data(self):
         """:48-62  same file names, formats and locations (one level above the PNG directory)."""
@@ -193,12 +235,12 @@ class BasePseudoGenerator:
     def _record_image(self, counts_row, img_path):
         """:82-89 from the per-image class counts computed on the device."""
         current_stats = {}
-        for i in range(self.cfg.dataset.num_classes):
+        for i in np.flatnonzero(counts_row):
             pix_num = int(counts_row[i])
-            if pix_num != 0:
-                current_stats[i] = pix_num
-                self.samples_class[i].append([img_path, pix_num])
-                self.statics_class[i] += pix_num
+            i = int(i)
+            current_stats[i] = pix_num
+            self.samples_class[i].append([img_path, pix_num])
+            self.statics_class[i] += pix_num
         current_stats['file'] = img_path
         self.sample_stats.append(current_stats)
 
@@ -228,239 +270,385 @@ class BasePseudoGenerator:
         return plbl_h[-1].astype(np.int64)
 
     # ------------------------------------------------------------ device loop
-    def _make_engine(self, logits, alpha=0.0, beta=0.0, gamma=1.0):
-        b, c, h, w = logits.shape       # a LowResLogits reports the up-sampled (image) size
+    def _group_size(self, b):
         group = int(_cfg_get(self.cfg, 'pseudo_policy.batch_size', b) or b)
-        group = max(group, b)
-        return IASEngine(c, h, w, group, alpha, beta, gamma, self._cp_gamma(), group * self.window_batches,
-                         device=self.device)
+        return max(group, b)
 
-    def _device_batches(self):
-        """(images on the device, image_paths) for every loader batch.  With ``prefetch > 0`` a producer thread walks the loader
-        and issues the host-to-device copies on its own stream, up to ``prefetch`` batches ahead, so the copies of the next window
-        run while the main thread sits in the stream sync at the end of the current one (the consumer waits on each batch's event)."""
-        depth = getattr(self, 'prefetch', 0)
-        if (depth is not None and depth <= 0) or self.device.type != 'cuda':
-            for data in self.t_loader:
-                yield data['images'].to(self.device, non_blocking=True), list(data['image_paths'])
+    def _make_engine(self, shape, alpha=0.0, beta=0.0, gamma=1.0):
+        """Engine with room for THREE windows: phase A of window j, the threshold chain of j-1 and the outputs of j-2 are
+        in flight together (module docstring)."""
+        b, c, h, w = shape                  # a LowResLogits reports the up-sampled (image) size
+        group = self._group_size(b)
+        n = 3 * group * self.window_batches
+        factory = getattr(self, '_engine_factory', None)
+        if factory is not None:
+            return factory(c, h, w, group, alpha, beta, gamma, self._cp_gamma(), n)
+        return IASEngine(c, h, w, group, alpha, beta, gamma, self._cp_gamma(), n, device=self.device)
+
+    def _staged(self, images, pipe):
+        """Host batch -> (device tensor, staging slot or None).  The copy runs on the copy stream into a ring slot; the main
+        stream is made to wait for it, the host is not."""
+        if self.device.type != 'cuda' or not torch.is_tensor(images) or images.is_cuda:
+            return (images.to(self.device) if torch.is_tensor(images) and images.device != self.device else images), None
+        if self.prefetch == 0:
+            return images.to(self.device, non_blocking=True), None
+        st = self._stager
+        nbytes = images.numel() * images.element_size()
+        if st is None or nbytes > st.slot_bytes:
+            if st is not None:                                       # a larger batch than the ring was built for
+                if pipe is not None:
+                    pipe.flush_queued()
+                torch.cuda.current_stream(self.device).synchronize()
+                st.close()
+            slot_bytes = max(nbytes, 1)
+            n_slots = 3 * self.window_batches                        # three windows of batches, window-aligned
+            if n_slots * slot_bytes > self.stage_bytes:             # big batches (full-resolution logits): a short ring
+                n_slots = max(4, min(n_slots, self.stage_bytes // slot_bytes))
+            st = self._stager = ops.Stager(n_slots, slot_bytes, self.device, _stream(self.device, 'copy'))
+            self._stage_cursor = 0
+        slot = self._stage_cursor % st.n_slots
+        if st.busy(slot):
+            if pipe is None:
+                raise HiastError('staging ring exhausted')
+            pipe.flush_queued()                                      # launches the queued phase A and releases its slots
+        self._stage_cursor += 1
+        return st.push(slot, images, stream_ptr(self.device)), slot
+
+    def _release_staged(self, slots):
+        st = self._stager
+        if st is None or not slots:
             return
-        import queue
-        import threading
-        q = queue.Queue()
-        copy_stream = _copy_stream(self.device)
-        stop = threading.Event()
-        slots = []                                # semaphore, created by the producer once the batch size is known
+        main = stream_ptr(self.device)
+        slots = sorted(slots)
+        run0 = prev = slots[0]
+        for s in slots[1:] + [None]:
+            if s is None or s != prev + 1:
+                st.release(run0, prev - run0 + 1, main)
+                run0 = s
+            prev = s
 
-        def producer():
-            try:
-                with torch.cuda.stream(copy_stream):
-                    for data in self.t_loader:
-                        if not slots:
-                            nbytes = max(1, data['images'].numel() * data['images'].element_size())
-                            # None: about 1.5 GB of batches in flight, at most one window (full-resolution logits: 4 batches;
-                            # images or stride-8 logits: the whole next window)
-                            n = depth if depth is not None else max(2, min(self.window_batches, int(1.5e9 // nbytes)))
-                            slots.append(threading.Semaphore(n))
-                        while not slots[0].acquire(timeout=0.05):
-                            if stop.is_set():
-                                return
-                        if stop.is_set():
-                            return
-                        imgs = data['images'].to(self.device, non_blocking=True)
-                        ev = torch.cuda.Event()
-                        ev.record(copy_stream)
-                        q.put((imgs, ev, list(data['image_paths'])))
-                q.put(None)
-            except BaseException as exc:          # surfaces in the consumer
-                q.put(exc)
+    def _already_done(self):
+        return self.t_dataset is not None and len(os.listdir(self.pseudo_label_save_dir)) >= len(self.t_dataset)
 
-        t = threading.Thread(target=producer, name='hiast-h2d', daemon=True)
-        t.start()
-        try:
-            while True:
-                item = q.get()
-                if item is None:
-                    break
-                if isinstance(item, BaseException):
-                    raise item
-                imgs, ev, paths = item
-                slots[0].release()
-                main = torch.cuda.current_stream(self.device)
-                main.wait_event(ev)
-                imgs.record_stream(main)
-                yield imgs, paths
-        finally:
-            stop.set()
-            t.join(timeout=5.0)
+    # --------------------------------------------------- one run of any policy
+    def _run_windows(self, scan, thr_const=None, alpha=0.0, beta=0.0, gamma=1.0, rank=0, world=1, pg=None, n_total=None):
+        """The loader through the window pipeline; fills every result attribute.  ``scan``: IAS thresholds (else the
+        constant ``thr_const`` per class)."""
+        C = self.cfg.dataset.num_classes
+        pipe = None
+        it = self._iterate_logits(lambda: pipe)
+        for logits, img_paths, slot in it:
+            if pipe is None:
+                engine = self._engine = self._make_engine(logits.shape, alpha, beta, gamma)
+                pipe = _WindowPipeline(self, engine, scan, rank, world, pg, n_total)
+                if scan:
+                    engine.thr_state.copy_(torch.from_numpy(np.asarray(self.class_threshold, dtype=np.float64)))
+                else:
+                    engine.thr_groups.copy_(torch.from_numpy(np.tile(np.asarray(thr_const, dtype=np.float64), (engine.max_groups, 1))))
+            pipe.add(logits, img_paths, slot)
+        if pipe is None:                                  # this rank owns no window (or the loader is empty)
+            engine = self._engine = self._make_engine((self._group_size(1), C, 4, 4), alpha, beta, gamma)
+            pipe = _WindowPipeline(self, engine, scan, rank, world, pg, n_total)
+            if scan:
+                engine.thr_state.copy_(torch.from_numpy(np.asarray(self.class_threshold, dtype=np.float64)))
+        pipe.finish()
+        self._wait_png()
+        self._collect(pipe, scan, rank, world, pg)
 
-    def _iterate_logits(self):
-        """Yields (logits [B,C,H,W] on the device, image_paths) exactly as :189-192 produces them."""
+    def _iterate_logits(self, get_pipe=lambda: None):
+        """Yields (logits [B,C,H,W] on the device or LowResLogits, image_paths, staging slot) as :189-192 produces them."""
         self.model.eval() if hasattr(self.model, 'eval') else None
         with torch.no_grad():
-            for imgs, image_paths in self._device_batches():
+            for data in self.t_loader:
+                imgs, slot = self._staged(data['images'], get_pipe())
+                image_paths = list(data['image_paths'])
                 out = self.model(imgs)
                 if 'logits' not in out and 'logits_lr' in out:
                     # the network's own (stride-8) output: the bilinear up-sampling of
                     # self_training_segmentor.py:27 is fused into phase A (SURVEY 8f rank 1)
                     lr = out['logits_lr']
                     lr = lr.float() if lr.dtype != torch.float32 else lr
-                    yield LowResLogits(lr.contiguous(), tuple(out.get('size', imgs.shape[2:]))), image_paths
+                    yield LowResLogits(lr.contiguous(), tuple(out.get('size', imgs.shape[2:]))), image_paths, slot
                     continue
                 logits = out['logits']
                 if logits.dtype != torch.float32:
                     logits = logits.float()
-                yield logits.contiguous(), image_paths
+                yield logits.contiguous(), image_paths, slot
 
-    def _already_done(self):
-        return self.t_dataset is not None and len(os.listdir(self.pseudo_label_save_dir)) >= len(self.t_dataset)
-
-
-class LowResLogits:
-    """Stride-8 logits [B,C,h,w] together with the size they are to be up-sampled to (bilinear, align_corners=True)."""
-
-    def __init__(self, logits_lr, size):
-        self.logits_lr, self.size = logits_lr, (int(size[0]), int(size[1]))
-
-    @property
-    def shape(self):
-        b, c = self.logits_lr.shape[:2]
-        return (b, c, self.size[0], self.size[1])
-
-
-def _phase_a(engine, logits, first_image):
-    """Phase A of one batch.  Full-resolution logits are consumed at once (they are 159 MB per image and the caller may
-    reuse the buffer).  Stride-8 logits (2.5 MB per image) are only queued: consecutive batches are concatenated and go through
-    ONE launch per window (`_flush_lowres`) -- a 2-image launch of the fused up-sampling kernel costs 106 us, its share of a
-    64-image launch 67 us."""
-    if isinstance(logits, LowResLogits) and hasattr(engine, 'phase_a_lowres'):
-        pend = engine.__dict__.setdefault('_pending_lr', [])
-        if pend:
-            last, last_first = pend[-1]
-            if (last_first + last.logits_lr.shape[0] != first_image or last.size != logits.size
-                    or last.logits_lr.shape[1:] != logits.logits_lr.shape[1:]):
-                _flush_lowres(engine)
-                pend = engine.__dict__.setdefault('_pending_lr', [])
-        pend.append((logits, first_image))
-    elif isinstance(logits, LowResLogits):
-        engine.phase_a_lowres(logits.logits_lr, first_image)
-    else:
-        engine.phase_a(logits, first_image)
-
-
-def _flush_lowres(engine):
-    """Launch phase A for the queued stride-8 batches (one launch for the contiguous run of images)."""
-    pend = engine.__dict__.pop('_pending_lr', None)
-    if not pend:
-        return
-    lr = pend[0][0].logits_lr if len(pend) == 1 else torch.cat([p[0].logits_lr for p in pend])
-    engine.phase_a_lowres(lr, pend[0][1])
-
-
-def _flush_window(gen, engine, paths, n_images, scan, before_emit=None):
-    """Phases B/C for the images in the window, then the outputs (``_emit_window``, deferred when possible).
-    ``before_emit()`` may queue more copies on the stream and returns the completion callback."""
-    if n_images == 0:
-        return
-    _flush_lowres(engine)
-    if scan:
-        engine.phase_b(0, n_images)
-    engine.phase_c(0, n_images)
-    engine.mean_prob(0, n_images)
-    after = before_emit() if before_emit is not None else None
-    _emit_window(gen, engine, paths, 0, n_images, defer=True, after=after)
+    def _collect(self, pipe, scan, rank, world, pg):
+        """Global results on every rank: the windows' thresholds, class counts and confidence sums are merged in the global
+        window order (ONE all_gather_object when R > 1), the mean-probability EMA (:95-105) is replayed over all groups, the
+        per-image statistics lists (:82-89) are rebuilt in image order."""
+        import torch.distributed as dist
+        e = pipe.e
+        C = self.cfg.dataset.num_classes
+        self.pow_rounding_certified = e.check_errors() if hasattr(e, 'check_errors') else True      # host sync
+        mine = {'windows': {r['w']: (r['paths'], r['counts'], r['confsum'], r['thr']) for r in pipe.results},
+                'thr_state': torch.as_tensor(e.thr_state).cpu().numpy().copy() if scan else None}
+        parts = [mine]
+        if world > 1:
+            parts = [None] * world
+            dist.all_gather_object(parts, mine, group=pg)
+        merged = {}
+        for p in parts:
+            merged.update(p['windows'])
+        order = sorted(merged)
+        if scan and order:                                # the final thresholds live where the last window was scanned
+            last_owner = max(range(len(parts)), key=lambda r: max(parts[r]['windows'], default=-1))
+            self.class_threshold = parts[last_owner]['thr_state']
+        B = e.B
+        self.threshold_trace = [merged[w][3] for w in order]
+        self.sample_stats = []
+        self.samples_class = {i: [] for i in range(C)}
+        self.statics_class = np.array([0] * C)
+        group_counts, confsums = [], []
+        for w in order:
+            paths, counts, confsum, _ = merged[w]
+            n = counts.shape[0]
+            g = (n + B - 1) // B
+            padded = np.zeros((g * B, C), dtype=np.int64)
+            padded[:n] = counts
+            group_counts.append(padded.reshape(g, B, C).sum(axis=1))
+            confsums.append(confsum[:g])
+            for i in range(n):
+                self._record_image(counts[i], paths[i])
+        if order:
+            dev = e.thr_state.device
+            e.mean_state.copy_(torch.from_numpy(np.asarray(self.class_mean_probs, dtype=np.float64)))
+            e.mean_prob_from_groups(torch.from_numpy(np.concatenate(confsums)).to(dev),
+                                    torch.from_numpy(np.concatenate(group_counts)).to(dev))
+            self.class_mean_probs = torch.as_tensor(e.mean_state).cpu().numpy().copy()
 
 
-def _can_defer(gen, engine):
-    """Deferred completion needs the device PNG writer with the native file writer and a CUDA engine."""
-    return (getattr(gen, 'defer_sync', True) and gen._device_png() and gen._png_pool is not None
-            and type(gen).save_pseudo_label_file is BasePseudoGenerator.save_pseudo_label_file
-            and torch.is_tensor(engine.plbl) and engine.plbl.is_cuda and engine.plbl.shape[2] <= 128 * 256)
+class _WindowPipeline:
+    """Windows of ``engine.max_images // 3`` images through phase A -> threshold chain -> outputs, three in flight (module
+    docstring).  ``add`` takes the batches of the rank's windows in order; ``finish`` drains.  With a host stand-in engine
+    (CPU tests of the orchestration) the same schedule runs eagerly."""
 
+    N_SLOTS = 3
 
-def _emit_window(gen, engine, paths, first, n_images, defer=False, after=None):
-    """Outputs of the masked window engine.plbl[first:first+n] (PNG files + per-image statistics).  ``defer=True`` (single-GPU
-    generators): everything is only QUEUED on the stream -- encoder, copies of the offset table / predicted blob bytes / counts,
-    an event -- and completed when the next window is emitted (``_finish_pending_emit``), so the host never waits for the GPU
-    at the end of a window and phase A of the next window is issued behind this one without a gap.  ``after`` runs on
-    completion (the IAS generator reads its threshold copies there)."""
-    if defer and _can_defer(gen, engine):
-        plbl, counts = engine.plbl[first:first + n_images], engine.counts[first:first + n_images]
-        gen._finish_pending_emit()                    # the previous window (its event is long past)
-        enc = gen._png_encoder
-        if enc is None or (enc.H, enc.W) != tuple(plbl.shape[1:]) or enc.max_images < n_images:
-            enc = gen._png_encoder = ops.PngEncoder(plbl.shape[1], plbl.shape[2], engine.max_images, device=engine.device)
-        slot = gen._png_slot = 1 - gen._png_slot
-        gen._wait_png_slot(slot)                      # the writers of two windows ago still read this pinned blob
-        cpins = gen.__dict__.setdefault('_pinned_counts2', {})
-        cpin = cpins.get(slot)
-        if cpin is None or cpin.shape[0] < n_images or cpin.shape[1:] != counts.shape[1:]:
-            cpin = cpins[slot] = torch.empty(engine.counts.shape, dtype=torch.int64).pin_memory()
-        cpin[:n_images].copy_(counts, non_blocking=True)
-        handle = enc.encode_async(plbl, slot)
-        gen._pending_emit = dict(enc=enc, handle=handle, slot=slot, paths=list(paths[:n_images]), n=n_images, counts=cpin,
-                                 after=after)
-        return
-    gen._finish_pending_emit()
-    _emit_window_sync(gen, engine, paths, first, n_images)
-    if after is not None:
-        after()
+    def __init__(self, gen, engine, scan, rank=0, world=1, pg=None, n_total=None):
+        from .sharded import window_images
+        self.gen, self.e, self.scan = gen, engine, bool(scan)
+        self.rank, self.world, self.pg, self.n_total = rank, world, pg, n_total
+        if world > 1 and n_total is None:
+            raise RuntimeError('the sharded generator needs dataset_len (the size of the whole target set)')
+        self.window = engine.max_images // self.N_SLOTS
+        self._window_images = window_images
+        self.n_windows_total = None if n_total is None else (n_total + self.window - 1) // self.window
+        self.cuda = torch.is_tensor(engine.plbl) and engine.plbl.is_cuda
+        self.j = 0                    # local window being filled
+        self.filled, self.paths, self.staged = 0, [], []
+        self.queued = []              # stride-8 batches of the current window awaiting their single phase-A launch
+        self.closed = []              # (n_images, paths) per closed local window
+        self.b_done = self.c_done = 0
+        self.results = []
+        self.pending = {}
+        self._host_jobs = {}
+        self.emitter = self.writer = None
+        if self.cuda:
+            dev = engine.device
+            self.main = torch.cuda.current_stream(dev)
+            self.side = _stream(dev, 'chain')
+            self.ev_a = [torch.cuda.Event() for _ in range(self.N_SLOTS)]
+            self.ev_b = [torch.cuda.Event() for _ in range(self.N_SLOTS)]
+            if gen._device_png() and engine.W > 128 * 256:
+                gen.png = 'host'                       # wider than the device writer's 32768-pixel rows: the reference's writer
+            self.mode = 'host' if not gen._device_png() else ('files' if gen._native_files() else 'blobs')
+            self.emitter = ops.WindowEmitter(engine, self.window, self.N_SLOTS, png=self.mode != 'host')
+            if self.mode == 'files':
+                if gen._writer is None:
+                    gen._writer = ops.FileWriter(gen._png_workers, dev)
+                self.writer = gen._writer
 
+    # ---------------------------------------------------------------- input side
+    def _global(self, j):
+        return j * self.world + self.rank
 
-def _emit_window_sync(gen, engine, paths, first, n_images):
-    """Outputs of the masked window engine.plbl[first:first+n]: PNG files + per-image statistics.
+    def _expected(self):
+        if self.n_total is None:
+            return self.window
+        return self._window_images(self._global(self.j), self.window, self.n_total)[1]
 
-    Device path (default): the label maps are encoded as PNG files on the device, one D2H copy moves the finished files to a
-    pinned blob (two blobs alternate) and ONE native call writes them while the next window is computed.  Host path
-    (``png='host'`` or a hooked ``save_pseudo_label``): uint8 label maps come back at 1 B/px through a pinned buffer (one
-    sync per window) and go to the hook / ``cv2.imwrite``."""
-    plbl, counts = engine.plbl[first:first + n_images], engine.counts[first:first + n_images]
-    if not torch.is_tensor(plbl):                     # a host stand-in engine (CPU tests of the orchestration)
-        plbl_h, counts_h = np.asarray(plbl), torch.as_tensor(counts).numpy()
-        for i in range(n_images):
-            gen._record_image(counts_h[i], paths[i])
-            gen._save_async(plbl_h[i].copy(), paths[i])
-        gen._wait_png()
-        return
-    if gen._device_png() and plbl.shape[2] > 128 * 256:
-        gen.png = 'host'                              # wider than the device writer's 32768-pixel rows: the reference's writer
-    native = (type(gen).save_pseudo_label_file is BasePseudoGenerator.save_pseudo_label_file and gen._png_pool is not None)
-    if gen._device_png():
-        cpin = getattr(gen, '_pinned_counts', None)
-        if cpin is None or cpin.shape[0] < n_images or cpin.shape[1:] != counts.shape[1:]:
-            cpin = gen._pinned_counts = torch.empty(engine.counts.shape, dtype=torch.int64).pin_memory()
-        cpin[:n_images].copy_(counts, non_blocking=True)
-        enc = gen._png_encoder
-        if enc is None or (enc.H, enc.W) != tuple(plbl.shape[1:]) or enc.max_images < n_images:
-            enc = gen._png_encoder = ops.PngEncoder(plbl.shape[1], plbl.shape[2], engine.max_images, device=engine.device)
-        slot = gen._png_slot = 1 - gen._png_slot
-        gen._wait_png_slot(slot)                      # the writers of two windows ago still read this pinned blob
-        files = enc.encode_to_host(plbl, slot)        # finished PNG files; syncs the stream once
-        counts_h = cpin.numpy()[:n_images].copy()
-        for i in range(n_images):
-            gen._record_image(counts_h[i], paths[i])
-        if native:
-            # one native call writes the whole window (POSIX writer threads, no interpreter lock)
-            blob_host, offsets = enc.host_blob(slot)
-            targets = [gen._pseudo_label_path(p) for p in paths[:n_images]]
-            gen._png_slot_jobs[slot].append(gen._png_pool.submit(ops.write_files, targets, blob_host, offsets,
-                                                                 gen._png_workers))
+    def add(self, logits, paths, staged_slot=None):
+        e = self.e
+        b = logits.shape[0]
+        want = self._expected()
+        if self.filled + b > want:
+            raise ValueError('window %d must hold %d images, the loader delivered more' % (self._global(self.j), want))
+        first = (self.j % self.N_SLOTS) * self.window + self.filled
+        if isinstance(logits, LowResLogits) and hasattr(e, 'phase_a_lowres'):
+            q = self.queued
+            if q and (q[-1][0].size != logits.size or q[-1][0].logits_lr.shape[1:] != logits.logits_lr.shape[1:]):
+                self.flush_queued()
+            self.queued.append((logits, first))
+            if staged_slot is not None:
+                self.staged.append(staged_slot)
         else:
-            for i in range(n_images):
-                gen._save_file_async(files[i], paths[i], slot)
-        return                                        # the files are written while the next window is computed
-    pins = getattr(gen, '_pinned', None)
-    if pins is None or pins[0].shape[0] < n_images or pins[0].shape[1:] != plbl.shape[1:]:
-        pins = gen._pinned = (torch.empty(engine.plbl.shape, dtype=torch.uint8).pin_memory(),
-                              torch.empty(engine.counts.shape, dtype=torch.int64).pin_memory())
-    pins[0][:n_images].copy_(plbl, non_blocking=True)   # host PNG path: 1 B/px back
-    pins[1][:n_images].copy_(counts, non_blocking=True)
-    torch.cuda.current_stream(engine.device).synchronize()
-    gen._wait_png()                                   # the previous window's encoders still read the pinned buffer
-    plbl_h, counts_h = pins[0].numpy(), pins[1].numpy()
-    for i in range(n_images):
-        gen._record_image(counts_h[i], paths[i])
-        gen._save_async(plbl_h[i], paths[i])
-    gen._wait_png()
+            if isinstance(logits, LowResLogits):                    # an engine without the fused up-sampling (host stand-in)
+                logits = torch.nn.functional.interpolate(logits.logits_lr, size=logits.size, mode='bilinear', align_corners=True)
+            e.phase_a(logits, first)
+            if staged_slot is not None:
+                self.gen._release_staged([staged_slot])             # consumed by the launch just queued
+        self.filled += b
+        self.paths += paths
+        if self.filled == want or (self.n_total is None and b != e.B):
+            self._close()
+
+    def flush_queued(self):
+        """ONE launch of the fused up-sampling kernel for the queued stride-8 batches (a 2-image launch costs 106 us, its share
+        of a 64-image launch 67 us).  Batches staged into consecutive ring slots are passed as one view, without a copy."""
+        q = self.queued
+        if q:
+            self.queued = []
+            first = q[0][1]
+            ts = [x[0].logits_lr for x in q]
+            lr = ts[0]
+            if len(ts) > 1:
+                lr = None
+                st = self.gen._stager
+                step = ts[0].numel() * 4
+                if st is not None and all(t.data_ptr() == ts[0].data_ptr() + k * step and t.shape == ts[0].shape
+                                          for k, t in enumerate(ts)):
+                    lr = st.view_of(ts[0].data_ptr(), step * len(ts), torch.float32, (len(ts) * ts[0].shape[0],) + tuple(ts[0].shape[1:]))
+                if lr is None:
+                    lr = torch.cat(ts)
+            self.e.phase_a_lowres(lr, first)
+        if self.staged:
+            self.gen._release_staged(self.staged)
+            self.staged = []
+
+    def _close(self):
+        self.flush_queued()
+        if self.cuda:
+            self.ev_a[self.j % self.N_SLOTS].record(self.main)
+        self.closed.append((self.filled, self.paths))
+        self.j += 1
+        self.filled, self.paths = 0, []
+        self._advance(final=False)
+
+    def finish(self):
+        if self.filled:
+            self._close()
+        if self.n_total is not None:
+            from .sharded import local_windows
+            mine = len(local_windows(self.n_windows_total, self.rank, self.world))
+            if len(self.closed) != mine:
+                raise ValueError('this rank owns %d windows, the loader filled %d' % (mine, len(self.closed)))
+        self._advance(final=True)
+        for es in sorted(self.pending, key=lambda k: self.pending[k]['j']):
+            self._complete(es)
+        for es in list(self._host_jobs):
+            self._wait_host_jobs(es)
+
+    # ---------------------------------------------------------------- the schedule
+    def _advance(self, final):
+        n_closed = len(self.closed)
+        b_target = n_closed if (final or not self.scan) else n_closed - 1
+        while self.b_done < b_target:
+            if self.scan:
+                self._chain(self.b_done)
+            self.b_done += 1
+        c_target = self.b_done if (final or not self.scan) else self.b_done - 1
+        while self.c_done < c_target:
+            self._outputs(self.c_done)
+            self.c_done += 1
+
+    def _chain(self, j):
+        """Token receive -> threshold scan of window j -> token send, on the chain stream behind the LATEST closed phase A
+        (so that it does not compete with a running phase A for SMs but runs beside the outputs of the window before)."""
+        import torch.distributed as dist
+        e = self.e
+        n = self.closed[j][0]
+        slot = (j % self.N_SLOTS) * self.window
+        w = self._global(j)
+        ring = self.world > 1
+
+        def body():
+            if ring and w > 0:
+                dist.recv(e.thr_state, src=self._peer(-1), group=self.pg)
+            e.phase_b(slot, n)
+            if ring and w < self.n_windows_total - 1:
+                dist.send(e.thr_state, dst=self._peer(+1), group=self.pg)
+
+        if not self.cuda:
+            body()
+            return
+        self.side.wait_event(self.ev_a[(len(self.closed) - 1) % self.N_SLOTS])
+        with torch.cuda.stream(self.side):
+            body()
+            self.ev_b[j % self.N_SLOTS].record(self.side)
+
+    def _peer(self, step):
+        import torch.distributed as dist
+        r = (self.rank + step) % self.world
+        return dist.get_global_rank(self.pg, r) if self.pg is not None else r
+
+    def _outputs(self, j):
+        """Phase C, the PNG encoder and the device-to-host copies of window j (one foreign call), then the hand-over to the
+        writer pool; nothing here waits for the GPU except the reuse of an emit slot three windows later."""
+        e, gen = self.e, self.gen
+        n, paths = self.closed[j]
+        first = (j % self.N_SLOTS) * self.window
+        w = self._global(j)
+        if not self.cuda:                                   # host stand-in engine: eager
+            e.phase_c(first, n)
+            g0, g = first // e.B, (n + e.B - 1) // e.B
+            plbl = np.asarray(e.plbl[first:first + n])
+            for i in range(n):
+                gen._save_async(plbl[i].copy(), paths[i])
+            self.results.append(dict(w=w, paths=paths, counts=torch.as_tensor(e.counts[first:first + n]).numpy().copy(),
+                                     confsum=torch.as_tensor(e.confsum[g0:g0 + g]).numpy().copy(),
+                                     thr=torch.as_tensor(e.thr_groups[g0:g0 + g]).numpy().copy()))
+            return
+        es = j % self.N_SLOTS
+        if es in self.pending:
+            self._complete(es)
+        self._wait_host_jobs(es)
+        if self.scan:
+            self.main.wait_event(self.ev_b[es])
+        copied = self.emitter.emit(es, first, n)
+        s = self.emitter.slots[es]
+        rec = dict(j=j, w=w, n=n, paths=paths, copied=copied)
+        if self.mode == 'files':
+            targets = [gen._pseudo_label_path(p) for p in paths]
+            rec['ticket'] = self.writer.submit(targets, s['blob_host'], s['offsets_host'], copied, s['blob_dev'],
+                                               stream_ptr(e.device))
+        else:
+            ev = rec['event'] = torch.cuda.Event(blocking=True)
+            ev.record(self.main)
+        self.pending[es] = rec
+        if not gen.defer_sync:
+            self._complete(es)
+
+    def _complete(self, es):
+        rec = self.pending.pop(es)
+        e, gen, s = self.e, self.gen, self.emitter.slots[es]
+        n, paths = rec['n'], rec['paths']
+        g = (n + e.B - 1) // e.B
+        if 'ticket' in rec:
+            self.writer.wait(rec['ticket'])                 # foreign call: sleeps until the window's files are on disk
+            self.emitter.learn(int(s['offsets_host'][n]))
+        else:
+            rec['event'].synchronize()
+            if self.mode == 'blobs':                        # save_pseudo_label_file hook: finished files one by one
+                o = s['offsets_host'][:n + 1].tolist()
+                if o[-1] > rec['copied']:
+                    s['blob_host'][rec['copied']:o[-1]].copy_(s['blob_dev'][rec['copied']:o[-1]])
+                self.emitter.learn(o[-1])
+                blob = s['blob_host'].numpy()
+                for i in range(n):
+                    gen.save_pseudo_label_file(blob[o[i]:o[i + 1]], paths[i])
+            else:                                           # save_pseudo_label hook / cv2.imwrite on uint8 label maps
+                plbl = s['plbl_host'].numpy()
+                jobs = [gen._save_async(plbl[i], paths[i]) for i in range(n)]
+                self._host_jobs[es] = [job for job in jobs if job is not None]
+        self.results.append(dict(w=rec['w'], paths=paths, counts=s['counts_host'][:n].numpy().copy(),
+                                 confsum=s['confsum_host'][:g].numpy().copy(), thr=s['thr_host'][:g].numpy().copy()))
+
+    def _wait_host_jobs(self, es):
+        for job in self._host_jobs.pop(es, []):             # cv2 encoders still reading the slot's pinned label maps
+            job.result()
 
 
 @PSEUDO_POLICY.register('CT')
@@ -478,22 +666,7 @@ class ConstantThresholdPseudoGenerator(BasePseudoGenerator):
         self.class_threshold = self.get_constant_threshold()
         C = self.cfg.dataset.num_classes
         thr = np.zeros(C) if self.class_threshold is None else np.asarray(self.class_threshold, dtype=np.float64)
-        engine, paths, n = None, [], 0
-        for logits, img_paths in self._iterate_logits():
-            if engine is None:
-                engine = self._engine = self._make_engine(logits)
-                engine.thr_groups.copy_(torch.from_numpy(np.tile(thr, (engine.max_groups, 1))))
-            b = logits.shape[0]
-            _phase_a(engine, logits, n)
-            paths += img_paths
-            n += b
-            if n + engine.B > engine.max_images or b != engine.B:
-                _flush_window(self, engine, paths, n, scan=False)
-                paths, n = [], 0
-        if engine is not None:
-            _flush_window(self, engine, paths, n, scan=False)
-            self.class_mean_probs = engine.mean_state.cpu().numpy()
-        self._wait_png()
+        self._run_windows(scan=False, thr_const=thr)
         self.save_data()
 
 
@@ -516,12 +689,14 @@ class CBSTPseudoGenerator(ConstantThresholdPseudoGenerator):
         cbst = self.cfg.pseudo_policy.cbst
         key_lo = ops.ias_key_lo(C)
         hist = None
-        for logits, _paths in self._iterate_logits():
+        for logits, _paths, slot in self._iterate_logits():
             b = logits.shape[0]
             if isinstance(logits, LowResLogits):                        # phase A (its own histogram is not used here)
                 conf, label, _ = ops.ias_upsample_softmax_hist(logits.logits_lr, logits.size, b)
             else:
                 conf, label, _ = ops.ias_softmax_hist(logits, b)
+            if slot is not None:
+                self._release_staged([slot])
             if hist is None:
                 hist = torch.zeros((C, ops.ias_row_stride(key_lo)), dtype=torch.int32, device=conf.device)
             ops.cbst_sample_hist(conf, label, C, b, int(cbst.sample_interval), key_lo, hist)
@@ -572,65 +747,27 @@ class IASPseudoGenerator(BasePseudoGenerator):
             out[c] = temp.item()
         return out
 
+    def _ranks(self):
+        return 0, 1, None
+
     def run(self):
         """:181-213"""
         if self._already_done():
             print('%% pseudo labels have existed')
             return
+        rank, world, pg = self._ranks()
         C = self.cfg.dataset.num_classes
         ias = self.cfg.pseudo_policy.ias
         self.class_threshold = 0.9 * np.ones(C)                                            # :185
-        self.threshold_trace = []
-        engine, paths, n = None, [], 0
-        for logits, img_paths in self._iterate_logits():
-            if engine is None:
-                engine = self._engine = self._make_engine(logits, ias.alpha, ias.beta, ias.gamma)
-                engine.thr_state.copy_(torch.from_numpy(self.class_threshold))
-                engine.mean_state.copy_(torch.from_numpy(self.class_mean_probs))
-            b = logits.shape[0]
-            _phase_a(engine, logits, n)                   # asynchronous; overlaps the next forward pass
-            paths += img_paths
-            n += b
-            if n + engine.B > engine.max_images or b != engine.B:
-                self._finish_window(engine, paths, n)
-                paths, n = [], 0
-        if engine is not None:
-            self._finish_window(engine, paths, n)
-            self.pow_rounding_certified = engine.check_errors()
-        self._wait_png()
-        self.save_data()
-
-    def _finish_window(self, engine, paths, n):
-        if n == 0:
-            return
-        g = engine._groups(n)
-
-        def before_emit():
-            # per-window host copies of the thresholds: queued into pinned buffers (one set per PNG slot), read on completion
-            if not _can_defer(self, engine):
-                def read_now():
-                    self.threshold_trace.append(engine.thr_groups[:g].cpu().numpy().copy())
-                    self.class_threshold = engine.thr_state.cpu().numpy()
-                    self.class_mean_probs = engine.mean_state.cpu().numpy()
-                return read_now
-            pins = self.__dict__.setdefault('_thr_pins', {})
-            slot = 1 - self._png_slot                  # the slot _emit_window is about to take
-            buf = pins.get(slot)
-            if buf is None or buf[0].shape != engine.thr_groups.shape:
-                buf = pins[slot] = (torch.empty(engine.thr_groups.shape, dtype=torch.float64).pin_memory(),
-                                    torch.empty(engine.thr_state.shape, dtype=torch.float64).pin_memory(),
-                                    torch.empty(engine.mean_state.shape, dtype=torch.float64).pin_memory())
-            buf[0][:g].copy_(engine.thr_groups[:g], non_blocking=True)
-            buf[1].copy_(engine.thr_state, non_blocking=True)
-            buf[2].copy_(engine.mean_state, non_blocking=True)
-
-            def read_later():
-                self.threshold_trace.append(buf[0][:g].numpy().copy())
-                self.class_threshold = buf[1].numpy().copy()
-                self.class_mean_probs = buf[2].numpy().copy()
-            return read_later
-
-        _flush_window(self, engine, paths, n, scan=True, before_emit=before_emit)
+        n_total = None                                   # one rank: windows simply close when they are full
+        if world > 1:
+            if self.t_dataset is None:
+                raise RuntimeError('the sharded generator needs dataset_len (the size of the whole target set)')
+            n_total = len(self.t_dataset)
+        self._run_windows(scan=True, alpha=ias.alpha, beta=ias.beta, gamma=ias.gamma, rank=rank, world=world, pg=pg,
+                          n_total=n_total)
+        if rank == 0:
+            self.save_data()
 
 
 def striped_batch_order(n_images_total, window_images, batch_size, rank, world_size):
@@ -653,12 +790,13 @@ class ShardedIASPseudoGenerator(IASPseudoGenerator):
 
     The pinned global order of the target set is cut into windows of ``window_batches`` batches; window w belongs to
     rank w mod R and **the injected loader yields only this rank's batches, in order** (``striped_batch_order`` gives the
-    batch sampler).  Per owned window: phase A of the NEXT window is issued batch by batch as the model produces logits,
-    then the 19-double threshold state is received from rank r-1 (NCCL / gloo recv), the window is scanned, the state is
-    sent on to rank r+1, and the window is masked, PNG-encoded on the device and written.  At the end the per-group sums
-    are all-gathered and every rank replays the mean-probability EMA, the statistics lists are gathered in global order,
-    and rank 0 writes ``save_data``'s files.  Results are bit-identical to the single-process generator
-    (tests/test_sharded_gloo.py with a host stand-in engine, tests/test_sharded_gpu.py with NCCL)."""
+    batch sampler).  Every rank runs the three-windows-in-flight pipeline of this module; the 19-double threshold state is
+    received from rank r-1 in front of a window's scan and sent on to rank r+1 behind it (NCCL / gloo), on the chain
+    stream.  At the end ONE all_gather_object merges the windows' thresholds, counts and confidence sums, every rank replays
+    the mean-probability EMA and rebuilds the statistics lists in the global image order, and rank 0 writes ``save_data``'s
+    files.  A rank that owns no window (more ranks than windows) takes part in the collectives with an empty share.
+    Results are bit-identical to the single-process generator (tests/test_sharded_gloo.py with a host stand-in engine,
+    tests/test_sharded_gpu.py with NCCL)."""
 
     def __init__(self, cfg, *args, engine_factory=None, process_group=None, **kw):
         import torch.distributed as dist
@@ -668,105 +806,8 @@ class ShardedIASPseudoGenerator(IASPseudoGenerator):
         if dist.is_available() and dist.is_initialized():
             dist.barrier(group=process_group)          # every rank has seen the empty save dir before anyone writes
 
-    def _make_engine(self, logits, alpha=0.0, beta=0.0, gamma=1.0):
-        b, c, h, w = logits.shape
-        group = max(int(_cfg_get(self.cfg, 'pseudo_policy.batch_size', b) or b), b)
-        n = 2 * group * self.window_batches                       # two windows: the next one's phase A runs ahead
-        if self._engine_factory is not None:
-            return self._engine_factory(c, h, w, group, alpha, beta, gamma, self._cp_gamma(), n)
-        return IASEngine(c, h, w, group, alpha, beta, gamma, self._cp_gamma(), n, device=self.device)
-
-    def run(self):
+    def _ranks(self):
         import torch.distributed as dist
-        from .sharded import ShardedIAS, window_images
-        if self._already_done():
-            print('%% pseudo labels have existed')
-            return
-        if self.t_dataset is None:
-            raise RuntimeError('the sharded generator needs dataset_len (the size of the whole target set)')
-        C = self.cfg.dataset.num_classes
-        ias = self.cfg.pseudo_policy.ias
-        self.class_threshold = 0.9 * np.ones(C)                                            # :185
-        n_total = len(self.t_dataset)
-        it = self._iterate_logits()
-        engine = drv = None
-        pending = None
-        per_window = {}                                   # global window -> (sample_stats rows, thr_groups)
-        first = next(it, None)
-        if first is not None:
-            engine = self._engine = self._make_engine(first[0], ias.alpha, ias.beta, ias.gamma)
-            engine.thr_state.copy_(torch.from_numpy(self.class_threshold))
-            window = engine.max_images // 2
-            drv = ShardedIAS(engine, window, n_total, process_group=self._pg)
-            drv._stash = []
-            for j, w in enumerate(drv.my_windows):
-                _, n = window_images(w, window, n_total)
-                slot, filled, paths = drv._slot(j), 0, []
-                while filled < n:                          # phase A of window j, batch by batch
-                    logits, p = first if first is not None else next(it)
-                    first = None
-                    _phase_a(engine, logits, slot + filled)
-                    filled += logits.shape[0]
-                    paths += p
-                if filled != n:
-                    raise ValueError('window %d must hold %d images, the loader delivered %d' % (w, n, filled))
-                if pending is not None:                    # ... while the previous window waits for its thresholds
-                    self._finish_sharded_window(drv, per_window, *pending)
-                pending = (w, j, paths, n)
-            if pending is not None:
-                self._finish_sharded_window(drv, per_window, *pending)
-        self._wait_png()
-        self._gather_state(drv, per_window, n_total)
-        rank = dist.get_rank(self._pg) if dist.is_available() and dist.is_initialized() else 0
-        if rank == 0:
-            self.save_data()
-
-    def _finish_sharded_window(self, drv, per_window, w, j, paths, n):
-        import torch.distributed as dist
-        e = drv.engine
-        slot = drv._slot(j)
-        _flush_lowres(e)                                 # phase A of this and of the next window, before the token wait
-        if w > 0 and drv.world > 1:
-            dist.recv(e.thr_state, src=drv._global((drv.rank - 1) % drv.world), group=drv.pg)
-        e.phase_b(slot, n)
-        if w < drv.n_windows_total - 1 and drv.world > 1:
-            dist.send(e.thr_state, dst=drv._global((drv.rank + 1) % drv.world), group=drv.pg)
-        e.phase_c(slot, n)
-        g0, g = slot // e.B, (n + e.B - 1) // e.B
-        drv._stash.append(torch.stack([torch.as_tensor(e.confsum[g0:g0 + g]), e.group_counts(slot, n)], dim=1).clone())
-        rows_before = len(self.sample_stats)
-        _emit_window(self, e, paths, slot, n)
-        thr_groups = torch.as_tensor(e.thr_groups[g0:g0 + g]).cpu().numpy().copy()
-        per_window[w] = (self.sample_stats[rows_before:], thr_groups)
-
-    def _gather_state(self, drv, per_window, n_total):
-        """Global results on every rank: thresholds / mean probabilities / class totals from the driver, the per-image
-        statistics lists re-assembled in the global image order."""
-        import torch.distributed as dist
-        C = self.cfg.dataset.num_classes
-        if drv is None:
-            return
-        thr, mean, statics = drv.finish_state()
-        self.class_threshold = thr.cpu().numpy().copy()
-        self.class_mean_probs = mean.cpu().numpy().copy()
-        self.pow_rounding_certified = drv.engine.check_errors() if hasattr(drv.engine, 'check_errors') else True
-        parts = [per_window]
-        if drv.world > 1:
-            parts = [None] * drv.world
-            dist.all_gather_object(parts, per_window, group=drv.pg)
-        merged = {}
-        for p in parts:
-            merged.update(p)
-        self.sample_stats, self.threshold_trace = [], []
-        self.samples_class = {i: [] for i in range(C)}
-        self.statics_class = np.array([0] * C)
-        for w in sorted(merged):
-            rows, thr_groups = merged[w]
-            self.threshold_trace.append(thr_groups)
-            for row in rows:
-                self.sample_stats.append(row)
-                for k, v in row.items():
-                    if k != 'file':
-                        self.samples_class[k].append([row['file'], v])
-                        self.statics_class[k] += v
-        assert np.array_equal(self.statics_class, statics.cpu().numpy()), 'gathered statistics disagree with the device sums'
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(self._pg), dist.get_world_size(self._pg), self._pg
+        return 0, 1, None

@@ -7,19 +7,18 @@ cross-group dependencies are the sequential ``class_threshold`` f64[C] (:207-209
 ``class_mean_probs`` f64[C] (:100-105).  With R ranks (one process per GPU) the pinned global order of
 image groups is cut into windows of ``window_images`` images and window w belongs to rank w mod R:
 
-    rank r, local window j  (global window w = j*R + r):
-        phase A of window j+1            <- issued first, so the GPU has work while the token travels
-        recv  thr f64[C] from rank r-1   (ncclRecv over NVLink; skipped for w = 0, which starts from 0.9)
-        phase B of window j              (device scan over the window's groups)
-        send  thr f64[C] to rank r+1     (ncclSend; skipped for the last window)
-        phase C of window j
+    rank r, local window j  (global window w = j*R + r), three window slots:
+        main stream    phase A of window j, phase C of window j-2, phase A of window j+1, ...
+        chain stream   behind A(j):  recv thr f64[C] from rank r-1   (ncclRecv over NVLink; skipped for w = 0, which starts from 0.9)
+                                     phase B of window j-1           (device scan over the window's groups)
+                                     send thr f64[C] to rank r+1     (ncclSend; skipped for the last window)
 
 The 152-byte token goes round the ring once per round of R windows; as long as R x (scan + hop) is
 shorter than one window of phase A + C the chain is hidden behind the bandwidth-bound work, which is
 what makes image/s scale with R.  No other data-path collective exists.  At the end the per-group
 (confidence sum, count)[C] of all windows are all-gathered (a few hundred KB) and every rank replays
-the tiny ``class_mean_probs`` EMA in global order; the final thresholds are broadcast from the rank
-that scanned the last window; ``statics_class`` falls out of the gathered counts.
+the tiny ``class_mean_probs`` EMA in global order; the final thresholds ride in the same all-gather (taken
+from the rank that scanned the last window); ``statics_class`` falls out of the gathered counts.
 
 Results are bit-identical to a single-rank run over the same global order (tests/test_sharded_gpu.py;
 on CPU with gloo and a host stand-in engine in tests/test_sharded_gloo.py).  With R = 1 the same code
@@ -30,6 +29,20 @@ from __future__ import annotations
 
 import torch
 import torch.distributed as dist
+
+
+_STREAMS = {}
+
+
+def device_stream(device, kind):
+    """One copy stream ('copy') and one high-priority chain stream ('chain') per device for the life of the process (NCCL and
+    the caching allocator keep per-stream state; a fresh stream per run would pay for it again)."""
+    device = torch.device(device)
+    key = (kind, device.index if device.index is not None else torch.cuda.current_device())
+    st = _STREAMS.get(key)
+    if st is None:
+        st = _STREAMS[key] = torch.cuda.Stream(device, priority=-1 if kind == 'chain' else 0)
+    return st
 
 
 def window_owner(w, world_size):
@@ -48,89 +61,138 @@ def window_images(w, window_size, n_images_total):
 
 
 class ShardedIAS:
-    """Drives one rank's engine (an ``IASEngine`` with room for two windows, or any object with the same phase
-    methods and state tensors -- the CPU tests use a host stand-in)."""
+    """Drives one rank's engine over device-resident windows (an ``IASEngine`` with room for two or, better, three
+    windows; or any object with the same phase methods and state tensors -- the CPU tests use a host stand-in).
+
+    Schedule with three window slots (``engine.max_images >= 3 * window_size``), per owned window j:
+
+        main stream    A(j)                        C(j-2)   A(j+1)                     C(j-1) ...
+        chain stream          [recv] B(j-1) [send]                 [recv] B(j) [send]
+
+    The chain of window j-1 is queued behind A(j) on a high-priority side stream, so it never competes with a running
+    phase A for SMs and runs in the shadow of phase C of window j-2; the main stream waits for it only in front of
+    C(j-1), one whole phase A later.  With two slots C(j-1) follows B(j-1) directly (the round-1 schedule)."""
 
     def __init__(self, engine, window_size, n_images_total, rank=None, world_size=None, process_group=None):
         if window_size % engine.B:
             raise ValueError('window_size must be a multiple of the group (batch) size')
         if engine.max_images < 2 * window_size:
-            raise ValueError('the engine needs room for two windows (double buffering)')
+            raise ValueError('the engine needs room for at least two windows')
         self.engine = engine
         self.pg = process_group
         use_dist = dist.is_available() and dist.is_initialized()
         self.rank = (dist.get_rank(process_group) if use_dist else 0) if rank is None else rank
         self.world = (dist.get_world_size(process_group) if use_dist else 1) if world_size is None else world_size
         self.window_size = int(window_size)
+        self.n_slots = 3 if engine.max_images >= 3 * window_size else 2
         self.n_total = int(n_images_total)
         self.n_windows_total = (self.n_total + self.window_size - 1) // self.window_size
         self.my_windows = local_windows(self.n_windows_total, self.rank, self.world)
-        self._stash = []
+        self.cuda = torch.is_tensor(engine.plbl) and engine.plbl.is_cuda
+        if self.cuda:
+            self.side = device_stream(engine.device, 'chain')
+            self.ev_a = [torch.cuda.Event() for _ in range(self.n_slots)]
+            self.ev_b = [torch.cuda.Event() for _ in range(self.n_slots)]
+        self._stash_conf = self._stash_counts = None
 
     def _global(self, group_rank):
         return dist.get_global_rank(self.pg, group_rank) if self.pg is not None else group_rank
 
     def _slot(self, j):
-        return (j % 2) * self.window_size
+        return (j % self.n_slots) * self.window_size
+
+    def _n(self, j):
+        return window_images(self.my_windows[j], self.window_size, self.n_total)[1]
 
     def run(self, window_logits, on_window=None):
         """``window_logits(w) -> logits f32 [n_w,C,H,W]`` on the device for GLOBAL window index w (called once per
-        owned window, one window ahead of its use).  ``on_window(w, plbl, counts, thr_groups)`` receives
-        device views of window w's results right after phase C is enqueued; they stay valid until the window
-        after next is started.  Returns (class_threshold, class_mean_probs, statics_class) device tensors."""
+        owned window).  ``on_window(w, plbl, counts, thr_groups)`` receives device views of window w's results right
+        after phase C is enqueued; they stay valid until the next-but-one window is started.  Returns (class_threshold,
+        class_mean_probs, statics_class) device tensors."""
         e = self.engine
         wins = self.my_windows
-        self._stash = []
-        # One rank: nothing to wait for, so a window goes through the fused persistent kernel (A + B + C in one launch,
-        # the conf / label spill never leaves L2).  With R > 1 the thresholds of a window arrive from another rank long
-        # after its phase A has run, so the three phases stay separate kernels (DESIGN.md section 5).
-        fused = self.world == 1 and bool(getattr(e, 'fused', False)) and hasattr(e, 'process_fused')
-        if wins and not fused:
-            self._phase_a(wins[0], 0, window_logits)
+        gw = self.window_size // e.B
+        dev = e.thr_state.device
+        k = max(len(wins), 1)
+        self._stash_conf = torch.zeros((k, gw, e.C), dtype=torch.int64, device=dev)
+        self._stash_counts = torch.zeros((k, self.window_size, e.C), dtype=torch.int64, device=dev)
+        lag = self.n_slots - 2                    # windows between a window's chain and its outputs
+        main = torch.cuda.current_stream(e.device) if self.cuda else None
+        b_done = c_done = 0
+
+        def advance(n_closed, final):
+            nonlocal b_done, c_done
+            b_target = n_closed if final else n_closed - 1
+            while b_done < b_target:
+                self._chain(b_done, n_closed - 1)
+                b_done += 1
+            c_target = b_done if final else b_done - lag
+            while c_done < c_target:
+                self._outputs(c_done, main, on_window)
+                c_done += 1
+
         for j, w in enumerate(wins):
-            _, n = window_images(w, self.window_size, self.n_total)
-            slot = self._slot(j)
-            if fused:
-                logits = window_logits(w)
-                if logits.shape[0] != n:
-                    raise ValueError('window %d must hold %d images, got %d' % (w, n, logits.shape[0]))
-                if not e.process_fused(logits, slot):
-                    e.phase_a(logits, slot)
-                    e.phase_b(slot, n)
-                    e.phase_c(slot, n)
-            else:
-                if j + 1 < len(wins):
-                    self._phase_a(wins[j + 1], j + 1, window_logits)
-                if w > 0 and self.world > 1:
-                    dist.recv(e.thr_state, src=self._global((self.rank - 1) % self.world), group=self.pg)
-                e.phase_b(slot, n)
-                if w < self.n_windows_total - 1 and self.world > 1:
-                    dist.send(e.thr_state, dst=self._global((self.rank + 1) % self.world), group=self.pg)
-                e.phase_c(slot, n)
-            g0, g = slot // e.B, (n + e.B - 1) // e.B
-            self._stash.append(torch.stack([e.confsum[g0:g0 + g], e.group_counts(slot, n)], dim=1).clone())
-            if on_window is not None:
-                on_window(w, e.plbl[slot:slot + n], e.counts[slot:slot + n], e.thr_groups[g0:g0 + g])
+            logits = window_logits(w)
+            n = self._n(j)
+            if logits.shape[0] != n:
+                raise ValueError('window %d must hold %d images, got %d' % (w, n, logits.shape[0]))
+            e.phase_a(logits, self._slot(j))
+            if self.cuda:
+                self.ev_a[j % self.n_slots].record(main)
+            advance(j + 1, final=False)
+        advance(len(wins), final=True)
         return self.finish_state()
 
-    def _phase_a(self, w, j, window_logits):
-        logits = window_logits(w)
-        _, n = window_images(w, self.window_size, self.n_total)
-        if logits.shape[0] != n:
-            raise ValueError('window %d must hold %d images, got %d' % (w, n, logits.shape[0]))
-        self.engine.phase_a(logits, self._slot(j))
+    def _chain(self, j, latest_closed):
+        e = self.engine
+        w = self.my_windows[j]
+        ring = self.world > 1
+
+        def body():
+            if ring and w > 0:
+                dist.recv(e.thr_state, src=self._global((self.rank - 1) % self.world), group=self.pg)
+            e.phase_b(self._slot(j), self._n(j))
+            if ring and w < self.n_windows_total - 1:
+                dist.send(e.thr_state, dst=self._global((self.rank + 1) % self.world), group=self.pg)
+
+        if not self.cuda:
+            body()
+            return
+        self.side.wait_event(self.ev_a[latest_closed % self.n_slots])
+        with torch.cuda.stream(self.side):
+            body()
+            self.ev_b[j % self.n_slots].record(self.side)
+
+    def _outputs(self, j, main, on_window):
+        e = self.engine
+        slot, n = self._slot(j), self._n(j)
+        if self.cuda:
+            main.wait_event(self.ev_b[j % self.n_slots])
+        e.phase_c(slot, n)
+        g0, g = slot // e.B, (n + e.B - 1) // e.B
+        self._stash_conf[j, :g].copy_(torch.as_tensor(e.confsum[g0:g0 + g]))
+        self._stash_counts[j, :n].copy_(torch.as_tensor(e.counts[slot:slot + n]))
+        if on_window is not None:
+            on_window(self.my_windows[j], e.plbl[slot:slot + n], e.counts[slot:slot + n], e.thr_groups[g0:g0 + g])
 
     def finish_state(self):
-        """All-gather the per-group sums, replay the mean-prob EMA over all groups in global order, broadcast the
-        final thresholds."""
+        """ONE all-gather carries every rank's per-group confidence sums and kept-pixel counts plus its threshold state;
+        every rank then replays the mean-prob EMA over all groups in global order and takes the final thresholds from the
+        rank that scanned the last window."""
         e = self.engine
         C, B = e.C, e.B
         gw = self.window_size // B
-        kmax = (self.n_windows_total + self.world - 1) // self.world
+        kmax = max((self.n_windows_total + self.world - 1) // self.world, 1)
         dev = e.thr_state.device
-        packed = torch.zeros((max(kmax, 1), gw, 2, C), dtype=torch.int64, device=dev)
-        for j, s in enumerate(self._stash):
-            packed[j, :s.shape[0]] = s
+        if self.cuda:
+            torch.cuda.current_stream(e.device).wait_stream(self.side)
+        packed = torch.zeros((kmax * gw * 2 + 1, C), dtype=torch.int64, device=dev)
+        nloc = len(self.my_windows)
+        if nloc and self._stash_conf is not None:
+            groups = self._stash_counts[:nloc].view(nloc, gw, B, C).sum(dim=2)
+            packed[:kmax * gw * 2].view(kmax, gw, 2, C)[:nloc, :, 0] = self._stash_conf[:nloc]
+            packed[:kmax * gw * 2].view(kmax, gw, 2, C)[:nloc, :, 1] = groups
+        packed[-1] = torch.as_tensor(e.thr_state).view(torch.int64)      # the 19 doubles ride along bit for bit
         if self.world > 1:
             gathered = [torch.empty_like(packed) for _ in range(self.world)]
             dist.all_gather(gathered, packed, group=self.pg)
@@ -139,15 +201,14 @@ class ShardedIAS:
         rows = []
         for w in range(self.n_windows_total):
             _, n = window_images(w, self.window_size, self.n_total)
-            rows.append(gathered[w % self.world][w // self.world, :(n + B - 1) // B])
+            rows.append(gathered[w % self.world][:kmax * gw * 2].view(kmax, gw, 2, C)[w // self.world, :(n + B - 1) // B])
         if rows:
             allg = torch.cat(rows)
             confsum, counts = allg[:, 0].contiguous(), allg[:, 1].contiguous()
             e.mean_prob_from_groups(confsum, counts)
             statics = counts.sum(dim=0)
+            last_owner = window_owner(self.n_windows_total - 1, self.world)
+            e.thr_state.copy_(gathered[last_owner][-1].view(torch.float64))
         else:
             statics = torch.zeros(C, dtype=torch.int64, device=dev)
-        if self.world > 1 and self.n_windows_total > 0:
-            last_owner = window_owner(self.n_windows_total - 1, self.world)
-            dist.broadcast(e.thr_state, src=self._global(last_owner), group=self.pg)
         return e.thr_state, e.mean_state, statics

@@ -34,7 +34,7 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, slots=2):
     import sys
     sys.path.insert(0, os.path.dirname(__file__))
     from host_engine import HostEngine
@@ -45,7 +45,7 @@ def _worker(rank, world, port, out_dir):
         s = SPEC
         logits = torch.cat([lg for lg, _ in gi.ias_batches(s)])
         window = 2 * s['B']                               # 2 groups per window -> 4 windows for 13 images
-        eng = HostEngine(s['C'], s['H'], s['W'], s['B'], s['alpha'], s['beta'], s['gamma'], s['cp_gamma'], 2 * window)
+        eng = HostEngine(s['C'], s['H'], s['W'], s['B'], s['alpha'], s['beta'], s['gamma'], s['cp_gamma'], slots * window)
         drv = ShardedIAS(eng, window, s['N'])
         got = {}
 
@@ -64,10 +64,12 @@ def _worker(rank, world, port, out_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('world', [2, 3])
-def test_sharded_equals_unsharded_equals_oracle(world, tmp_path):
+@pytest.mark.parametrize('world,slots', [(2, 3), (3, 3), (2, 2)])
+def test_sharded_equals_unsharded_equals_oracle(world, slots, tmp_path):
+    """slots = 3: chain of window j-1 behind phase A of window j, outputs of window j-2 (the pipelined schedule);
+    slots = 2: outputs directly behind the chain (the round-1 schedule)."""
     port = _free_port()
-    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, str(tmp_path), slots), nprocs=world, join=True)
     s = SPEC
     oracle = oias.IASOracle(s['C'], s['alpha'], s['beta'], s['gamma'], s['cp_gamma'])
     oracle.run(gi.ias_batches(s))
@@ -104,7 +106,7 @@ class _Identity:
         return {'logits': x}
 
 
-def _gen_worker(rank, world, port, out_dir):
+def _gen_worker(rank, world, port, out_dir, window_batches=2):
     import json
     import sys
     sys.path.insert(0, os.path.dirname(__file__))
@@ -119,7 +121,6 @@ def _gen_worker(rank, world, port, out_dir):
     try:
         s = SPEC
         batches = gi.ias_batches(s)                         # global order, batch k = images 2k, 2k+1
-        window_batches = 2
         order = striped_batch_order(s['N'], window_batches * s['B'], s['B'], rank, world)
         loader = [{'images': batches[idx[0] // s['B']][0], 'image_paths': batches[idx[0] // s['B']][1]} for idx in order]
         assert all(len(idx) == len(b['image_paths']) for idx, b in zip(order, loader))
@@ -134,12 +135,14 @@ def _gen_worker(rank, world, port, out_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('world', [2, 3])
-def test_sharded_generator_equals_oracle_and_writes_the_reference_files(world, tmp_path):
+@pytest.mark.parametrize('world,window_batches', [(2, 2), (3, 2), (3, 4)])
+def test_sharded_generator_equals_oracle_and_writes_the_reference_files(world, window_batches, tmp_path):
+    """(3, 4): 13 images in windows of 8 = two windows for three ranks -- the rank without a window must still take part in
+    the collectives and end with the global results."""
     import json
     cv2 = pytest.importorskip('cv2')
     port = _free_port()
-    mp.spawn(_gen_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_gen_worker, args=(world, port, str(tmp_path), window_batches), nprocs=world, join=True)
     s = SPEC
     oracle = oias.IASOracle(s['C'], s['alpha'], s['beta'], s['gamma'], s['cp_gamma'])
     batches = gi.ias_batches(s)
