@@ -149,7 +149,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '25'],
+                                          '--format=csv,noheader,nounits', '-lms', '5'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -230,7 +230,8 @@ def gpu_arm(args):
 
     K, Wm = args.steps, max(args.warmup, 3)
     pool = make_pool(device, args.dist, WINDOW)
-    engine = IASEngine(C, H, W, GROUP, ALPHA, BETA, GAMMA, CP_GAMMA, 2 * WINDOW, device=device)
+    # three window slots: phase A of window j, the threshold chain of j-1 and phase C of j-2 are in flight together
+    engine = IASEngine(C, H, W, GROUP, ALPHA, BETA, GAMMA, CP_GAMMA, 3 * WINDOW, device=device)
 
     def barrier():
         torch.cuda.synchronize()
@@ -239,10 +240,11 @@ def gpu_arm(args):
             torch.cuda.synchronize()
 
     a_events = []
-    fused_used = []
+    launches = {'n': 0}
 
     class TimedEngine:
-        """Forwards to the engine; brackets every phase-A launch with CUDA events on the launching stream."""
+        """Forwards to the engine; brackets every phase-A launch with CUDA events on the launching stream and counts the
+        kernels of this library that are launched."""
         def __getattr__(self, name):
             return getattr(engine, name)
 
@@ -252,21 +254,24 @@ def gpu_arm(args):
             engine.phase_a(logits, first_image)
             e1.record()
             a_events.append((e0, e1))
+            launches['n'] += 1                      # k_softmax_hist_grs
 
-        def process_fused(self, logits, first_image=0):      # one rank: A + B + C in one persistent kernel
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            ok = engine.process_fused(logits, first_image)
-            e1.record()
-            if ok:
-                a_events.append((e0, e1))
-                fused_used.append(1)
-            return ok
+        def phase_b(self, first_image, n_images):
+            engine.phase_b(first_image, n_images)
+            launches['n'] += 2                      # k_hist_prefix + k_threshold_scan
 
-    def run_job(n_steps, timed):
+        def phase_c(self, first_image, n_images):
+            engine.phase_c(first_image, n_images)
+            launches['n'] += 1                      # k_select_private
+
+        def mean_prob_from_groups(self, confsum, counts):
+            engine.mean_prob_from_groups(confsum, counts)
+            launches['n'] += 1                      # k_meanprob_scan
+
+    def run_job(n_steps, timed, on_window=None):
         total_windows = n_steps * world
         drv = ShardedIAS(TimedEngine() if timed else engine, WINDOW, total_windows * WINDOW, rank, world)
-        return drv.run(lambda w: pool)
+        return drv.run(lambda w: pool, on_window)
 
     # warm-up (also creates the NCCL p2p communicators)
     run_job(Wm, timed=False)
@@ -276,22 +281,37 @@ def gpu_arm(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        time.sleep(0.05)
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    wall0 = time.perf_counter()
     t0.record()
     run_job(K, timed=True)
     t1.record()
     barrier()
+    wall1 = time.perf_counter()
     ms = t0.elapsed_time(t1)
-    clocks = sampler.stop() if rank == 0 else None
     certified = engine.check_errors()
+    n_launches = launches['n']
     a_ms = sum(e0.elapsed_time(e1) for e0, e1 in a_events) / max(len(a_events), 1)
+    # The timed region of a short run is a few tens of milliseconds: keep the SAME load running (untimed) until the clock
+    # sampler has seen it for at least 0.3 s, so that the clocks line rests on enough samples.
+    t_end = time.perf_counter() + max(0.0, 0.3 - (wall1 - wall0))
+    while time.perf_counter() < t_end:
+        run_job(max(K, 10), timed=False)
+        torch.cuda.synchronize()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    if clocks is not None:
+        clocks['sampled_over'] = 'the timed steps plus the same load repeated untimed for >= 0.3 s, nvidia-smi -lms 5'
     if world > 1:
         t = torch.tensor([ms, a_ms], dtype=torch.float64, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, a_ms = float(t[0]), float(t[1])
     images = K * WINDOW * world
     value = images / (ms / 1e3)
+
+    parity = sharded_parity(engine, pool, rank, world, device, run_job) if world > 1 else None
 
     # ---- e2e through the reference-facing API with host buffers (every rank its own replica of the call)
     e2e = measure_e2e(args, device, rank, world, barrier)
@@ -307,29 +327,104 @@ def gpu_arm(args):
                        'images_per_step_per_gpu': WINDOW, 'images_total': images, 'alpha': ALPHA, 'beta': BETA,
                        'gamma': GAMMA, 'distribution': args.dist, 'resident_pool_maps': WINDOW,
                        'l2': 'inputs exceed L2 (10.2 GB streamed per step)',
-                       'parallelism': (('one rank: fused A+B+C kernel per window, no collective' if fused_used else
-                                        'one rank: phases A, B (prefix + scan), C and the mean-prob scan per window, no collective')
-                                       if world == 1 else
-                                       'windows striped over %d ranks; 19-double threshold state via NCCL send/recv' % world)},
+                       'parallelism': ('one rank, three windows in flight: phase A(j) | threshold chain(j-1) on a side stream '
+                                       'beside phase C(j-2); no collective' if world == 1 else
+                                       'windows striped over %d ranks, three windows in flight per rank; 19-double threshold '
+                                       'state via NCCL send/recv on the chain stream; one all-gather at the end' % world)},
             'hbm_frac_of_peak': ALG_BYTES_PER_IMAGE * value / world / 1e9 / peak,
-            'roofline': {'kernel': 'k_ias_fused (phases A+B+C in one persistent kernel; the events also cover its 4 memsets)'
-                                   if fused_used else 'k_softmax_hist_grs (phase A)', 'bound': 'hbm', 'achieved': achieved, 'peak': peak,
+            'roofline': {'kernel': 'k_softmax_hist_grs (phase A)', 'bound': 'hbm', 'achieved': achieved, 'peak': peak,
                          'unit': 'GB/s', 'frac': achieved / peak, 'traffic': ncu_traffic(), 'peak_source': peak_src,
                          'algorithmic_bytes_per_launch': ALG_BYTES_PER_IMAGE * WINDOW, 'launch_ms': a_ms,
                          'share_of_step': a_ms / (ms / K)},
             'e2e': e2e,
-            'gpu_launches': (2 if fused_used else 5) * K,
+            'gpu_launches': n_launches,
             'clocks': clocks,
             'pow_rounding_certified': bool(certified),
         }
+        if parity is not None:
+            line['parity'] = parity
         if world == 1 and not args.no_cpu_baseline:
             v, secs, threads = run_cpu_port(args.cpu_images)
             line['cpu_baseline'] = {
                 'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'host_cpus': os.cpu_count(),
                 'sample': '%d maps of 19x1024x2048, batch 2 (%.1f s of host work); PNG write excluded' % (args.cpu_images, secs)}
         print(json.dumps(line), flush=True)
+    if parity is not None and not (parity['thr_equal'] and parity['plbl_sha_equal']):
+        raise SystemExit('sharded run differs from the single-rank replay: %r' % (parity,))
     if world > 1:
         dist.destroy_process_group()
+
+
+def sharded_parity(engine, pool, rank, world, device, run_job, windows_per_rank=2):
+    """After the timed job: the same global job, `windows_per_rank` windows per rank, once sharded (every rank, NCCL token) and
+    once replayed on rank 0 alone; thresholds per group and SHA-256 of every window's pseudo-labels must agree."""
+    import hashlib
+    import torch
+    import torch.distributed as dist
+    from hiast_b200.sharded import ShardedIAS
+
+    def job(drv):
+        got = {}
+
+        def on_window(w, plbl, counts, thr_groups):
+            got[w] = (thr_groups.clone(), plbl.clone())
+        engine.thr_state.fill_(0.9)
+        engine.mean_state.zero_()
+        thr, mean, statics = drv.run(lambda w: pool, on_window)
+        torch.cuda.synchronize()
+        out = {}
+        for w, (tg, pl) in got.items():
+            out[w] = (tg.cpu().numpy().tobytes(), hashlib.sha256(pl.cpu().numpy().tobytes()).hexdigest())
+        return out, thr.cpu().numpy().tobytes(), mean.cpu().numpy().tobytes(), statics.cpu().numpy().tobytes()
+
+    n_windows = windows_per_rank * world
+    mine = job(ShardedIAS(engine, WINDOW, n_windows * WINDOW, rank, world))
+    parts = [None] * world
+    dist.all_gather_object(parts, mine)
+    res = None
+    if rank == 0:
+        ref_windows, ref_thr, ref_mean, ref_statics = job(ShardedIAS(engine, WINDOW, n_windows * WINDOW, 0, 1))
+        merged = {}
+        for p in parts:
+            merged.update(p[0])
+        res = {'windows': n_windows, 'images': n_windows * WINDOW,
+               'thr_equal': sorted(merged) == sorted(ref_windows) and all(merged[w][0] == ref_windows[w][0] for w in ref_windows)
+               and all(p[1] == ref_thr for p in parts),
+               'plbl_sha_equal': all(merged.get(w, (None, None))[1] == ref_windows[w][1] for w in ref_windows),
+               'mean_probs_equal': all(p[2] == ref_mean for p in parts),
+               'statics_equal': all(p[3] == ref_statics for p in parts),
+               'how': 'same global job sharded over %d ranks vs replayed on rank 0 alone, after the timed region' % world}
+    dist.barrier()
+    engine.thr_state.fill_(0.9)
+    engine.mean_state.zero_()
+    return res
+
+
+def h2d_ceiling(host, device, world, barrier, seconds=0.25):
+    """Concurrent pinned host-to-device copy bandwidth of all ranks (GB/s, whole job): what the full-resolution e2e leg can
+    reach at best on this host (VERDICT r1 #1)."""
+    import torch
+    import torch.distributed as dist
+    dst = torch.empty_like(host, device=device)
+    dst.copy_(host, non_blocking=True)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 0
+    t_end = time.perf_counter() + seconds
+    e0.record()
+    while time.perf_counter() < t_end:
+        dst.copy_(host, non_blocking=True)
+        n += 1
+        if n % 4 == 0:
+            torch.cuda.current_stream().synchronize()
+    e1.record()
+    torch.cuda.synchronize()
+    gbs = n * host.numel() * host.element_size() / (e0.elapsed_time(e1) / 1e3) / 1e9
+    t = torch.tensor([gbs], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t)
+    barrier()
+    return float(t[0])
 
 
 def measure_e2e(args, device, rank, world, barrier):
@@ -345,6 +440,7 @@ def measure_e2e(args, device, rank, world, barrier):
     steps = max(1, args.e2e_steps)
     host = torch.empty((n_host, C, H, W), dtype=torch.float32).pin_memory()
     host.copy_(synth_logits_cpu(2).repeat(n_host // 2, 1, 1, 1))
+    ceiling_gbs = h2d_ceiling(host, device, world, barrier)
 
     class Identity:
         def eval(self):
@@ -399,6 +495,8 @@ def measure_e2e(args, device, rank, world, barrier):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         secs = float(t[0])
     res = {'value': steps * WINDOW * world / secs, 'unit': UNIT, 'steps': steps,
+           'h2d_ceiling_gbs': ceiling_gbs, 'h2d_achieved_gbs': steps * WINDOW * world * C * H * W * 4 / secs / 1e9,
+           'h2d_frac_of_ceiling': steps * WINDOW * world * C * H * W * 4 / secs / 1e9 / ceiling_gbs,
            'h2d_bytes_per_step': WINDOW * C * H * W * 4,
            'd2h_bytes_per_step': WINDOW * (H * W + C * 8) + (WINDOW // GROUP) * C * 8,
            'api': ("PSEUDO_POLICY['IAS'](cfg).run() on pinned host logits, identity model, PNG write stubbed" if world == 1 else
@@ -427,7 +525,7 @@ def measure_e2e(args, device, rank, world, barrier):
         gen.run()
         return gen
 
-    steps_lr = 4 * steps
+    steps_lr = max(4 * steps, 46)             # 46 windows = 2944 images, the size of the Cityscapes train set (2975)
     run_lr(WINDOW)
     barrier()
     t0 = time.perf_counter()
@@ -455,24 +553,26 @@ def measure_e2e(args, device, rank, world, barrier):
             pass
 
     def run_png(n_images, mode):
+        """Seconds of construct + run() (files on disk when it returns), number of files, bytes on disk."""
         d = tempfile.mkdtemp()
         try:
             cls = GenPng if mode == 'device' else GenPngHost
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
             gen = cls(cfg, model=LowRes(), loader=loader_lr(n_images), save_dir=os.path.join(d, 'pl'),
                       dataset_len=total(n_images) if mode == 'device' else None,
                       window_batches=WINDOW // GROUP, device=device, png=mode)
             gen.run()
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
             files = os.listdir(os.path.join(d, 'pl'))
-            return len(files), sum(os.path.getsize(os.path.join(d, 'pl', f)) for f in files)
+            return dt, len(files), sum(os.path.getsize(os.path.join(d, 'pl', f)) for f in files)
         finally:
             shutil.rmtree(d, ignore_errors=True)
 
     run_png(WINDOW, 'device')
     barrier()
-    t0 = time.perf_counter()
-    n_files, n_bytes = run_png(steps_lr * WINDOW, 'device')
-    torch.cuda.synchronize()
-    secs = time.perf_counter() - t0
+    secs, n_files, n_bytes = run_png(steps_lr * WINDOW, 'device')
     if world > 1:
         t = torch.tensor([secs], dtype=torch.float64, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -480,12 +580,11 @@ def measure_e2e(args, device, rank, world, barrier):
     assert n_files == steps_lr * WINDOW
     png = {'value': steps_lr * WINDOW * world / secs, 'unit': UNIT, 'steps': steps_lr, 'files_written': n_files,
            'mean_file_bytes': n_bytes / max(1, n_files), 'd2h_bytes_per_step': n_bytes / steps_lr + WINDOW * C * 8,
-           'api': 'same call with the PNG files written (device encoder, one native hiast_write_files call per window with %d POSIX writers, double-buffered)' % 8}
+           'files_dir': tempfile.gettempdir(),
+           'api': 'same call with the PNG files written (device encoder, native writer pool with %d POSIX writers per rank, completion deferred by three windows)' % IASPseudoGenerator._default_workers()}
     if rank == 0:                                   # the reference's writer (cv2.imwrite on host label maps) beside it
         n_host_png = WINDOW
-        t0 = time.perf_counter()
-        run_png(n_host_png, 'host')
-        png['host_cv2_imwrite_images_per_s'] = n_host_png / (time.perf_counter() - t0)
+        png['host_cv2_imwrite_images_per_s'] = n_host_png / run_png(n_host_png, 'host')[0]
     barrier()
     res['from_stride8_logits']['with_png_files'] = png
     return res

@@ -385,8 +385,6 @@ class PngEncoder:
         self._offsets = torch.empty(self.max_images + 1, dtype=torch.int64, device=self.device)
         self._host = {}
         self._last_offsets = {}
-        self._async = {}
-        self._predicted = int(self.max_file * self.max_images / 4) + 4096   # bytes of a window's files, refined per call
         self._host_off = torch.empty(self.max_images + 1, dtype=torch.int64).pin_memory()
 
     def _launch(self, labels):
@@ -409,59 +407,6 @@ class PngEncoder:
             self._blob = torch.empty(self.max_file * self.max_images + 4096, dtype=torch.uint8, device=self.device)
             self._launch(labels)
         return self._blob[:total], self._offsets[:n + 1], self._host_off[:n + 1]
-
-    # ---- deferred form: nothing on the host waits for the GPU until ``finish`` --------------------------------------
-    def encode_async(self, labels, slot=0):
-        """Launch the encoder for ``labels`` into the slot's own worst-case device blob, queue the copies of the offset table
-        and of the predicted number of blob bytes (1.25 x the previous total) to the slot's pinned buffers, record an event and
-        return a handle.  ``finish(handle)`` waits for the event only -- by then usually long past -- and tops the copy up in the
-        rare case the files were larger than predicted (the device blob of a slot is not reused before the slot's next call)."""
-        require_cuda(labels, torch.uint8, 'labels')
-        n = labels.shape[0]
-        if tuple(labels.shape[1:]) != (self.H, self.W) or n > self.max_images:
-            raise _lib.HiastError('labels must be [<=%d, %d, %d], got %s' % (self.max_images, self.H, self.W, tuple(labels.shape)))
-        st = self._async.get(slot)
-        if st is None:
-            cap = self.max_file * self.max_images + 4096
-            st = self._async[slot] = dict(blob=torch.empty(cap, dtype=torch.uint8, device=self.device),
-                                          offsets=torch.empty(self.max_images + 1, dtype=torch.int64, device=self.device),
-                                          host_off=torch.empty(self.max_images + 1, dtype=torch.int64).pin_memory())
-        check(lib().hiast_png_encode(ptr(labels), n, self.H, self.W, ptr(st['blob']), st['blob'].numel(), ptr(st['offsets']),
-                                     ptr(self._ws), self._ws.numel(), stream_ptr(self.device)), 'hiast_png_encode')
-        st['host_off'][:n + 1].copy_(st['offsets'][:n + 1], non_blocking=True)
-        host = self._host.get(slot)
-        want = min(st['blob'].numel(), max(self._predicted, 1 << 20))
-        if host is None or host.numel() < want:
-            host = self._host[slot] = torch.empty(want + want // 4, dtype=torch.uint8).pin_memory()
-        pred = min(host.numel(), st['blob'].numel())
-        pred = min(pred, max(self._predicted, 1 << 20))
-        host[:pred].copy_(st['blob'][:pred], non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream(self.device))
-        return (slot, n, pred, ev)
-
-    def finish(self, handle):
-        """(pinned uint8 numpy blob, n+1 offsets) of an ``encode_async`` call."""
-        slot, n, pred, ev = handle
-        ev.synchronize()
-        st = self._async[slot]
-        o = st['host_off'][:n + 1].tolist()
-        total = o[-1]
-        host = self._host[slot]
-        if total > pred:                                  # larger than predicted: fetch the rest now (device blob still intact)
-            if host.numel() < total:
-                bigger = torch.empty(total + total // 4, dtype=torch.uint8).pin_memory()
-                bigger[:pred].copy_(host[:pred])
-                host = self._host[slot] = bigger
-            host[pred:total].copy_(st['blob'][pred:total], non_blocking=True)
-            torch.cuda.current_stream(self.device).synchronize()
-        self._predicted = total + total // 4 + 65536
-        self._last_offsets[slot] = o
-        return host.numpy(), o
-
-    def host_blob(self, slot=0):
-        """(pinned uint8 numpy blob, n+1 offsets) of the last ``encode_to_host(..., slot)``: what ``write_files`` takes."""
-        return self._host[slot].numpy(), self._last_offsets[slot]
 
     def encode_to_host(self, labels, slot=0):
         """List of numpy uint8 arrays, one PNG file each: views of the pinned buffer `slot`, valid until the next call
@@ -682,6 +627,7 @@ class WindowEmitter:
 
     def __init__(self, engine, window_images, n_slots=3, png=True):
         e = self.engine = engine
+        self.in_use = False
         self.window, self.n_slots, self.png = int(window_images), int(n_slots), bool(png)
         self.device = e.device
         n, g, c, hw = self.window, (self.window + e.B - 1) // e.B, e.C, e.H * e.W
@@ -719,7 +665,30 @@ class WindowEmitter:
             self.slots.append(s)
         self._emit = l.hiast_ias_emit_window
 
-    def emit(self, slot, first_image, n_images, with_mean_prob=False):
+    _CACHE = {}
+
+    @classmethod
+    def get(cls, engine, window_images, n_slots=3, png=True):
+        """An emitter for this engine geometry, reused across generator runs of one process (its pinned and device buffers
+        -- several hundred MB at full resolution -- take ~10 ms to allocate and pin)."""
+        key = (str(engine.device), engine.C, engine.H, engine.W, engine.B, float(engine.cp_gamma), int(window_images), int(n_slots),
+               bool(png))
+        em = cls._CACHE.get(key)
+        if em is None or em.in_use:                      # in use: another live pipeline owns its buffers
+            em = cls(engine, window_images, n_slots, png)
+            if key not in cls._CACHE:
+                if len(cls._CACHE) >= 4:
+                    cls._CACHE.clear()
+                cls._CACHE[key] = em
+        em.engine = engine
+        em.in_use = True
+        return em
+
+    def done(self):
+        """The pipeline that took this emitter from ``get`` has completed every window."""
+        self.in_use = False
+
+    def emit(self, slot, first_image, n_images, with_mean_prob=False, stream=None):
         """Queue the outputs of engine images [first_image, first_image + n) into emit slot ``slot`` on the current stream."""
         e, s = self.engine, self.slots[slot]
         a = s['args']
@@ -735,7 +704,7 @@ class WindowEmitter:
         copied = 0
         if self.png:
             copied = a.blob_copy_bytes = min(self.predicted, s['blob_dev'].numel())
-        check(self._emit(C.byref(a), stream_ptr(self.device)), 'hiast_ias_emit_window')
+        check(self._emit(C.byref(a), stream if stream is not None else stream_ptr(self.device)), 'hiast_ias_emit_window')
         return copied
 
     def learn(self, total_bytes):

@@ -244,6 +244,28 @@ class BasePseudoGenerator:
         current_stats['file'] = img_path
         self.sample_stats.append(current_stats)
 
+    def _record_images(self, counts, paths):
+        """:82-89 for a whole run at once: the same three structures ``_record_image`` appends to, rebuilt from the
+        [n_images, C] count matrix in image order."""
+        C = self.cfg.dataset.num_classes
+        n = counts.shape[0]
+        rows, cols = np.nonzero(counts)
+        vals = counts[rows, cols].tolist()
+        cols_l = cols.tolist()
+        cut = np.searchsorted(rows, np.arange(n + 1)).tolist()
+        stats = []
+        for i in range(n):
+            a, b = cut[i], cut[i + 1]
+            d = dict(zip(cols_l[a:b], vals[a:b]))
+            d['file'] = paths[i]
+            stats.append(d)
+        self.sample_stats = stats
+        self.samples_class = {}
+        for c in range(C):
+            idx = np.flatnonzero(counts[:, c])
+            self.samples_class[c] = [[paths[i], v] for i, v in zip(idx.tolist(), counts[idx, c].tolist())]
+        self.statics_class = np.array([0] * C) + (counts.sum(axis=0) if n else 0)
+
     def _cp_gamma(self):
         return float(_cfg_get(self.cfg, 'preprocessor.copy_paste.gamma', 0.99))
 
@@ -312,13 +334,20 @@ class BasePseudoGenerator:
                 raise HiastError('staging ring exhausted')
             pipe.flush_queued()                                      # launches the queued phase A and releases its slots
         self._stage_cursor += 1
-        return st.push(slot, images, stream_ptr(self.device)), slot
+        return st.push(slot, images, self._main_stream_ptr()), slot
+
+    def _main_stream_ptr(self):
+        """The current stream of the device as a void* (looked up once per run: the lookup costs ~15 us in torch)."""
+        p = getattr(self, '_main_ptr', None)
+        if p is None:
+            p = self._main_ptr = stream_ptr(self.device)
+        return p
 
     def _release_staged(self, slots):
         st = self._stager
         if st is None or not slots:
             return
-        main = stream_ptr(self.device)
+        main = self._main_stream_ptr()
         slots = sorted(slots)
         run0 = prev = slots[0]
         for s in slots[1:] + [None]:
@@ -336,6 +365,7 @@ class BasePseudoGenerator:
         constant ``thr_const`` per class)."""
         C = self.cfg.dataset.num_classes
         pipe = None
+        self._main_ptr = None
         it = self._iterate_logits(lambda: pipe)
         for logits, img_paths, slot in it:
             if pipe is None:
@@ -398,10 +428,7 @@ class BasePseudoGenerator:
             self.class_threshold = parts[last_owner]['thr_state']
         B = e.B
         self.threshold_trace = [merged[w][3] for w in order]
-        self.sample_stats = []
-        self.samples_class = {i: [] for i in range(C)}
-        self.statics_class = np.array([0] * C)
-        group_counts, confsums = [], []
+        group_counts, confsums, all_counts, all_paths = [], [], [], []
         for w in order:
             paths, counts, confsum, _ = merged[w]
             n = counts.shape[0]
@@ -410,8 +437,9 @@ class BasePseudoGenerator:
             padded[:n] = counts
             group_counts.append(padded.reshape(g, B, C).sum(axis=1))
             confsums.append(confsum[:g])
-            for i in range(n):
-                self._record_image(counts[i], paths[i])
+            all_counts.append(counts)
+            all_paths += paths
+        self._record_images(np.concatenate(all_counts) if all_counts else np.zeros((0, C), dtype=np.int64), all_paths)
         if order:
             dev = e.thr_state.device
             e.mean_state.copy_(torch.from_numpy(np.asarray(self.class_mean_probs, dtype=np.float64)))
@@ -455,7 +483,8 @@ class _WindowPipeline:
             if gen._device_png() and engine.W > 128 * 256:
                 gen.png = 'host'                       # wider than the device writer's 32768-pixel rows: the reference's writer
             self.mode = 'host' if not gen._device_png() else ('files' if gen._native_files() else 'blobs')
-            self.emitter = ops.WindowEmitter(engine, self.window, self.N_SLOTS, png=self.mode != 'host')
+            self.emitter = ops.WindowEmitter.get(engine, self.window, self.N_SLOTS, png=self.mode != 'host')
+            self.main_ptr = stream_ptr(dev)
             if self.mode == 'files':
                 if gen._writer is None:
                     gen._writer = ops.FileWriter(gen._png_workers, dev)
@@ -540,6 +569,9 @@ class _WindowPipeline:
             self._complete(es)
         for es in list(self._host_jobs):
             self._wait_host_jobs(es)
+        if self.emitter is not None:
+            self.gen._wait_png()
+            self.emitter.done()
 
     # ---------------------------------------------------------------- the schedule
     def _advance(self, final):
@@ -607,13 +639,12 @@ class _WindowPipeline:
         self._wait_host_jobs(es)
         if self.scan:
             self.main.wait_event(self.ev_b[es])
-        copied = self.emitter.emit(es, first, n)
+        copied = self.emitter.emit(es, first, n, stream=self.main_ptr)
         s = self.emitter.slots[es]
         rec = dict(j=j, w=w, n=n, paths=paths, copied=copied)
         if self.mode == 'files':
             targets = [gen._pseudo_label_path(p) for p in paths]
-            rec['ticket'] = self.writer.submit(targets, s['blob_host'], s['offsets_host'], copied, s['blob_dev'],
-                                               stream_ptr(e.device))
+            rec['ticket'] = self.writer.submit(targets, s['blob_host'], s['offsets_host'], copied, s['blob_dev'], self.main_ptr)
         else:
             ev = rec['event'] = torch.cuda.Event(blocking=True)
             ev.record(self.main)

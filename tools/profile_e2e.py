@@ -54,8 +54,14 @@ def main():
         g = cls(cfg, model=LowRes(), loader=loader(n), save_dir=os.path.join(tempfile.mkdtemp(), 'pl'), window_batches=WINDOW // GROUP)
         g.run()
 
+    import time
     run(WINDOW)
     torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    run(args.steps * WINDOW)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    print('unprofiled: %.1f images/s (%.2f ms per %d-image window)' % (args.steps * WINDOW / dt, dt / args.steps * 1e3, WINDOW))
     pr = cProfile.Profile()
     pr.enable()
     run(args.steps * WINDOW)
