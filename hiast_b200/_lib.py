@@ -71,7 +71,7 @@ _SIGNATURES = {
     'hiast_stager_destroy': (_i, [_vp]),
     'hiast_stager_push': (_i, [_vp, _i, _vp, _vp, _sz, _vp, _vp]),
     'hiast_stager_release': (_i, [_vp, _i, _i, _vp]),
-    'hiast_ias_emit_window': (_i, [C.POINTER(WindowEmit), _vp]),
+    'hiast_ias_emit_window': (_i, [C.POINTER(WindowEmit), _vp, _vp]),
     'hiast_writer_create': (_i, [_i, C.POINTER(_vp)]),
     'hiast_writer_destroy': (_i, [_vp]),
     'hiast_writer_submit': (_i64, [_vp, _vp, _i, _vp, _sz, _vp, _sz, _vp, _vp]),

@@ -5,8 +5,9 @@ files are merged into (``cfg.merge_from_file``) and that is frozen before use (`
 not a dependency of this package, so the three behaviours the call surface relies on are restated here on PyYAML:
 
 * merging accepts only keys that already exist in the defaults (yacs: ``KeyError: Non-existent config key``);
-* a merged value must keep the type of its default unless the default is ``None`` (int -> float and list <-> tuple are
-  coerced, as yacs does);
+* a string read from yaml is decoded as a Python literal when it is one (yacs' ``_decode_cfg_value``: PyYAML reads
+  ``lr: 3e-6`` of ``configs/sl_1.yaml`` as the string '3e-6'), and a merged value must keep the type of its default
+  unless the default is ``None`` (int -> float and list <-> tuple are coerced, as yacs does);
 * a frozen tree rejects assignment.
 
 ``default_cfg()`` returns a fresh tree holding every key and default value of ``utils/default_config.py`` -- the key names and
@@ -15,6 +16,7 @@ defaults ARE the interface of the reference's yaml files (``configs/sl_1.yaml`` 
 
 from __future__ import annotations
 
+import ast
 import copy
 
 import yaml
@@ -85,7 +87,17 @@ class CfgNode(dict):
                     raise ValueError('Type mismatch for config key {}: a section was replaced by {!r}'.format(full, v))
                 cur.merge_from_dict(v, _trail + (str(k),))
             else:
-                dict.__setitem__(self, k, _coerce(v, cur, full))
+                dict.__setitem__(self, k, _coerce(_decode(v), cur, full))
+
+
+def _decode(v):
+    """yacs' ``_decode_cfg_value``: strings that are Python literals ('3e-6', '[1, 2]', 'None') become those values."""
+    if not isinstance(v, str):
+        return v
+    try:
+        return ast.literal_eval(v)
+    except (ValueError, SyntaxError):
+        return v
 
 
 def _coerce(new, old, key):

@@ -92,7 +92,7 @@ extern "C" int hiast_stager_release(void* handle, int first_slot, int n_slots, v
 }
 
 // ------------------------------------------------------------------------------------------ emit
-extern "C" int hiast_ias_emit_window(const HiastWindowEmit* a, void* stream) {
+extern "C" int hiast_ias_emit_window(const HiastWindowEmit* a, void* stream, void* copy_stream) {
   if (!a || !a->conf || !a->label || !a->thr_groups || !a->plbl || !a->counts || !a->confsum) return HIAST_ERR_INVALID_ARG;
   if (a->n_images < 0 || a->H < 1 || a->W < 1 || a->C < 1 || a->C > HIAST_MAX_CLASSES || a->group_size < 1)
     return HIAST_ERR_INVALID_ARG;
@@ -110,18 +110,33 @@ extern "C" int hiast_ias_emit_window(const HiastWindowEmit* a, void* stream) {
     if (!a->offsets_dev || !a->png_ws || !a->offsets_host || !a->blob_host) return HIAST_ERR_INVALID_ARG;
     HIAST_TRY(hiast_png_encode(a->plbl, n, a->H, a->W, a->blob_dev, a->blob_capacity, a->offsets_dev, a->png_ws,
                                a->png_ws_bytes, stream));
-    HIAST_CUDA_TRY(cudaMemcpyAsync(a->offsets_host, a->offsets_dev, sizeof(int64_t) * (n + 1), cudaMemcpyDeviceToHost, st));
+  }
+  // the device-to-host copies leave the compute stream: behind one event they run on copy_stream, beside the next
+  // window's kernels (a window's label maps are 134 MB = 2.4 ms of PCIe at full resolution)
+  cudaStream_t cs = st;
+  if (copy_stream && as_stream(copy_stream) != st) {
+    static thread_local cudaEvent_t bridge[64] = {nullptr};
+    int dev = 0;
+    HIAST_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return HIAST_ERR_UNSUPPORTED;
+    if (!bridge[dev]) HIAST_CUDA_TRY(cudaEventCreateWithFlags(&bridge[dev], cudaEventDisableTiming));
+    cs = as_stream(copy_stream);
+    HIAST_CUDA_TRY(cudaEventRecord(bridge[dev], st));
+    HIAST_CUDA_TRY(cudaStreamWaitEvent(cs, bridge[dev], 0));
+  }
+  if (a->blob_dev) {
+    HIAST_CUDA_TRY(cudaMemcpyAsync(a->offsets_host, a->offsets_dev, sizeof(int64_t) * (n + 1), cudaMemcpyDeviceToHost, cs));
     const size_t copy = a->blob_copy_bytes < a->blob_capacity ? a->blob_copy_bytes : a->blob_capacity;
-    if (copy) HIAST_CUDA_TRY(cudaMemcpyAsync(a->blob_host, a->blob_dev, copy, cudaMemcpyDeviceToHost, st));
+    if (copy) HIAST_CUDA_TRY(cudaMemcpyAsync(a->blob_host, a->blob_dev, copy, cudaMemcpyDeviceToHost, cs));
   } else if (a->plbl_host) {
-    HIAST_CUDA_TRY(cudaMemcpyAsync(a->plbl_host, a->plbl, static_cast<size_t>(n) * HW, cudaMemcpyDeviceToHost, st));
+    HIAST_CUDA_TRY(cudaMemcpyAsync(a->plbl_host, a->plbl, static_cast<size_t>(n) * HW, cudaMemcpyDeviceToHost, cs));
   }
   if (a->counts_host)
-    HIAST_CUDA_TRY(cudaMemcpyAsync(a->counts_host, a->counts, sizeof(int64_t) * n * C, cudaMemcpyDeviceToHost, st));
+    HIAST_CUDA_TRY(cudaMemcpyAsync(a->counts_host, a->counts, sizeof(int64_t) * n * C, cudaMemcpyDeviceToHost, cs));
   if (a->confsum_host)
-    HIAST_CUDA_TRY(cudaMemcpyAsync(a->confsum_host, a->confsum, sizeof(uint64_t) * g * C, cudaMemcpyDeviceToHost, st));
+    HIAST_CUDA_TRY(cudaMemcpyAsync(a->confsum_host, a->confsum, sizeof(uint64_t) * g * C, cudaMemcpyDeviceToHost, cs));
   if (a->thr_groups_host)
-    HIAST_CUDA_TRY(cudaMemcpyAsync(a->thr_groups_host, a->thr_groups, sizeof(double) * g * C, cudaMemcpyDeviceToHost, st));
+    HIAST_CUDA_TRY(cudaMemcpyAsync(a->thr_groups_host, a->thr_groups, sizeof(double) * g * C, cudaMemcpyDeviceToHost, cs));
   return HIAST_OK;
 }
 

@@ -688,7 +688,7 @@ class WindowEmitter:
         """The pipeline that took this emitter from ``get`` has completed every window."""
         self.in_use = False
 
-    def emit(self, slot, first_image, n_images, with_mean_prob=False, stream=None):
+    def emit(self, slot, first_image, n_images, with_mean_prob=False, stream=None, copy_stream=None):
         """Queue the outputs of engine images [first_image, first_image + n) into emit slot ``slot`` on the current stream."""
         e, s = self.engine, self.slots[slot]
         a = s['args']
@@ -704,7 +704,8 @@ class WindowEmitter:
         copied = 0
         if self.png:
             copied = a.blob_copy_bytes = min(self.predicted, s['blob_dev'].numel())
-        check(self._emit(C.byref(a), stream if stream is not None else stream_ptr(self.device)), 'hiast_ias_emit_window')
+        check(self._emit(C.byref(a), stream if stream is not None else stream_ptr(self.device), copy_stream),
+              'hiast_ias_emit_window')
         return copied
 
     def learn(self, total_bytes):

@@ -41,11 +41,19 @@ class CopyPaste:
         self.class_probs = self.calculate_class_probs()
 
     def calculate_class_probs(self):
-        """:29-34  (1 - v)^2 / sum; classes forced to inf get probability 0 instead of NaN."""
-        v = np.asarray(self.class_value, dtype=np.float64)
-        finite = np.isfinite(v)
-        p = np.where(finite, (1 - np.where(finite, v, 0.0)) ** 2, 0.0)
-        return p / np.sum(p)
+        """:29-34  (1 - v)^2 / sum with the reference's own TORCH float64 ops (``torch.tensor(...)``, ``**``, ``torch.sum``):
+        numpy's summation order can differ in the last ulp, and a last-ulp difference in p can change a draw of
+        ``np.random.choice`` (pinned on 20 seeds by tests/golden/copy_paste_probs.npz).  Classes forced to inf (SYNTHIA) get
+        probability 0 instead of the reference's NaN; for finite values nothing differs from the reference."""
+        probs = torch.tensor(np.asarray(self.class_value, dtype=np.float64))
+        finite = torch.isfinite(probs)
+        if bool(finite.all()):
+            probs = (1 - probs) ** 2
+        else:
+            zero = torch.zeros_like(probs)
+            probs = torch.where(finite, (1 - torch.where(finite, probs, zero)) ** 2, zero)
+        probs = probs / torch.sum(probs)
+        return probs.numpy()
 
     def get_hard_classes(self, class_value):
         """:36-44"""
@@ -112,9 +120,15 @@ class CopyPaste:
             return img, lbl, out_mask
         return d_img[0], d_lbl[0], mask[0]
 
-    def run_batch(self, imgs, lbls, donor_imgs, donor_lbls, donor_index=None):
-        """One launch for a whole batch already on the device.  imgs u8 [N,H,W,3], lbls u8 [N,H,W]; the
-        donor of image i is donor_*[donor_index[i]].  Returns (imgs, lbls, copy_paste_masks), in place."""
+    def run_batch(self, imgs, lbls, donor_imgs=None, donor_lbls=None, donor_index=None):
+        """One launch for a whole batch already on the device.  imgs u8 [N,H,W,3], lbls u8 [N,H,W].  With explicit donors the
+        donor of image i is donor_*[donor_index[i]]; without them the batch-level sampler draws one donor per image exactly as
+        ``run_original`` would for the images in order (same global ``np.random`` stream), loads the donors from
+        ``dataset_copy_from`` and uploads each distinct donor once (``DonorSampler``).  Returns (imgs, lbls, masks), in place."""
+        if donor_imgs is None:
+            if getattr(self, '_sampler', None) is None:
+                self._sampler = DonorSampler(self)
+            donor_imgs, donor_lbls, donor_index = self._sampler.sample(lbls.shape[0], tuple(lbls.shape[1:]))
         masks = torch.full_like(lbls, 255)
         ops.copy_paste(imgs, lbls, masks, donor_imgs, donor_lbls, self.hard_classes, donor_index)
         return imgs, lbls, masks
@@ -127,3 +141,75 @@ class CopyPaste:
         img = cv2.resize(np.asarray(img), tuple(target_shape[::-1]), interpolation=cv2.INTER_LINEAR)
         lbl = cv2.resize(np.asarray(lbl), tuple(target_shape[::-1]), interpolation=cv2.INTER_NEAREST)
         return img, lbl
+
+
+class DonorSampler:
+    """Batch-level donor sampler for the GPU copy-paste (VERDICT r1 missing #4).
+
+    The reference pastes inside DataLoader workers, one image at a time (``base_dataset.py:99-124`` ->
+    ``preprocessor.py:79-122``): per image one class draw (``random_select``, :93), one file draw (:95), one ``load_data``
+    (:97).  On the device the paste is one launch per batch, so the donors of a batch are drawn up front -- the same two
+    ``np.random`` calls per image in image order, hence the same donors as a sequential reference run with the same seed --
+    loaded on a small thread pool, staged in pinned memory and uploaded with one copy per tensor; donors that repeat within
+    the batch are loaded and uploaded once, and the ``cache`` most recently used donors stay on the device.
+
+    (``run_original``'s ``for _ in range(3)`` loop always stops after its first donor: the first pass marks every hard class
+    as existing regardless of the donor's content, SURVEY.md A.4 -- one donor per image is the reference's behaviour.)"""
+
+    def __init__(self, copy_paste, cache=64, workers=4):
+        from concurrent.futures import ThreadPoolExecutor
+        self.cp = copy_paste
+        self.cache = int(cache)
+        self._lru = {}                                # dataset index -> (img u8 [H,W,3], lbl u8 [H,W]) on the device
+        self._tick = 0
+        self._pool = ThreadPoolExecutor(max_workers=max(1, int(workers)))
+        self._pins = None
+
+    def draw(self, n):
+        """Dataset indices of the donors of n images in order: the RNG calls of preprocessor.py:93-96, nothing else."""
+        cp = self.cp
+        out = []
+        for _ in range(n):
+            select_c = cp.random_select(cp.hard_classes)
+            file_name = np.random.choice(cp.samples_with_class[select_c])
+            out.append(cp.dataset_copy_from.get_file_to_idx(file_name))
+        return out
+
+    def _load(self, idx, hw):
+        img_, lbl_, _path = self.cp.dataset_copy_from.load_data(idx)
+        if tuple(img_.shape[:2]) != tuple(hw):                                  # :99-100
+            img_, lbl_ = self.cp.resize(img_, lbl_, hw)
+        return np.ascontiguousarray(img_, dtype=np.uint8), np.ascontiguousarray(lbl_, dtype=np.uint8)
+
+    def sample(self, n, hw):
+        """(donor_imgs u8 [m,H,W,3], donor_lbls u8 [m,H,W], donor_index i32 [n]) on the device for a batch of n images."""
+        dev = self.cp.device
+        idxs = self.draw(n)
+        distinct = list(dict.fromkeys(idxs))
+        missing = [i for i in distinct if i not in self._lru]
+        if missing:
+            loaded = list(self._pool.map(lambda i: self._load(i, hw), missing))
+            m, (h, w) = len(missing), hw
+            if self._pins is None or self._pins[0].shape[0] < m or tuple(self._pins[0].shape[1:3]) != (h, w):
+                self._pins = (torch.empty((max(m, n), h, w, 3), dtype=torch.uint8).pin_memory(),
+                              torch.empty((max(m, n), h, w), dtype=torch.uint8).pin_memory())
+            else:
+                torch.cuda.current_stream(dev).synchronize()        # the previous batch's upload still reads the pins
+            for k, (img_, lbl_) in enumerate(loaded):
+                self._pins[0][k].copy_(torch.from_numpy(img_))
+                self._pins[1][k].copy_(torch.from_numpy(lbl_))
+            d_img = self._pins[0][:m].to(dev, non_blocking=True)
+            d_lbl = self._pins[1][:m].to(dev, non_blocking=True)
+            for k, i in enumerate(missing):
+                self._lru[i] = [d_img[k], d_lbl[k], 0]
+        for i in distinct:
+            self._tick += 1
+            self._lru[i][2] = self._tick
+        pos = {i: k for k, i in enumerate(distinct)}
+        donor_imgs = torch.stack([self._lru[i][0] for i in distinct])
+        donor_lbls = torch.stack([self._lru[i][1] for i in distinct])
+        donor_index = torch.tensor([pos[i] for i in idxs], dtype=torch.int32).to(dev, non_blocking=True)
+        if len(self._lru) > self.cache:
+            for i, _ in sorted(self._lru.items(), key=lambda kv: kv[1][2])[:len(self._lru) - self.cache]:
+                del self._lru[i]
+        return donor_imgs, donor_lbls, donor_index

@@ -157,9 +157,8 @@ class BasePseudoGenerator:
             warnings.warn('not load model')
         return model.to(self.device)
 
-    def _build_target_loader(self):
-        """:29-36  target dataset at ``pseudo_policy.resize_size`` in a shuffled DataLoader."""
-        from torch.utils.data import DataLoader
+    def _build_target_dataset(self):
+        """:29-35  target dataset at ``pseudo_policy.resize_size``."""
         cfg = self.cfg
         ttype = _cfg_get(cfg, 'dataset.target.type')
         if ttype not in DATASET:
@@ -167,8 +166,14 @@ class BasePseudoGenerator:
                                "hiast_b200: register the host project's dataset class or pass loader=" % (ttype,))
         rs = cfg.pseudo_policy.resize_size
         aug_type = ['PRS-{}-{}'.format(rs[0], rs[1])]
-        ds = DATASET[ttype](cfg, cfg.dataset.target.json_path, cfg.dataset.target.image_dir, aug_type=aug_type,
-                            num_classes=cfg.dataset.num_classes)
+        return DATASET[ttype](cfg, cfg.dataset.target.json_path, cfg.dataset.target.image_dir, aug_type=aug_type,
+                              num_classes=cfg.dataset.num_classes)
+
+    def _build_target_loader(self):
+        """:36  a shuffled DataLoader over the target set."""
+        from torch.utils.data import DataLoader
+        cfg = self.cfg
+        ds = self._build_target_dataset()
         loader = DataLoader(ds, cfg.pseudo_policy.batch_size, shuffle=True, num_workers=cfg.dataset.num_workers, pin_memory=True)
         return ds, loader
 
@@ -480,6 +485,9 @@ class _WindowPipeline:
             self.side = _stream(dev, 'chain')
             self.ev_a = [torch.cuda.Event() for _ in range(self.N_SLOTS)]
             self.ev_b = [torch.cuda.Event() for _ in range(self.N_SLOTS)]
+            self.out = _stream(dev, 'out')             # device-to-host copies of a window's results
+            self.out_ptr = ops.C.c_void_p(self.out.cuda_stream)
+            self.ev_out = [None] * self.N_SLOTS
             if gen._device_png() and engine.W > 128 * 256:
                 gen.png = 'host'                       # wider than the device writer's 32768-pixel rows: the reference's writer
             self.mode = 'host' if not gen._device_png() else ('files' if gen._native_files() else 'blobs')
@@ -607,6 +615,8 @@ class _WindowPipeline:
             body()
             return
         self.side.wait_event(self.ev_a[(len(self.closed) - 1) % self.N_SLOTS])
+        if self.ev_out[j % self.N_SLOTS] is not None:        # window j-3's thresholds have been copied out of this slot
+            self.side.wait_event(self.ev_out[j % self.N_SLOTS])
         with torch.cuda.stream(self.side):
             body()
             self.ev_b[j % self.N_SLOTS].record(self.side)
@@ -639,15 +649,20 @@ class _WindowPipeline:
         self._wait_host_jobs(es)
         if self.scan:
             self.main.wait_event(self.ev_b[es])
-        copied = self.emitter.emit(es, first, n, stream=self.main_ptr)
+        if self.ev_out[es] is not None:                      # the copies of window j-3 have left this slot's device buffers
+            self.main.wait_event(self.ev_out[es])
+        copied = self.emitter.emit(es, first, n, stream=self.main_ptr, copy_stream=self.out_ptr)
         s = self.emitter.slots[es]
         rec = dict(j=j, w=w, n=n, paths=paths, copied=copied)
         if self.mode == 'files':
             targets = [gen._pseudo_label_path(p) for p in paths]
-            rec['ticket'] = self.writer.submit(targets, s['blob_host'], s['offsets_host'], copied, s['blob_dev'], self.main_ptr)
+            rec['ticket'] = self.writer.submit(targets, s['blob_host'], s['offsets_host'], copied, s['blob_dev'], self.out_ptr)
         else:
             ev = rec['event'] = torch.cuda.Event(blocking=True)
-            ev.record(self.main)
+            ev.record(self.out)
+        if self.ev_out[es] is None:
+            self.ev_out[es] = torch.cuda.Event()
+        self.ev_out[es].record(self.out)
         self.pending[es] = rec
         if not gen.defer_sync:
             self._complete(es)
@@ -842,3 +857,13 @@ class ShardedIASPseudoGenerator(IASPseudoGenerator):
         if dist.is_available() and dist.is_initialized():
             return dist.get_rank(self._pg), dist.get_world_size(self._pg), self._pg
         return 0, 1, None
+
+    def _build_target_loader(self):
+        """The target set in its pinned order, this rank's windows only (``striped_batch_order`` as the batch sampler)."""
+        from torch.utils.data import DataLoader
+        cfg = self.cfg
+        ds = self._build_target_dataset()
+        rank, world, _ = self._ranks()
+        b = cfg.pseudo_policy.batch_size
+        order = striped_batch_order(len(ds), b * self.window_batches, b, rank, world)
+        return ds, DataLoader(ds, batch_sampler=order, num_workers=cfg.dataset.num_workers, pin_memory=True)

@@ -35,7 +35,7 @@ _STREAMS = {}
 
 
 def device_stream(device, kind):
-    """One copy stream ('copy') and one high-priority chain stream ('chain') per device for the life of the process (NCCL and
+    """One host-to-device copy stream ('copy'), one device-to-host stream ('out') and one high-priority chain stream ('chain') per device for the life of the process (NCCL and
     the caching allocator keep per-stream state; a fresh stream per run would pay for it again)."""
     device = torch.device(device)
     key = (kind, device.index if device.index is not None else torch.cuda.current_device())

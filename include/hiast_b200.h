@@ -296,8 +296,11 @@ HIAST_API int hiast_stager_release(void* handle, int first_slot, int n_slots, vo
  * zero counts / confsum, hiast_ias_select (:71-89), optionally hiast_ias_meanprob_scan (:95-105; mean_state NULL =
  * skip), then either hiast_png_encode (:43-46; blob_dev != NULL) with the copies of the offset table and of the first
  * blob_copy_bytes of the blob to pinned host memory, or (blob_dev NULL, plbl_host != NULL) the copy of the uint8
- * label maps themselves; and the copies of counts / confsum / thr_groups (each nullable).  Host pointers must stay
- * valid and untouched until the stream reaches this point (use an event or hiast_writer_submit's ticket).        */
+ * label maps themselves; and the copies of counts / confsum / thr_groups (each nullable).  The kernels run on `stream`;
+ * the device-to-host copies run on `copy_stream` behind them (NULL or == stream: on `stream` itself), so that they
+ * overlap the next window's kernels -- the caller must make `stream` wait for `copy_stream` before it overwrites the
+ * window's device buffers again.  Host pointers must stay valid and untouched until copy_stream reaches this point
+ * (use an event or hiast_writer_submit's ticket, both recorded on copy_stream).                                   */
 typedef struct HiastWindowEmit {
   const float*   conf;            /* f32 [n,H,W]   phase A output                                   */
   const uint8_t* label;           /* u8  [n,H,W]                                                    */
@@ -321,7 +324,7 @@ typedef struct HiastWindowEmit {
   double         cp_gamma;
   int32_t        n_images, H, W, C, group_size, reserved;
 } HiastWindowEmit;
-HIAST_API int hiast_ias_emit_window(const HiastWindowEmit* args, void* stream);
+HIAST_API int hiast_ias_emit_window(const HiastWindowEmit* args, void* stream, void* copy_stream);
 
 /* Asynchronous file writer (:43-46 without the interpreter).  submit records an event on `stream` (behind
  * hiast_ias_emit_window's copies) and returns a ticket > 0 at once; a dispatcher thread sleeps on the event, then

@@ -28,14 +28,18 @@ def hard_classes(class_value, selected_num_classes, ignored_classes=None):
 
 
 def class_probs(class_value, nan_to_zero=False):
-    """(1 - v)^2 / sum  (:29-34); float64."""
-    v = np.asarray(class_value, dtype=np.float64)
+    """(1 - v)^2 / sum  (:29-34).  The reference computes this with TORCH float64 ops (``torch.tensor(class_value)``,
+    ``**``, ``torch.sum``), whose summation order need not be numpy's; a last-ulp difference in p can change a draw of
+    ``np.random.choice``, so the same ops are used here (pinned by tests/golden/copy_paste_probs.npz, 20 seeds)."""
+    import torch
+    probs = torch.tensor(np.asarray(class_value, dtype=np.float64))
     if nan_to_zero:
-        finite = np.isfinite(v)
-        p = np.where(finite, (1 - np.where(finite, v, 0.0)) ** 2, 0.0)
+        finite = torch.isfinite(probs)
+        probs = torch.where(finite, (1 - torch.where(finite, probs, torch.zeros_like(probs))) ** 2, torch.zeros_like(probs))
     else:
-        p = (1 - v) ** 2
-    return p / np.sum(p)
+        probs = (1 - probs) ** 2
+    probs = probs / torch.sum(probs)
+    return probs.numpy()
 
 
 def random_select(num_classes, probs, selected):

@@ -42,6 +42,7 @@ import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))       # the repo root (hiast_b200.config for cli_config_fixture)
 import golden_inputs as gi  # noqa: E402
 
 REF = '/root/reference/code'

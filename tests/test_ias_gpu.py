@@ -252,6 +252,43 @@ def test_full_resolution_properties():
     assert torch.equal(hist2, hist_raw) and torch.equal(conf2, conf) and torch.equal(label2, label)
 
 
+@pytest.mark.parametrize('dist', ['D1_diffuse', 'D2_peaked'])
+def test_full_resolution_engine_vs_oracle(dist):
+    """BASELINE.json configs[1] at FULL resolution against the oracle end to end (VERDICT r1 weak #1 i):
+    8 maps of 19x1024x2048, batch 2, through IASEngine.process; the oracle (the reference's loop body, oracle/ias.py) is fed
+    by torch's CUDA softmax exactly as the reference is (:192-193).  Thresholds of every group, pseudo-labels of every
+    pixel, per-image counts and class totals bit-exact; class_mean_probs 1e-6."""
+    from hiast_b200.ias_engine import IASEngine
+    C, H, W, B, N = 19, 1024, 2048, 2, 8
+    g = torch.Generator(device='cuda').manual_seed(1234)
+    if dist == 'D1_diffuse':
+        logits = torch.randn(N, C, H, W, generator=g, device='cuda') * 3
+    else:
+        low = torch.randn(N, C, 32, 64, generator=g, device='cuda') * 4
+        logits = torch.nn.functional.interpolate(low, size=(H, W), mode='bilinear', align_corners=True)
+        logits += torch.randn(N, C, H, W, generator=g, device='cuda') * 0.5
+    eng = IASEngine(C, H, W, B, 0.5, 0.9, 8.0, 0.99, N)
+    plbl, counts, thr_groups = eng.process(logits)
+    oracle = oias.IASOracle(C, 0.5, 0.9, 8.0, 0.99)
+    oracle.run([(logits[i:i + B], ['img_%d.png' % k for k in range(i, i + B)]) for i in range(0, N, B)])
+    assert eng.check_errors()
+    assert np.array_equal(thr_groups.cpu().numpy(), np.stack(oracle.threshold_trace))
+    assert np.array_equal(eng.thr_state.cpu().numpy(), oracle.class_threshold)
+    got = plbl.cpu().numpy()
+    for i in range(N):
+        assert np.array_equal(got[i], oracle.labels[i]), i
+    want_counts = np.zeros((N, C), dtype=np.int64)
+    for i, row in enumerate(oracle.sample_stats):
+        for k, v in row.items():
+            if k != 'file':
+                want_counts[i, k] = v
+    assert np.array_equal(counts.cpu().numpy(), want_counts)
+    assert np.array_equal(counts.sum(0).cpu().numpy(), oracle.statics_class)
+    np.testing.assert_allclose(eng.mean_state.cpu().numpy(), oracle.class_mean_probs, rtol=1e-6)
+    ignored = float((got == 255).mean())
+    assert 0.05 < ignored < 0.98, ignored                         # the case is not degenerate
+
+
 @pytest.mark.parametrize('mode', [56, 80, 81, 83])
 def test_full_resolution_hist_variants_match_plain_red(mode):
     if mode not in modes():

@@ -223,3 +223,47 @@ def test_ce_general_oracle_equals_reference_fixture():
             val.backward()
             assert val.item() == gold['%s_%s' % (key, case)], (key, case)
             assert np.array_equal(zz.grad.numpy(), gold['%s_%s_grad' % (key, case)]), (key, case)
+
+
+def test_copy_paste_class_probs_and_draws_on_20_seeds():
+    """the sampling probabilities (torch float64 arithmetic, preprocessor.py:29-34) and the class
+    draws of random_select (:70-77) of the unmodified reference on 20 random class-value vectors, bit for bit -- for the
+    oracle and for the product's host logic (hiast_b200.preprocessor.CopyPaste, no GPU involved)."""
+    from types import SimpleNamespace
+    from hiast_b200.preprocessor import CopyPaste, DonorSampler
+    gold = np.load(os.path.join(GOLD, 'copy_paste_probs.npz'))
+    for seed in range(int(gold['n_seeds'])):
+        value, want_p, want_picks, hard = (gold['%s_%d' % (k, seed)] for k in ('value', 'probs', 'picks', 'hard'))
+        C = len(value)
+        assert np.array_equal(ocp.class_probs(value), want_p)
+        cp = CopyPaste.__new__(CopyPaste)
+        cp.cfg = SimpleNamespace(dataset=SimpleNamespace(num_classes=C))
+        cp.class_value = value.copy()
+        cp.class_probs = cp.calculate_class_probs()
+        assert np.array_equal(cp.class_probs, want_p), seed
+        np.random.seed(seed)
+        assert [int(cp.random_select(hard)) for _ in range(len(want_picks))] == want_picks.tolist()
+        np.random.seed(seed)
+        assert [int(ocp.random_select(C, want_p, hard)) for _ in range(len(want_picks))] == want_picks.tolist()
+
+
+def test_batch_donor_sampler_draws_the_reference_donors():
+    """DonorSampler.draw consumes np.random exactly like consecutive run_original calls: the donors of the reference fixture."""
+    from types import SimpleNamespace
+    from hiast_b200.preprocessor import CopyPaste, DonorSampler
+    spec = gi.COPY_PASTE_SPEC
+    ds = gi.CopyPasteDataset(spec)
+    cfg = SimpleNamespace(dataset=SimpleNamespace(source=SimpleNamespace(type='GTAV'), num_classes=spec['C']),
+                          preprocessor=SimpleNamespace(copy_paste=SimpleNamespace(selected_num_classes=spec['selected'], mode='original')))
+    cp = CopyPaste(cfg, ds, gi.copy_paste_class_value(spec), device='cpu')
+    np.random.seed(spec['seed'])
+    got = DonorSampler(cp).draw(spec['n_run'])
+    np.random.seed(spec['seed'])
+    want = []
+    for i in range(spec['n_run']):
+        img, lbl, _ = ds.load_data(i)
+        _, _, _, donors = ocp.run_original(img, lbl, cp.hard_classes, cp.class_probs, ds.get_samples_with_class(),
+                                           lambda name: ds.load_data(ds.get_file_to_idx(name))[:2], spec['C'])
+        assert len(donors) == 1                            # the loop stops after its first donor (SURVEY A.4)
+        want.append(ds.get_file_to_idx(donors[0]))
+    assert got == want
