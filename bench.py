@@ -16,8 +16,8 @@ of 64 synthetic maps (10.2 GB: every step streams 80x the L2, no flush needed).
                 (pinned) logits: H2D of every batch and D2H of every label map inside the timed region.
 * ``roofline``  phase A (the dominant kernel): algorithmic bytes (77 B/px) / its mean launch time, measured
                 with CUDA events inside the timed steps, against MEASURED_PEAKS.json's HBM copy bandwidth.
-* ``cpu_baseline`` / ``--impl reference``: the oracle port of the reference's CPU path (faithful op sequence,
-                oracle/ias.py) on the host cores, on a bounded sample of the same workload.
+* ``cpu_baseline`` / ``--impl reference``: the UNMODIFIED reference (oracle/_ref/code, ``IASPseudoGenerator.run``) on the host
+                cores, on a bounded sample of the same workload; the oracle port only if that copy is absent.
 
 Multi-GPU (torchrun, one rank per GPU): windows are striped over ranks and the 19-double threshold state is
 handed rank to rank with NCCL send/recv (hiast_b200/sharded.py); weak scaling, per-GPU work fixed.
@@ -92,24 +92,39 @@ def synth_logits_cpu(n, seed=1234):
     return out
 
 
-def run_cpu_port(n_images, steps=1, warmup=0):
-    """The reference's CPU path (oracle port, faithful op sequence) on a bounded sample.  images/s."""
+def run_cpu_arm(n_images, steps=1, warmup=0):
+    """The reference's CPU path on a bounded sample: images/s, best step seconds, torch threads, kind.
+
+    kind 'reference': the UNMODIFIED ``IASPseudoGenerator.run`` (workflows/pseudo_label_generator.py:181-213) from
+    ``oracle/_ref/code`` (the hot-path files copied there by ``__graft_entry__.build()`` in the build container; git-ignored,
+    travels with the snapshot) through the import shim of ``oracle/ref.py``.  kind 'port': the oracle's faithful restatement
+    (same op sequence, pinned bit for bit against the reference's outputs) when that copy is absent."""
     import torch
     from oracle import ias as oias
+    from oracle import ref as oref
     # torchrun exports OMP_NUM_THREADS=1; only one rank runs this leg, so it may use every host core
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     logits = synth_logits_cpu(n_images)
     batches = [(logits[i:i + GROUP], ['img_%05d.png' % (i + j) for j in range(min(GROUP, n_images - i))])
                for i in range(0, n_images, GROUP)]
+    kind = 'reference' if oref.available() else 'port'
     best = None
     for it in range(warmup + steps):
-        o = oias.IASOracle(C, ALPHA, BETA, GAMMA, CP_GAMMA, faithful=True, keep_labels=False)
         t0 = time.perf_counter()
-        o.run(batches)
+        if kind == 'reference':
+            oref.run_ias(batches, C, ALPHA, BETA, GAMMA, CP_GAMMA, keep_labels=False)
+        else:
+            oias.IASOracle(C, ALPHA, BETA, GAMMA, CP_GAMMA, faithful=True, keep_labels=False).run(batches)
         dt = time.perf_counter() - t0
         if it >= warmup:
             best = dt if best is None else min(best, dt)
-    return n_images / best, best, torch.get_num_threads()
+    return n_images / best, best, torch.get_num_threads(), kind
+
+
+CPU_NOTE = {'reference': 'the unmodified reference (oracle/_ref/code: workflows/pseudo_label_generator.py IASPseudoGenerator.run) on the '
+                         'host cores, identity model on synthetic logits, cv2.imwrite stubbed',
+            'port': 'oracle/_ref is absent on this box: the oracle port (oracle/ias.py, faithful op sequence, pinned bit for bit '
+                    'against the reference) on the host cores'}
 
 
 def reference_arm(args):
@@ -119,16 +134,15 @@ def reference_arm(args):
     n = args.cpu_images
     steps = max(1, min(args.steps, 2))
     warm = max(0, min(args.warmup, 1))     # a CPU step takes seconds: at most one untimed pass
-    value, secs, threads = run_cpu_port(n, steps=steps, warmup=warm)
+    value, secs, threads, kind = run_cpu_arm(n, steps=steps, warmup=warm)
     sample = '%d maps of 19x1024x2048, batch 2 (%d groups), per step; PNG write excluded' % (n, (n + 1) // 2)
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': steps,
         'warmup': warm, 'ms_per_step': secs * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': 'GTA5->Cityscapes IAS pseudo-labelling, 19x1024x2048 logit maps, batch 2 (configs[1])',
-                   'note': 'reference is pure Python/numpy and cannot travel to the GPU box; this is the oracle port '
-                           '(oracle/ias.py, faithful op sequence) on the host cores'},
-        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample,
+                   'note': CPU_NOTE[kind]},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': kind, 'sample': sample,
                          'host_cpus': os.cpu_count(),
                          'note': 'only softmax/max use all torch threads; the numpy/Python part is single-threaded '
                                  'by construction, as in the reference'},
@@ -344,9 +358,9 @@ def gpu_arm(args):
         if parity is not None:
             line['parity'] = parity
         if world == 1 and not args.no_cpu_baseline:
-            v, secs, threads = run_cpu_port(args.cpu_images)
+            v, secs, threads, kind = run_cpu_arm(args.cpu_images)
             line['cpu_baseline'] = {
-                'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'host_cpus': os.cpu_count(),
+                'value': v, 'unit': UNIT, 'cores': threads, 'kind': kind, 'host_cpus': os.cpu_count(), 'note': CPU_NOTE[kind],
                 'sample': '%d maps of 19x1024x2048, batch 2 (%.1f s of host work); PNG write excluded' % (args.cpu_images, secs)}
         print(json.dumps(line), flush=True)
     if parity is not None and not (parity['thr_equal'] and parity['plbl_sha_equal']):
@@ -552,9 +566,23 @@ def measure_e2e(args, device, rank, world, barrier):
         def save_data(self):
             pass
 
-    def run_png(n_images, mode):
+    # Where the files go.  The container's /tmp is an ext4 image on a throttled virtual disk (tools/fs_probe.py on the B200 boxes:
+    # 5-10 k files/s from one process, erratic; 3.8 k images/s end to end once the page cache is dirty) -- that would time the VM's
+    # disk, not this pipeline.  tmpfs (/dev/shm: 60 k files/s from one process) stands in for a local NVMe scratch directory; the
+    # same call on the container disk is reported beside it on a short sample.
+    def files_root(kind):
+        if kind == 'fast' and os.path.isdir('/dev/shm') and os.access('/dev/shm', os.W_OK):
+            try:
+                st = os.statvfs('/dev/shm')
+                if st.f_bavail * st.f_frsize > 4 << 30:
+                    return '/dev/shm'
+            except OSError:
+                pass
+        return tempfile.gettempdir()
+
+    def run_png(n_images, mode, where='fast'):
         """Seconds of construct + run() (files on disk when it returns), number of files, bytes on disk."""
-        d = tempfile.mkdtemp()
+        d = tempfile.mkdtemp(dir=files_root(where))
         try:
             cls = GenPng if mode == 'device' else GenPngHost
             torch.cuda.synchronize()
@@ -580,8 +608,15 @@ def measure_e2e(args, device, rank, world, barrier):
     assert n_files == steps_lr * WINDOW
     png = {'value': steps_lr * WINDOW * world / secs, 'unit': UNIT, 'steps': steps_lr, 'files_written': n_files,
            'mean_file_bytes': n_bytes / max(1, n_files), 'd2h_bytes_per_step': n_bytes / steps_lr + WINDOW * C * 8,
-           'files_dir': tempfile.gettempdir(),
+           'files_dir': files_root('fast'),
            'api': 'same call with the PNG files written (device encoder, native writer pool with %d POSIX writers per rank, completion deferred by three windows)' % IASPseudoGenerator._default_workers()}
+    secs_disk = run_png(8 * WINDOW, 'device', where='disk')[0]
+    if world > 1:
+        t = torch.tensor([secs_disk], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        secs_disk = float(t[0])
+    png['on_container_disk'] = {'value': 8 * WINDOW * world / secs_disk, 'steps': 8, 'files_dir': files_root('disk'),
+                                'note': 'ext4 image on the VM\'s virtual disk: file-system bound and erratic (tools/fs_probe.py)'}
     if rank == 0:                                   # the reference's writer (cv2.imwrite on host label maps) beside it
         n_host_png = WINDOW
         png['host_cv2_imwrite_images_per_s'] = n_host_png / run_png(n_host_png, 'host')[0]

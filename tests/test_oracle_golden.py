@@ -267,3 +267,22 @@ def test_batch_donor_sampler_draws_the_reference_donors():
         assert len(donors) == 1                            # the loop stops after its first donor
         want.append(ds.get_file_to_idx(donors[0]))
     assert got == want
+
+
+def test_travelling_reference_copy_runs_and_equals_the_port():
+    """oracle/_ref/code (the reference's hot-path files, copied by __graft_entry__.build() where /root/reference is mounted)
+    through oracle/ref.py's shim: the unmodified IASPseudoGenerator.run equals the oracle port on the same batches -- the
+    CPU arm of bench.py (kind 'reference') and its fallback (kind 'port') are the same computation."""
+    from oracle import ref as oref
+    if oref.available() is None:
+        pytest.skip('no reference copy on this box')
+    spec = gi.IAS_SPECS['ias_small']
+    batches = gi.ias_batches(spec)
+    gen = oref.run_ias(batches, spec['C'], spec['alpha'], spec['beta'], spec['gamma'], spec['cp_gamma'])
+    o = oias.IASOracle(spec['C'], spec['alpha'], spec['beta'], spec['gamma'], spec['cp_gamma'], faithful=True)
+    o.run(batches)
+    assert np.array_equal(gen.class_threshold, o.class_threshold)
+    assert np.array_equal(gen.statics_class, o.statics_class)
+    assert np.array_equal(gen.class_mean_probs, o.class_mean_probs)
+    assert gen.sample_stats == o.sample_stats
+    assert all(np.array_equal(a, b) for a, b in zip(gen.captured, o.labels))
