@@ -53,6 +53,7 @@ def parse_args():
     ap.add_argument('--dist', default='mixed', choices=['mixed', 'diffuse', 'peaked'])
     ap.add_argument('--e2e-steps', type=int, default=4)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-extra', action='store_true', help='skip the legs for BASELINE configs[2], [3], [4]')
     ap.add_argument('--cpu-images', type=int, default=8)
     return ap.parse_args()
 
@@ -330,6 +331,12 @@ def gpu_arm(args):
     # ---- e2e through the reference-facing API with host buffers (every rank its own replica of the call)
     e2e = measure_e2e(args, device, rank, world, barrier)
 
+    extra = None
+    if not args.no_extra:
+        del pool
+        torch.cuda.empty_cache()
+        extra = measure_extra(device, rank, world, barrier)
+
     if rank == 0:
         peak, peak_src = peaks()
         achieved = ALG_BYTES_PER_IMAGE * WINDOW / (a_ms / 1e3) / 1e9
@@ -357,6 +364,8 @@ def gpu_arm(args):
         }
         if parity is not None:
             line['parity'] = parity
+        if extra is not None:
+            line['extra'] = extra
         if world == 1 and not args.no_cpu_baseline:
             v, secs, threads, kind = run_cpu_arm(args.cpu_images)
             line['cpu_baseline'] = {
@@ -439,6 +448,31 @@ def h2d_ceiling(host, device, world, barrier, seconds=0.25):
         dist.all_reduce(t)
     barrier()
     return float(t[0])
+
+
+def measure_extra(device, rank, world, barrier):
+    """The other BASELINE.json configs (tools/bench_extra.py).  Kernel legs on rank 0 at N = 1 only; the sharded jobs
+    (configs[3], configs[4]) on every rank.  A leg that fails is reported as its error, the headline stands."""
+    import traceback
+    from tools import bench_extra as bx
+    peak, _ = peaks()
+    out = {}
+
+    def leg(name, fn, *a, **k):
+        try:
+            out[name] = fn(*a, **k)
+        except Exception as exc:                          # noqa: BLE001
+            out[name] = {'error': '%s: %s' % (type(exc).__name__, exc), 'trace': traceback.format_exc()[-600:]}
+            if world > 1:
+                raise                                     # a rank that drops out of a collective would hang the others
+
+    if world == 1:
+        leg('configs2_loss_fwd_bwd', bx.loss_leg, device, peak)
+        leg('copy_paste_kernel', bx.copy_paste_leg, device, peak)
+        leg('confusion_kernel', bx.confusion_leg, device, peak)
+    leg('configs3_synthia_ias_copy_paste', bx.synthia_leg, device, rank, world, barrier)
+    leg('configs4_full_round', bx.full_round_leg, device, rank, world, barrier)
+    return out
 
 
 def measure_e2e(args, device, rank, world, barrier):

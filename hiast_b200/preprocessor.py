@@ -150,8 +150,9 @@ class DonorSampler:
     ``preprocessor.py:79-122``): per image one class draw (``random_select``, :93), one file draw (:95), one ``load_data``
     (:97).  On the device the paste is one launch per batch, so the donors of a batch are drawn up front -- the same two
     ``np.random`` calls per image in image order, hence the same donors as a sequential reference run with the same seed --
-    loaded on a small thread pool, staged in pinned memory and uploaded with one copy per tensor; donors that repeat within
-    the batch are loaded and uploaded once, and the ``cache`` most recently used donors stay on the device.
+    loaded on a small thread pool, staged in pinned memory and uploaded into a device SLAB of ``cache`` donor slots; the
+    kernel reads donor i of the batch from slot ``donor_index[i]``.  A donor that repeats (within the batch or across
+    batches) is loaded and uploaded once; the least recently used slots are recycled.
 
     (``run_original``'s ``for _ in range(3)`` loop always stops after its first donor: the first pass marks every hard class
     as existing regardless of the donor's content, SURVEY.md A.4 -- one donor per image is the reference's behaviour.)"""
@@ -160,10 +161,11 @@ class DonorSampler:
         from concurrent.futures import ThreadPoolExecutor
         self.cp = copy_paste
         self.cache = int(cache)
-        self._lru = {}                                # dataset index -> (img u8 [H,W,3], lbl u8 [H,W]) on the device
+        self._slot_of = {}                            # dataset index -> slab slot
+        self._used = {}                               # slab slot -> last use tick
         self._tick = 0
         self._pool = ThreadPoolExecutor(max_workers=max(1, int(workers)))
-        self._pins = None
+        self._slab = self._pins = self._uploaded = None
 
     def draw(self, n):
         """Dataset indices of the donors of n images in order: the RNG calls of preprocessor.py:93-96, nothing else."""
@@ -182,34 +184,46 @@ class DonorSampler:
         return np.ascontiguousarray(img_, dtype=np.uint8), np.ascontiguousarray(lbl_, dtype=np.uint8)
 
     def sample(self, n, hw):
-        """(donor_imgs u8 [m,H,W,3], donor_lbls u8 [m,H,W], donor_index i32 [n]) on the device for a batch of n images."""
+        """(donor slab imgs u8 [S,H,W,3], slab lbls u8 [S,H,W], donor_index i32 [n]) on the device for a batch of n images."""
         dev = self.cp.device
+        h, w = int(hw[0]), int(hw[1])
         idxs = self.draw(n)
         distinct = list(dict.fromkeys(idxs))
-        missing = [i for i in distinct if i not in self._lru]
+        slots = max(self.cache, len(distinct))
+        if self._slab is None or tuple(self._slab[1].shape[1:]) != (h, w) or self._slab[1].shape[0] < slots:
+            self._slab = (torch.empty((slots, h, w, 3), dtype=torch.uint8, device=dev),
+                          torch.empty((slots, h, w), dtype=torch.uint8, device=dev))
+            self._slot_of, self._used = {}, {}
+        missing = [i for i in distinct if i not in self._slot_of]
         if missing:
-            loaded = list(self._pool.map(lambda i: self._load(i, hw), missing))
-            m, (h, w) = len(missing), hw
-            if self._pins is None or self._pins[0].shape[0] < m or tuple(self._pins[0].shape[1:3]) != (h, w):
-                self._pins = (torch.empty((max(m, n), h, w, 3), dtype=torch.uint8).pin_memory(),
-                              torch.empty((max(m, n), h, w), dtype=torch.uint8).pin_memory())
-            else:
-                torch.cuda.current_stream(dev).synchronize()        # the previous batch's upload still reads the pins
-            for k, (img_, lbl_) in enumerate(loaded):
+            total = self._slab[1].shape[0]
+            free = [s for s in range(total) if s not in self._used]
+            if len(free) < len(missing):              # recycle the least recently used slots that this batch does not need
+                keep = {self._slot_of[i] for i in distinct if i in self._slot_of}
+                victims = sorted((t, s) for s, t in self._used.items() if s not in keep)[:len(missing) - len(free)]
+                gone = {s for _, s in victims}
+                self._slot_of = {i: s for i, s in self._slot_of.items() if s not in gone}
+                for s in gone:
+                    del self._used[s]
+                free += sorted(gone)
+            loaded = list(self._pool.map(lambda i: self._load(i, (h, w)), missing))
+            m = len(missing)
+            if self._uploaded is not None:
+                self._uploaded.synchronize()          # the previous batch's uploads still read the pinned staging buffers
+            if self._pins is None or self._pins[1].shape[0] < m or tuple(self._pins[1].shape[1:]) != (h, w):
+                self._pins = (torch.empty((max(m, 8), h, w, 3), dtype=torch.uint8).pin_memory(),
+                              torch.empty((max(m, 8), h, w), dtype=torch.uint8).pin_memory())
+            for k, (i, (img_, lbl_)) in enumerate(zip(missing, loaded)):
+                s = free[k]
                 self._pins[0][k].copy_(torch.from_numpy(img_))
                 self._pins[1][k].copy_(torch.from_numpy(lbl_))
-            d_img = self._pins[0][:m].to(dev, non_blocking=True)
-            d_lbl = self._pins[1][:m].to(dev, non_blocking=True)
-            for k, i in enumerate(missing):
-                self._lru[i] = [d_img[k], d_lbl[k], 0]
+                self._slab[0][s].copy_(self._pins[0][k], non_blocking=True)
+                self._slab[1][s].copy_(self._pins[1][k], non_blocking=True)
+                self._slot_of[i] = s
+            self._uploaded = torch.cuda.Event()
+            self._uploaded.record(torch.cuda.current_stream(dev))
+        self._tick += 1
         for i in distinct:
-            self._tick += 1
-            self._lru[i][2] = self._tick
-        pos = {i: k for k, i in enumerate(distinct)}
-        donor_imgs = torch.stack([self._lru[i][0] for i in distinct])
-        donor_lbls = torch.stack([self._lru[i][1] for i in distinct])
-        donor_index = torch.tensor([pos[i] for i in idxs], dtype=torch.int32).to(dev, non_blocking=True)
-        if len(self._lru) > self.cache:
-            for i, _ in sorted(self._lru.items(), key=lambda kv: kv[1][2])[:len(self._lru) - self.cache]:
-                del self._lru[i]
-        return donor_imgs, donor_lbls, donor_index
+            self._used[self._slot_of[i]] = self._tick
+        donor_index = torch.tensor([self._slot_of[i] for i in idxs], dtype=torch.int32).to(dev, non_blocking=True)
+        return self._slab[0], self._slab[1], donor_index

@@ -351,3 +351,96 @@ def test_h2d_prefetch_thread_does_not_change_results(prefetch, tmp_path):
                                 save_dir=str(tmp_path / 'run2' / 'pseudo_labels'), window_batches=2, prefetch=prefetch)
     with pytest.raises(OSError):
         gen2.run()
+
+
+def test_cli_script_end_to_end(tmp_path, monkeypatch):
+    """the reference's script surface (generate_pseudo_labels.py:8-48) on a temp yaml -- six flags, yaml merge,
+    ONE-argument PSEUDO_POLICY[type](cfg) resolving the model through MODEL and the target set through DATASET -- and the
+    files of pseudo_label_generator.py:43-62 on disk with the oracle's contents."""
+    import cv2
+    import hiast_b200
+    from hiast_b200 import cli
+    from hiast_b200.registry import DATASET, MODEL
+    hiast_b200.register_all()
+    C, H, W, N = 7, 24, 40, 9
+
+    class ToySegmentor(torch.nn.Module):
+        def __init__(self, cfg):
+            super().__init__()
+            self.head = torch.nn.Conv2d(3, cfg.dataset.num_classes, 1)
+
+        def forward(self, x):
+            return {'logits': self.head(x) * 6}
+
+    class ToyTarget(torch.utils.data.Dataset):
+        def __init__(self, cfg, json_path, image_dir, aug_type=None, num_classes=None):
+            g = torch.Generator().manual_seed(3)
+            self.imgs = torch.randn(N, 3, H, W, generator=g)
+
+        def __len__(self):
+            return N
+
+        def __getitem__(self, i):
+            return {'images': self.imgs[i], 'image_paths': 'city/img_%02d.png' % i}
+
+    monkeypatch.setitem(MODEL, 'ToySegmentor', ToySegmentor)
+    monkeypatch.setitem(DATASET, 'ToyTarget', ToyTarget)
+    torch.manual_seed(11)
+    ref_model = ToySegmentor(SimpleNamespace(dataset=SimpleNamespace(num_classes=C)))
+    ckpt = str(tmp_path / 'ckpt.pth')
+    torch.save(ref_model.state_dict(), ckpt)
+    cfg_file = tmp_path / 'sl.yaml'
+    cfg_file.write_text("model:\n  type: 'ToySegmentor'\ndataset:\n  num_classes: %d\n  num_workers: 0\n  target:\n    type: 'ToyTarget'\n"
+                        "    json_path: 't.json'\n    image_dir: 't'\npseudo_policy:\n  batch_size: 2\n  resize_size: [ %d, %d ]\n"
+                        "  type: 'IAS'\n  ias:\n    alpha: 0.5\n    beta: 0.9\n    gamma: 8.0\n" % (C, H, W))
+    save_dir = str(tmp_path / 'run' / 'pseudo_labels')
+    torch.manual_seed(5)                                    # the reference's DataLoader shuffles (:36): pin the order
+    gen = cli.main(['--config_file', str(cfg_file), '--pseudo_resume_from', ckpt, '--pseudo_save_dir', save_dir])
+    files = sorted(os.listdir(save_dir))
+    assert files == ['img_%02d_pseudo_label.png' % i for i in range(N)]
+    # the same pass through the oracle, in the order the generator saw the images
+    order = [row['file'] for row in gen.sample_stats]
+    assert sorted(order) == ['city/img_%02d.png' % i for i in range(N)]
+    ds = ToyTarget(None, None, None)
+    idx = [int(p[-6:-4]) for p in order]
+    with torch.no_grad():
+        logits = ref_model.cuda()(ds.imgs[idx].cuda())['logits']
+    oracle = oias.IASOracle(C, 0.5, 0.9, 8.0, 0.99)
+    oracle.run([(logits[i:i + 2], order[i:i + 2]) for i in range(0, N, 2)])
+    assert np.array_equal(gen.class_threshold, oracle.class_threshold)
+    assert gen.sample_stats == oracle.sample_stats
+    for i, p in enumerate(order):
+        png = cv2.imread(os.path.join(save_dir, os.path.splitext(os.path.basename(p))[0] + '_pseudo_label.png'), cv2.IMREAD_UNCHANGED)
+        assert np.array_equal(png, oracle.labels[i])
+    root = os.path.join(save_dir, '..')
+    assert np.array_equal(np.load(os.path.join(root, 'class_threshold.npy')), oracle.class_threshold)
+    assert np.array_equal(np.load(os.path.join(root, 'statics_class.npy')), oracle.statics_class)
+    np.testing.assert_allclose(np.load(os.path.join(root, 'class_mean_probabilities.npy')), oracle.class_mean_probs, rtol=1e-6)
+    assert json.load(open(os.path.join(root, 'samples_with_class.json'))) == json.loads(json.dumps(oracle.samples_class))
+    assert json.load(open(os.path.join(root, 'sample_class_stats.json'))) == json.loads(json.dumps(oracle.sample_stats))
+
+
+def test_unsupported_lowres_shape_falls_back_to_interpolate(tmp_path):
+    """the fused up-sampling kernel covers C in {16, 19} and W % 4 == 0; any other stride-8 input (here the
+    reference's 9-class Cityscapes->Oxford setting, odd width) takes F.interpolate + the generic phase A, same results."""
+    import hiast_b200
+    hiast_b200.register_all()
+    from hiast_b200 import PSEUDO_POLICY
+    C, H, W, N, B = 9, 40, 66, 5, 2
+    g = torch.Generator().manual_seed(8)
+    lrs = [torch.randn(min(B, N - i), C, 6, 9, generator=g) * 4 for i in range(0, N, B)]
+    paths = [['im%d.png' % (i + k) for k in range(len(lrs[i // B]))] for i in range(0, N, B)]
+
+    class LowRes:
+        def __call__(self, x):
+            return {'logits_lr': x, 'size': (H, W)}
+
+    spec = dict(C=C, B=B, alpha=0.5, beta=0.9, gamma=8.0, cp_gamma=0.99)
+    gen = PSEUDO_POLICY['IAS'](make_cfg(spec), model=LowRes(), loader=[{'images': a, 'image_paths': p} for a, p in zip(lrs, paths)],
+                               dataset_len=N, save_dir=str(tmp_path / 'r' / 'pl'), window_batches=2)
+    gen.run()
+    full = [torch.nn.functional.interpolate(a.cuda(), size=(H, W), mode='bilinear', align_corners=True) for a in lrs]
+    oracle = oias.IASOracle(C, 0.5, 0.9, 8.0, 0.99)
+    oracle.run(list(zip(full, paths)))
+    assert np.array_equal(gen.class_threshold, oracle.class_threshold)
+    assert gen.sample_stats == oracle.sample_stats
