@@ -69,9 +69,10 @@ class ShardedIAS:
         main stream    A(j)                        C(j-2)   A(j+1)                     C(j-1) ...
         chain stream          [recv] B(j-1) [send]                 [recv] B(j) [send]
 
-    The chain of window j-1 is queued behind A(j) on a high-priority side stream, so it never competes with a running
-    phase A for SMs and runs in the shadow of phase C of window j-2; the main stream waits for it only in front of
-    C(j-1), one whole phase A later.  With two slots C(j-1) follows B(j-1) directly (the round-1 schedule)."""
+    The chain of window j-1 is queued behind A(j) on a high-priority side stream and A(j+1) waits for it, so it never
+    competes with a running phase A for SMs and runs in the shadow of phase C of window j-2.  On R ranks the token needs
+    r hops to reach rank r: the ranks fall into a stagger of one hop each once, after which every token is already there
+    when it is needed.  With two slots C(j-1) follows B(j-1) directly (the round-1 schedule)."""
 
     def __init__(self, engine, window_size, n_images_total, rank=None, world_size=None, process_group=None):
         if window_size % engine.B:
@@ -140,6 +141,10 @@ class ShardedIAS:
             if self.cuda:
                 self.ev_a[j % self.n_slots].record(main)
             advance(j + 1, final=False)
+            if self.cuda and b_done:
+                # the next phase A waits for the chain just queued: the ranks fall into a stagger of one hop each ONCE and
+                # the receive / scan kernels never share the SMs with a phase A (see _WindowPipeline._close)
+                main.wait_event(self.ev_b[(b_done - 1) % self.n_slots])
         advance(len(wins), final=True)
         return self.finish_state()
 
