@@ -614,6 +614,8 @@ def measure_e2e(args, device, rank, world, barrier):
                 pass
         return tempfile.gettempdir()
 
+    last_trace = {}
+
     def run_png(n_images, mode, where='fast'):
         """Seconds of construct + run() (files on disk when it returns), number of files, bytes on disk."""
         d = tempfile.mkdtemp(dir=files_root(where))
@@ -627,6 +629,8 @@ def measure_e2e(args, device, rank, world, barrier):
             gen.run()
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
+            last_trace.clear()
+            last_trace.update(getattr(gen, 'pipeline_trace', {}))
             files = os.listdir(os.path.join(d, 'pl'))
             return dt, len(files), sum(os.path.getsize(os.path.join(d, 'pl', f)) for f in files)
         finally:
@@ -640,9 +644,13 @@ def measure_e2e(args, device, rank, world, barrier):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         secs = float(t[0])
     assert n_files == steps_lr * WINDOW
+    tr = dict(last_trace)
+    host_trace = {'rank0_seconds': {k: round(v, 4) for k, v in tr.items() if k in ('wait_completion', 'close', 'total')},
+                  'note': 'host time of rank 0 inside run(): blocked on a window\'s completion / closing windows (launches, token '
+                          'calls, emit) / total between the first close and the end'}
     png = {'value': steps_lr * WINDOW * world / secs, 'unit': UNIT, 'steps': steps_lr, 'files_written': n_files,
            'mean_file_bytes': n_bytes / max(1, n_files), 'd2h_bytes_per_step': n_bytes / steps_lr + WINDOW * C * 8,
-           'files_dir': files_root('fast'),
+           'files_dir': files_root('fast'), 'host_trace': host_trace,
            'api': 'same call with the PNG files written (device encoder, native writer pool with %d POSIX writers per rank, completion deferred by three windows)' % IASPseudoGenerator._default_workers()}
     secs_disk = run_png(8 * WINDOW, 'device', where='disk')[0]
     if world > 1:

@@ -538,12 +538,21 @@ __global__ void __launch_bounds__(kThreadsL, 2) k_loss_fwd_pk(LossArgs a, Partia
 
 template <int C>
 __global__ void __launch_bounds__(kThreadsL, 2) k_loss_bwd_pk(LossArgs a, const float* __restrict__ scales,
-                                                              float* __restrict__ grad) {
+                                                              float* __restrict__ grad, const float* __restrict__ scales_used) {
   extern __shared__ __align__(128) float2 s_loss_stage[];
   const LossStage<C> st(s_loss_stage, a);
   const long long total = static_cast<long long>(a.B) * st.HW2;
   const long long stride = static_cast<long long>(gridDim.x) * kThreadsL;
   const float sc[4] = {scales[0], scales[1], scales[2], scales[3]};
+  if (scales_used) {
+    // `grad` already holds the gradient the one-pass kernel wrote for the scales it ASSUMED: nothing to do if the scales
+    // autograd actually delivered are the same bits (every thread takes the same branch; no barrier has been reached)
+    bool same = true;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (a.terms & (1 << k)) same = same && (__float_as_uint(sc[k]) == __float_as_uint(scales_used[k]));
+    if (same) return;
+  }
   float poison = 0.f;   // NaN iff an enabled scale is non-finite (empty region in the reference: every gradient is NaN)
 #pragma unroll
   for (int k = 0; k < 4; ++k)
@@ -631,6 +640,222 @@ __global__ void __launch_bounds__(kThreadsL, 2) k_loss_bwd_pk(LossArgs a, const 
     yb = nyb;
   }
   asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+}
+
+// ---- one-pass forward + backward ------------------------------------------------------------------
+// The two-pass design reads (z, t, plbl) twice: 160 + 236 = 396 B/px.  The CE / KLD / ENT divisors depend on the labels only
+// (n_conf, n_ign) and the SoftCE divisor is C * n_region unless some product is exactly zero, so after a label-only pre-pass
+// (1 or 8 B/px) ONE pass can write the gradient for an ASSUMED upstream gradient per term while it accumulates the forward
+// sums: 236 (+ labels) B/px.  autograd later delivers the real upstream gradients; hiast_st_loss_bwd_checked compares the
+// scales they imply with the ones used here and rewrites the gradient only when they differ (first step after a change of
+// the loss scale, an exactly-zero SoftCE product, weights changed): exact in every case, one pass in the steady state.
+struct LabelCounts {
+  unsigned long long n_conf, n_ign;
+};
+
+__global__ void __launch_bounds__(256) k_label_count(const void* __restrict__ plbl, int plbl_bytes, long long n,
+                                                     LabelCounts* __restrict__ out) {
+  long long ign = 0, tot = 0;
+  const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long nth = static_cast<long long>(gridDim.x) * blockDim.x;
+  if (plbl_bytes == 8 && (reinterpret_cast<uintptr_t>(plbl) % 16 == 0)) {
+    const longlong2* p = static_cast<const longlong2*>(plbl);
+    for (long long i = tid; i < n / 2; i += nth) {
+      const longlong2 v = __ldg(p + i);
+      ign += (v.x == HIAST_IGNORE_LABEL) + (v.y == HIAST_IGNORE_LABEL);
+      tot += 2;
+    }
+    if (tid == 0 && (n & 1)) {
+      ign += (static_cast<const long long*>(plbl)[n - 1] == HIAST_IGNORE_LABEL);
+      tot += 1;
+    }
+  } else if (plbl_bytes == 1 && (reinterpret_cast<uintptr_t>(plbl) % 16 == 0)) {
+    const uint4* p = static_cast<const uint4*>(plbl);
+    for (long long i = tid; i < n / 16; i += nth) {
+      const uint4 v = __ldg(p + i);
+      ign += __popc(__vcmpeq4(v.x, 0xffffffffu) & 0x01010101u) + __popc(__vcmpeq4(v.y, 0xffffffffu) & 0x01010101u) +
+             __popc(__vcmpeq4(v.z, 0xffffffffu) & 0x01010101u) + __popc(__vcmpeq4(v.w, 0xffffffffu) & 0x01010101u);
+      tot += 16;
+    }
+    for (long long i = (n / 16) * 16 + tid; i < n; i += nth) {
+      ign += (static_cast<const uint8_t*>(plbl)[i] == HIAST_IGNORE_LABEL);
+      tot += 1;
+    }
+  } else {
+    for (long long i = tid; i < n; i += nth) {
+      ign += (load_label(plbl, plbl_bytes, static_cast<size_t>(i)) == HIAST_IGNORE_LABEL);
+      tot += 1;
+    }
+  }
+  ign = warp_sum(ign);
+  tot = warp_sum(tot);
+  if (lane_id() == 0 && tot) {
+    atomicAdd(&out->n_ign, static_cast<unsigned long long>(ign));
+    atomicAdd(&out->n_conf, static_cast<unsigned long long>(tot - ign));
+  }
+}
+
+// scales of the gradient for upstream gradients gw[4]: float(double(gw) / divisor), the arithmetic of the autograd
+// Function (hiast_b200/losses.py) so that equal inputs give equal bits
+__device__ __forceinline__ void fused_scales(const LabelCounts& lc, const float* gw, int C, int region, float (&sc)[4]) {
+  const double nc = static_cast<double>(lc.n_conf), ni = static_cast<double>(lc.n_ign);
+  const double nr = region == HIAST_REGION_ALL ? nc + ni : (region == HIAST_REGION_IGNORED ? ni : nc);
+  sc[0] = static_cast<float>(static_cast<double>(gw[0]) / nc);
+  sc[1] = static_cast<float>(static_cast<double>(gw[1]) / (C * nc));
+  sc[2] = static_cast<float>(static_cast<double>(gw[2]) / (C * ni));
+  sc[3] = static_cast<float>(static_cast<double>(gw[3]) / (C * nr));
+}
+
+template <int C>
+__global__ void __launch_bounds__(kThreadsL, 2) k_loss_fused_pk(LossArgs a, const LabelCounts* __restrict__ lc,
+                                                                const float* __restrict__ grad_weights,
+                                                                float* __restrict__ scales_used, float* __restrict__ grad,
+                                                                Partial* __restrict__ partials) {
+  extern __shared__ __align__(128) float2 s_loss_stage[];
+  const LossStage<C> st(s_loss_stage, a);
+  const long long total = static_cast<long long>(a.B) * st.HW2;
+  const long long stride = static_cast<long long>(gridDim.x) * kThreadsL;
+  float sc[4];
+  {
+    const LabelCounts c0 = *lc;
+    const float gw[4] = {grad_weights[0], grad_weights[1], grad_weights[2], grad_weights[3]};
+    fused_scales(c0, gw, C, a.region, sc);
+    if (blockIdx.x == 0 && threadIdx.x < 4) scales_used[threadIdx.x] = sc[threadIdx.x];
+  }
+  float poison = 0.f;   // NaN iff an enabled scale is non-finite (empty region in the reference: every gradient is NaN)
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (a.terms & (1 << k)) poison += 0.f * sc[k];
+  const pk::u64 poison2 = pk::splat(poison);
+  const float s_ce = (a.terms & HIAST_TERM_CE) ? sc[0] : 0.f;
+  const float s_kld = (a.terms & HIAST_TERM_KLD) ? sc[1] : 0.f;
+  const float s_ent = (a.terms & HIAST_TERM_ENT) ? sc[2] : 0.f;
+  const float s_cst = (a.terms & HIAST_TERM_CST) ? sc[3] : 0.f;
+  const bool want_cst = (a.terms & HIAST_TERM_CST) != 0;
+  // the seven forward accumulators live in a per-thread column of shared memory, not in registers: the gradient pass needs
+  // every register the two-pass backward kernel uses (128 per thread at two CTAs per SM)
+  double* sacc = reinterpret_cast<double*>(s_loss_stage + 2 * C * kThreadsL) + threadIdx.x;
+#pragma unroll
+  for (int k = 0; k < 7; ++k) sacc[k * kThreadsL] = 0.0;
+  long long i = static_cast<long long>(blockIdx.x) * kThreadsL + threadIdx.x;
+  auto label_pos = [&](long long idx) {
+    const int bb = static_cast<int>(idx / st.HW2);
+    return static_cast<size_t>(bb) * a.HW + (idx - static_cast<long long>(bb) * st.HW2) * kPxL;
+  };
+  int ya = 0, yb = 0;
+  if (i < total) {
+    st.prefetch_z(i);
+    st.prefetch_t(i);
+    load_label_pair(a.plbl, a.plbl_bytes, label_pos(i), ya, yb);
+  }
+  for (; i < total; i += stride) {
+    st.wait_older();                       // z of this pair
+    float z[kPxL][C];
+    const float guard = st.load_z(z);
+    const bool more = i + stride < total;
+    int nya = 0, nyb = 0;
+    if (more && guard == guard) {
+      st.prefetch_z(i + stride);
+      load_label_pair(a.plbl, a.plbl_bytes, label_pos(i + stride), nya, nyb);
+    } else {
+      asm volatile("cp.async.commit_group;\n" ::: "memory");
+    }
+    const int b = static_cast<int>(i / st.HW2);
+    const int64_t p2i = i - static_cast<long long>(b) * st.HW2;
+    const bool iga = (ya == HIAST_IGNORE_LABEL), igb = (yb == HIAST_IGNORE_LABEL);
+    PairLS<C> ls;
+    ls.init(z[0], z[1]);
+    const bool csa = want_cst && in_region(a.region, iga);
+    const bool csb = want_cst && in_region(a.region, igb);
+    const pk::u64 A2 = pk::pack(iga ? 0.f : s_ce + s_kld, igb ? 0.f : s_ce + s_kld);
+    const pk::u64 K2 = pk::pack(iga ? 0.f : -(s_kld * (1.0f / C)), igb ? 0.f : -(s_kld * (1.0f / C)));
+    const pk::u64 NE2 = pk::pack(iga ? -s_ent : 0.f, igb ? -s_ent : 0.f);
+    const pk::u64 NC2 = pk::pack(csa ? -s_cst : 0.f, csb ? -s_cst : 0.f);
+    const float cea = iga ? 0.f : s_ce, ceb = igb ? 0.f : s_ce;
+    const pk::u64 ign_mask = lane_mask(iga, igb);
+    const bool want_ent = (a.terms & HIAST_TERM_ENT) && (iga || igb);
+    st.wait_older();                       // this pair's teacher probabilities
+    // pass 1 over the channels: everything the forward sums need, the entropy inner product and the teacher mass
+    pk::u64 sl2 = 0, h2 = 0, sc2 = 0, T2 = 0;
+    float lpya = 0.f, lpyb = 0.f, mna = INFINITY, mnb = INFINITY;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const pk::u64 d2 = ls.d(z[0][c], z[1][c]);
+      const pk::u64 lp2 = pk::sub2(d2, ls.logs2);
+      sl2 = (c == 0) ? lp2 : pk::add2(sl2, lp2);
+      float lpa, lpb;
+      pk::unpack(lp2, lpa, lpb);
+      lpya = (c == ya) ? lpa : lpya;
+      lpyb = (c == yb) ? lpb : lpyb;
+      if (want_ent) h2 = pk::fma2(pk::mul2(pk::exp2x(d2), ls.inv2), lp2 & ign_mask, h2);   // confident lanes: p * 0
+      if (want_cst) {
+        const pk::u64 t2 = st.t2(c);
+        T2 = (c == 0) ? t2 : pk::add2(T2, t2);
+        const pk::u64 pr2 = pk::mul2(lp2, t2);   // = -(-lp * t), same magnitude and zero-ness
+        sc2 = (c == 0) ? pr2 : pk::add2(sc2, pr2);
+        float pa, pb;
+        pk::unpack(pr2, pa, pb);
+        mna = fminf(mna, fabsf(pa));
+        mnb = fminf(mnb, fabsf(pb));
+      }
+    }
+    {
+      float sla, slb, ha, hb, sca, scb, logsa, logsb;
+      pk::unpack(sl2, sla, slb);
+      pk::unpack(h2, ha, hb);
+      pk::unpack(sc2, sca, scb);
+      pk::unpack(ls.logs2, logsa, logsb);
+      auto finish = [&](bool ign, int64_t p, float m, float logs, float lpy, float sl, float h, float scv, float mn) {
+        if (!ign) {
+          if (a.terms & HIAST_TERM_CE) sacc[0 * kThreadsL] += static_cast<double>(-lpy);
+          if (a.terms & HIAST_TERM_KLD) sacc[1 * kThreadsL] += static_cast<double>(-sl * (1.0f / C));
+          sacc[4 * kThreadsL] += 1.0;          // counts as exact doubles (< 2^53)
+        } else {
+          if (a.terms & HIAST_TERM_ENT) sacc[2 * kThreadsL] += static_cast<double>(-h);
+          sacc[5 * kThreadsL] += 1.0;
+        }
+        if (want_cst && in_region(a.region, ign)) {
+          sacc[3 * kThreadsL] += static_cast<double>(-scv);
+          sacc[6 * kThreadsL] += static_cast<double>((mn > 0.f) ? C : recount_nonzero<C>(a, b, p, m, logs));
+        }
+      };
+      finish(iga, p2i * kPxL, ls.ma, logsa, lpya, sla, ha, sca, mna);
+      finish(igb, p2i * kPxL + 1, ls.mb, logsb, lpyb, slb, hb, scb, mnb);
+    }
+    // pass 2: the gradient, channel by channel right before the store
+    const pk::u64 NT2 = T2 ^ 0x8000000080000000ull;
+    float2* gs = reinterpret_cast<float2*>(grad + static_cast<size_t>(b) * C * a.HW) + p2i;
+    float tguard = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const pk::u64 d2 = ls.d(z[0][c], z[1][c]);
+      const pk::u64 p2 = pk::mul2(pk::exp2x(d2), ls.inv2);
+      const pk::u64 lpm2 = pk::sub2(d2, ls.logs2) & ign_mask;
+      const pk::u64 t2 = st.t2(c);
+      pk::u64 g2 = pk::fma2(p2, A2, K2);
+      g2 = pk::fma2(pk::mul2(p2, pk::sub2(lpm2, h2)), NE2, g2);      // - ent p (lp - h)   (0 on confident lanes)
+      g2 = pk::fma2(pk::fma2(p2, NT2, t2), NC2, g2);                  // - cst (t - p T)
+      g2 = pk::add2(g2, poison2);
+      float ga, gb, t0, t1;
+      pk::unpack(g2, ga, gb);
+      pk::unpack(t2, t0, t1);
+      tguard = fmaxf(tguard, t0);
+      if (c == ya) ga -= cea;
+      if (c == yb) gb -= ceb;
+      __stcs(gs + static_cast<size_t>(c) * st.HW2, make_float2(ga, gb));
+    }
+    if (more && tguard == tguard) st.prefetch_t(i + stride);          // the t slots have been read
+    else asm volatile("cp.async.commit_group;\n" ::: "memory");
+    ya = nya;
+    yb = nyb;
+  }
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+  PixelSums acc;
+  acc.ce = sacc[0 * kThreadsL]; acc.kld = sacc[1 * kThreadsL]; acc.ent = sacc[2 * kThreadsL]; acc.cst = sacc[3 * kThreadsL];
+  acc.n_conf = static_cast<long long>(sacc[4 * kThreadsL]);
+  acc.n_ign = static_cast<long long>(sacc[5 * kThreadsL]);
+  acc.n_nz = static_cast<long long>(sacc[6 * kThreadsL]);
+  block_reduce_store(acc, partials);
 }
 
 // Generic path: runtime C <= 255, any HW; channel column re-read through L1.
@@ -894,8 +1119,8 @@ extern "C" int hiast_st_loss_bwd(const float* z, const float* t, const void* plb
     HIAST_TRY(loss_configure_smem(C, smem));
     const bool packed = cst_kind_host(terms) == HIAST_CST_SOFTCE && !g_loss_scalar;
     if (packed) {
-      if (C == 19) k_loss_bwd_pk<19><<<grid, kThreadsL, smem, st>>>(a, scales, grad_z);
-      else k_loss_bwd_pk<16><<<grid, kThreadsL, smem, st>>>(a, scales, grad_z);
+      if (C == 19) k_loss_bwd_pk<19><<<grid, kThreadsL, smem, st>>>(a, scales, grad_z, nullptr);
+      else k_loss_bwd_pk<16><<<grid, kThreadsL, smem, st>>>(a, scales, grad_z, nullptr);
     } else {
       if (C == 19) k_loss_bwd<19><<<grid, kThreadsL, smem, st>>>(a, scales, grad_z);
       else k_loss_bwd<16><<<grid, kThreadsL, smem, st>>>(a, scales, grad_z);
@@ -903,6 +1128,64 @@ extern "C" int hiast_st_loss_bwd(const float* z, const float* t, const void* plb
   } else {
     k_loss_bwd_generic<<<grid, kThreadsL, 0, st>>>(a, scales, grad_z);
   }
+  HIAST_CHECK_LAUNCH();
+  return HIAST_OK;
+}
+
+extern "C" size_t hiast_st_loss_fused_workspace_bytes(int B, int C, int64_t HW) {
+  return hiast_st_loss_workspace_bytes(B, C, HW) + 64;
+}
+
+extern "C" int hiast_st_loss_fused(const float* z, const float* t, const void* plbl, int plbl_bytes, int B, int C, int64_t HW,
+                                   int region, int terms, const float* grad_weights, double* sums, int64_t* counts,
+                                   float* scales_used, float* grad_z, void* workspace, size_t workspace_bytes, void* stream) {
+  const int rc = check_loss_args(z, t, plbl, plbl_bytes, B, C, HW, region, terms);
+  if (rc != HIAST_OK) return rc;
+  if (!grad_weights || !sums || !counts || !scales_used || !grad_z || !workspace) return HIAST_ERR_INVALID_ARG;
+  if (workspace_bytes < hiast_st_loss_fused_workspace_bytes(B, C, HW)) return HIAST_ERR_WORKSPACE;
+  LossArgs a = {z, t, plbl, plbl_bytes, B, C, HW, region, terms};
+  if (B == 0 || !loss_vector_ok(a, grad_z) || cst_kind_host(terms) != HIAST_CST_SOFTCE || g_loss_scalar ||
+      reinterpret_cast<uintptr_t>(workspace) % 16 != 0)
+    return HIAST_ERR_UNSUPPORTED;         // callers take hiast_st_loss_fwd + hiast_st_loss_bwd
+  cudaStream_t st = as_stream(stream);
+  LabelCounts* lc = static_cast<LabelCounts*>(workspace);
+  Partial* parts = reinterpret_cast<Partial*>(static_cast<char*>(workspace) + 64);
+  HIAST_CUDA_TRY(cudaMemsetAsync(lc, 0, sizeof(LabelCounts), st));
+  const long long n = static_cast<long long>(B) * HW;
+  const int cgrid = static_cast<int>(std::max<long long>(1, std::min<long long>((n / 16 + 255) / 256, sm_count() * 4)));
+  k_label_count<<<cgrid, 256, 0, st>>>(plbl, plbl_bytes, n, lc);
+  HIAST_CHECK_LAUNCH();
+  const int grid = std::min(loss_grid(n), sm_count() * 2);
+  const size_t smem = loss_stage_bytes(C) + 7 * sizeof(double) * kThreadsL;     // + the forward accumulator columns
+  HIAST_TRY(loss_configure_smem(C, loss_stage_bytes(C)));
+  if (C == 19) {
+    HIAST_TRY(ensure_dyn_smem(k_loss_fused_pk<19>, smem));
+    k_loss_fused_pk<19><<<grid, kThreadsL, smem, st>>>(a, lc, grad_weights, scales_used, grad_z, parts);
+  } else {
+    HIAST_TRY(ensure_dyn_smem(k_loss_fused_pk<16>, smem));
+    k_loss_fused_pk<16><<<grid, kThreadsL, smem, st>>>(a, lc, grad_weights, scales_used, grad_z, parts);
+  }
+  HIAST_CHECK_LAUNCH();
+  k_loss_finalize<<<1, kThreadsL, 0, st>>>(parts, grid, sums, reinterpret_cast<long long*>(counts));
+  HIAST_CHECK_LAUNCH();
+  return HIAST_OK;
+}
+
+extern "C" int hiast_st_loss_bwd_checked(const float* z, const float* t, const void* plbl, int plbl_bytes, int B, int C,
+                                         int64_t HW, int region, int terms, const float* scales, const float* scales_used,
+                                         float* grad_z, void* stream) {
+  const int rc = check_loss_args(z, t, plbl, plbl_bytes, B, C, HW, region, terms);
+  if (rc != HIAST_OK) return rc;
+  if (!scales || !scales_used || !grad_z) return HIAST_ERR_INVALID_ARG;
+  if (B == 0) return HIAST_OK;
+  LossArgs a = {z, t, plbl, plbl_bytes, B, C, HW, region, terms};
+  if (!loss_vector_ok(a, grad_z) || cst_kind_host(terms) != HIAST_CST_SOFTCE) return HIAST_ERR_UNSUPPORTED;
+  cudaStream_t st = as_stream(stream);
+  const int grid = std::min(loss_grid(static_cast<long long>(B) * HW), sm_count() * 2);
+  const size_t smem = loss_stage_bytes(C);
+  HIAST_TRY(loss_configure_smem(C, smem));
+  if (C == 19) k_loss_bwd_pk<19><<<grid, kThreadsL, smem, st>>>(a, scales, grad_z, scales_used);
+  else k_loss_bwd_pk<16><<<grid, kThreadsL, smem, st>>>(a, scales, grad_z, scales_used);
   HIAST_CHECK_LAUNCH();
   return HIAST_OK;
 }

@@ -17,7 +17,7 @@ from ._lib import IGNORE, KEY_ONE, REGION, TERM_CE, TERM_CST, TERM_ENT, TERM_KLD
 
 __all__ = [
     'ias_key_lo', 'ias_num_bins', 'ias_row_stride', 'ias_new_hist', 'ias_softmax_hist', 'ias_upsample_softmax_hist', 'ias_conf_hist', 'ias_threshold_scan',
-    'ias_select', 'ias_meanprob_scan', 'ias_fused_window', 'UNSUPPORTED', 'cbst_sample_hist', 'cbst_quantile', 'copy_paste', 'hard_lut', 'st_loss_fwd', 'st_loss_bwd',
+    'ias_select', 'ias_meanprob_scan', 'ias_fused_window', 'UNSUPPORTED', 'cbst_sample_hist', 'cbst_quantile', 'copy_paste', 'hard_lut', 'st_loss_fwd', 'st_loss_bwd', 'st_loss_fused', 'st_loss_bwd_checked',
     'confusion_matrix', 'confusion_from_logits', 'iou_from_confusion', 'PngEncoder', 'resize_nearest_u8', 'softmax_flip_sum', 'probs_upsample_argmax', 'ce_general_fwd', 'ce_general_bwd', 'write_files',
     'Stager', 'FileWriter', 'WindowEmitter',
 ]
@@ -319,6 +319,48 @@ def st_loss_bwd(z, t, plbl, scales, region='ignored', terms=TERM_CE | TERM_KLD |
         grad = torch.empty_like(z)
     check(lib().hiast_st_loss_bwd(ptr(z), ptr(t), ptr(plbl), plbl.element_size(), b, c, hw, REGION[region], int(terms),
                                   ptr(scales), ptr(grad), stream_ptr(z.device)), 'hiast_st_loss_bwd')
+    return grad
+
+
+def st_loss_fused(z, t, plbl, grad_weights, region='ignored', terms=TERM_CE | TERM_KLD | TERM_ENT | TERM_CST, grad=None):
+    """Forward + backward in one pass for ASSUMED upstream gradients ``grad_weights`` f32[4] (device).  Returns
+    (sums f64[4], counts i64[3], scales_used f32[4], grad_z) or None when the configuration is not covered (nothing launched)."""
+    require_cuda(z, torch.float32, 'logits')
+    require_cuda(grad_weights, torch.float32, 'grad_weights')
+    b, c = z.shape[0], z.shape[1]
+    hw = z[0, 0].numel() if b else 1
+    if t is not None:
+        require_cuda(t, torch.float32, 'target')
+        assert t.shape == z.shape
+    _plbl_arg(plbl)
+    assert plbl.numel() == b * hw
+    dev = z.device
+    need = lib().hiast_st_loss_fused_workspace_bytes(b, c, hw)
+    key = ('fused', dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < need:
+        ws = _ws_cache[key] = torch.empty(max(need, 1 << 16), dtype=torch.uint8, device=dev)
+    sums = torch.empty(4, dtype=torch.float64, device=dev)
+    counts = torch.empty(3, dtype=torch.int64, device=dev)
+    used = torch.empty(4, dtype=torch.float32, device=dev)
+    if grad is None:
+        grad = torch.empty_like(z)
+    status = lib().hiast_st_loss_fused(ptr(z), ptr(t), ptr(plbl), plbl.element_size(), b, c, hw, REGION[region], int(terms),
+                                       ptr(grad_weights), ptr(sums), ptr(counts), ptr(used), ptr(grad), ptr(ws), ws.numel(),
+                                       stream_ptr(dev))
+    if status == UNSUPPORTED:
+        return None
+    check(status, 'hiast_st_loss_fused')
+    return sums, counts, used, grad
+
+
+def st_loss_bwd_checked(z, t, plbl, scales, scales_used, grad, region='ignored', terms=TERM_CE | TERM_KLD | TERM_ENT | TERM_CST):
+    """``grad`` (written by ``st_loss_fused`` for ``scales_used``) is left alone if ``scales`` are the same bits, else rewritten."""
+    require_cuda(scales, torch.float32, 'scales')
+    b, c = z.shape[0], z.shape[1]
+    hw = z[0, 0].numel() if b else 1
+    check(lib().hiast_st_loss_bwd_checked(ptr(z), ptr(t), ptr(plbl), plbl.element_size(), b, c, hw, REGION[region], int(terms),
+                                          ptr(scales), ptr(scales_used), ptr(grad), stream_ptr(z.device)), 'hiast_st_loss_bwd_checked')
     return grad
 
 

@@ -478,6 +478,8 @@ class _WindowPipeline:
         self.results = []
         self.pending = {}
         self._host_jobs = {}
+        # where the host's time goes (seconds): waiting for a window's completion, closing windows, everything else is the loader loop
+        self.trace = {'wait_completion': 0.0, 'close': 0.0, 'windows': 0, 't0': None, 'total': 0.0}
         self.emitter = self.writer = None
         if self.cuda:
             dev = engine.device
@@ -556,6 +558,15 @@ class _WindowPipeline:
             self.staged = []
 
     def _close(self):
+        import time
+        t_close = time.perf_counter()
+        if self.trace['t0'] is None:
+            self.trace['t0'] = t_close
+        self.trace['windows'] += 1
+        self._close_inner()
+        self.trace['close'] += time.perf_counter() - t_close
+
+    def _close_inner(self):
         self.flush_queued()
         if self.cuda:
             self.ev_a[self.j % self.N_SLOTS].record(self.main)
@@ -588,6 +599,10 @@ class _WindowPipeline:
         if self.emitter is not None:
             self.gen._wait_png()
             self.emitter.done()
+        import time
+        if self.trace['t0'] is not None:
+            self.trace['total'] = time.perf_counter() - self.trace['t0']
+        self.gen.pipeline_trace = dict(self.trace)
 
     # ---------------------------------------------------------------- the schedule
     def _advance(self, final):
@@ -676,6 +691,14 @@ class _WindowPipeline:
             self._complete(es)
 
     def _complete(self, es):
+        import time
+        t_wait = time.perf_counter()
+        try:
+            self._complete_inner(es)
+        finally:
+            self.trace['wait_completion'] += time.perf_counter() - t_wait
+
+    def _complete_inner(self, es):
         rec = self.pending.pop(es)
         e, gen, s = self.e, self.gen, self.emitter.slots[es]
         n, paths = rec['n'], rec['paths']

@@ -20,7 +20,7 @@ from torch import nn
 from torch.nn import functional as F
 
 from ._lib import TERM_CE, TERM_CST, TERM_ENT, TERM_KLD
-from .losses import IGNORE, fused_terms
+from .losses import IGNORE, GradHint, fused_terms
 from .registry import LOSS, MODEL
 
 # What build_region_weight hands to _kld / _entropy instead of a dense [B,C,H,W] tensor.
@@ -105,7 +105,17 @@ class SelfTrainingSegmentor(nn.Module):
         region = cfg.cst_training.cst_loss.region if use_cst else 'ignored'
         if region not in ('ignored', 'confident', 'all'):
             raise ValueError('{} is not a valid region'.format(region))
-        out = fused_terms(t_logits, t_plbl, t_cst_lbl if use_cst else None, region=region, terms=terms)
+        # one pass over (z, t, plbl) for forward AND backward: the gradient is written for the upstream gradients this
+        # composition produces under sum(losses).backward() (base_trainer.py:129-133) and verified / redone in backward
+        weights = (w_seg, w_kld if w_kld > 0 else 0.0, w_ent if w_ent > 0 else 0.0,
+                   cfg.cst_training.cst_loss.weight if use_cst else 0.0)
+        hint = None
+        if getattr(self, 'one_pass', True) and t_logits.is_cuda:
+            key = (weights, t_logits.device)
+            hint = self.__dict__.setdefault('_hints', {}).get(key)
+            if hint is None:
+                hint = self._hints[key] = GradHint(weights, t_logits.device)
+        out = fused_terms(t_logits, t_plbl, t_cst_lbl if use_cst else None, region=region, terms=terms, grad_hint=hint)
         losses['target_seg_loss'] = w_seg * out[0]
         if w_kld > 0:
             losses['kld_confident_loss'] = w_kld * out[1]

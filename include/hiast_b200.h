@@ -197,6 +197,24 @@ HIAST_API int hiast_st_loss_bwd(const float* z, const float* t, const void* plbl
                       int B, int C, int64_t HW, int region, int terms,
                       const float* scales, float* grad_z, void* stream);
 
+/* a10-a15 forward AND backward in ONE pass over (z, t, plbl): 236 B/px instead of the 160 + 236 of the two calls above.
+ * A label-only pre-pass fixes n_conf / n_ign; the main pass accumulates the forward sums and writes
+ *   grad_z = sum_k scales_used[k] * d(term k)/dz,   scales_used[k] = float(double(grad_weights[k]) / divisor_k)
+ * with divisor = {n_conf, C*n_conf, C*n_ign, C*n_region}: the gradient for ASSUMED upstream gradients grad_weights f32[4]
+ * (device; the caller's loss weights times the upstream scalar it expects).  sums / counts as hiast_st_loss_fwd;
+ * scales_used f32[4] (device) records the assumption.  When autograd later delivers the real upstream gradients, the
+ * caller computes the scales they imply and calls hiast_st_loss_bwd_checked: if they are the same bits as scales_used the
+ * kernel exits at once (grad_z is already right), else it rewrites grad_z like hiast_st_loss_bwd -- exact in every case
+ * (changed loss scale, SoftCE divisor != C*n_region because some product was exactly 0).  SoftCE kind, C in {16, 19},
+ * even HW only: otherwise HIAST_ERR_UNSUPPORTED and nothing is launched (use the two calls above).                    */
+HIAST_API size_t hiast_st_loss_fused_workspace_bytes(int B, int C, int64_t HW);
+HIAST_API int hiast_st_loss_fused(const float* z, const float* t, const void* plbl, int plbl_bytes, int B, int C, int64_t HW,
+                        int region, int terms, const float* grad_weights, double* sums, int64_t* counts,
+                        float* scales_used, float* grad_z, void* workspace, size_t workspace_bytes, void* stream);
+HIAST_API int hiast_st_loss_bwd_checked(const float* z, const float* t, const void* plbl, int plbl_bytes, int B, int C,
+                              int64_t HW, int region, int terms, const float* scales, const float* scales_used,
+                              float* grad_z, void* stream);
+
 /* ---- (4) confusion matrix / mIoU  utils/metrics.py:6-19 --------------------------------- */
 /* cm i64 [(K+1),(K+1)] (rows = target, cols = pred, index K = value outside [0,K)),
  * ACCUMULATED over the pixels whose target != ignore_index.  If pred_masked_out != NULL it

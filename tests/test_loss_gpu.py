@@ -286,3 +286,87 @@ def test_ce_general_matches_reference_fixture_and_oracle(key):
     assert a.item() == b.item()
     with pytest.raises(ValueError):
         LOSS['CE'](z.cuda(), labels.cuda(), refer_labels=refer.cuda(), region='nowhere')
+
+
+# ------------------------------------------------------------------ one-pass forward + backward (hiast_st_loss_fused)
+def _loss_inputs(shape, seed, ignore_frac=0.5, uint8=False):
+    b, c, h, w = shape
+    g = torch.Generator().manual_seed(seed)
+    z = (torch.randn(b, c, h, w, generator=g) * 3).cuda()
+    t = torch.softmax(torch.randn(b, c, h, w, generator=g) * 3, dim=1).cuda()
+    y = torch.randint(0, c, (b, h, w), generator=g)
+    y[torch.rand(b, h, w, generator=g) < ignore_frac] = 255
+    return z, t, (y.to(torch.uint8) if uint8 else y).cuda()
+
+
+@pytest.mark.parametrize('region', ['ignored', 'confident', 'all'])
+@pytest.mark.parametrize('shape,uint8', [((2, 19, 64, 128), False), ((1, 16, 33, 52), True), ((3, 19, 17, 26), False)])
+def test_one_pass_kernel_equals_two_pass_kernels(region, shape, uint8):
+    """hiast_st_loss_fused == hiast_st_loss_fwd + hiast_st_loss_bwd with the scales it reports, and
+    hiast_st_loss_bwd_checked leaves the gradient alone for equal scales / rewrites it for different ones."""
+    from hiast_b200 import ops
+    z, t, y = _loss_inputs(shape, sum(shape))
+    y = y.to(torch.uint8) if uint8 else y
+    gw = torch.tensor([1.0, 0.1, 1.0, 0.5], device='cuda')
+    res = ops.st_loss_fused(z, t, y, gw, region)
+    assert res is not None
+    sums, counts, used, grad = res
+    sums2, counts2 = ops.st_loss_fwd(z, t, y, region)
+    assert torch.equal(counts, counts2)
+    np.testing.assert_allclose(sums.cpu().numpy(), sums2.cpu().numpy(), rtol=1e-12)
+    c = shape[1]
+    cnt = counts.double()
+    want_scales = (gw.double() / torch.stack([cnt[0], c * cnt[0], c * cnt[1], cnt[2]])).float()
+    assert torch.equal(used, want_scales)                          # counts[2] == C * n_region here (no zero product)
+    want = ops.st_loss_bwd(z, t, y, used, region)
+    assert torch.equal(grad, want)
+    # the check: same scales -> untouched (sentinel survives); other scales -> rewritten
+    sentinel = torch.full_like(grad, 7.0)
+    ops.st_loss_bwd_checked(z, t, y, used.clone(), used, sentinel, region)
+    assert bool((sentinel == 7.0).all())
+    ops.st_loss_bwd_checked(z, t, y, used * 2, used, sentinel, region)
+    assert torch.equal(sentinel, ops.st_loss_bwd(z, t, y, used * 2, region))
+
+
+def test_one_pass_through_compute_loss_adapts_to_the_upstream_scale():
+    """SelfTrainingSegmentor.compute_loss takes the one-pass kernel; results equal the two-pass composition for upstream
+    1.0 (expectation met), for a loss-scaled backward (first step: gradient rewritten; later steps: expectation adapted)
+    and when a SoftCE product is exactly zero (divisor != C * n_ign: rewritten)."""
+    from hiast_b200.segmentor import SelfTrainingSegmentor
+    spec = dict(w_seg=1.0, w_kld=0.1, w_ent=1.0, w_cst=0.5, region='ignored')
+    z0, t, y = _loss_inputs((2, 19, 48, 64), 5)
+    t[:, 3] = 0.0                                                  # exact zeros among the products of every ignored pixel
+    one, two = SelfTrainingSegmentor(make_cfg(spec)), SelfTrainingSegmentor(make_cfg(spec))
+    two.one_pass = False
+    for scale in (1.0, 1.0, 1024.0, 1024.0, 1024.0, 3.7, 1.0):
+        grads, vals = [], []
+        for seg in (one, two):
+            z = z0.clone().requires_grad_(True)
+            out = seg.compute_loss(z, y, t)
+            (sum(out.values()) * scale).backward()
+            grads.append(z.grad)
+            vals.append([v.item() for v in out.values()])
+        np.testing.assert_allclose(vals[0], vals[1], rtol=1e-7)
+        assert torch.equal(grads[0], grads[1]), scale
+    # without exact zeros and with the expected upstream the backward is a no-op on the forward's gradient
+    z0, t, y = _loss_inputs((2, 19, 48, 64), 6)
+    z = z0.clone().requires_grad_(True)
+    out = one.compute_loss(z, y, t)
+    sum(out.values()).backward()
+    z2 = z0.clone().requires_grad_(True)
+    out2 = two.compute_loss(z2, y, t)
+    sum(out2.values()).backward()
+    assert torch.equal(z.grad, z2.grad)
+
+
+def test_one_pass_empty_regions_reproduce_the_reference_nans():
+    from hiast_b200.segmentor import SelfTrainingSegmentor
+    spec = dict(w_seg=1.0, w_kld=0.1, w_ent=1.0, w_cst=0.5, region='ignored')
+    z0, t, y = _loss_inputs((1, 19, 16, 32), 9, ignore_frac=0.0)   # no ignored pixel: ENT and CST are 0/0
+    seg = SelfTrainingSegmentor(make_cfg(spec))
+    z = z0.clone().requires_grad_(True)
+    out = seg.compute_loss(z, y, t)
+    assert torch.isnan(out['ent_ignored_loss']) and torch.isnan(out['cst_loss'])
+    assert torch.isfinite(out['target_seg_loss'])
+    sum(out.values()).backward()
+    assert torch.isnan(z.grad).all()
