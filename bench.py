@@ -645,7 +645,7 @@ def measure_e2e(args, device, rank, world, barrier):
         secs = float(t[0])
     assert n_files == steps_lr * WINDOW
     tr = dict(last_trace)
-    host_trace = {'rank0_seconds': {k: round(v, 4) for k, v in tr.items() if k in ('wait_completion', 'close', 'total')},
+    host_trace = {'rank0_seconds': {k: round(v, 4) for k, v in tr.items() if k in ('wait_completion', 'close', 'total', 'collect')},
                   'note': 'host time of rank 0 inside run(): blocked on a window\'s completion / closing windows (launches, token '
                           'calls, emit) / total between the first close and the end'}
     png = {'value': steps_lr * WINDOW * world / secs, 'unit': UNIT, 'steps': steps_lr, 'files_written': n_files,

@@ -104,6 +104,32 @@ class BasePseudoGenerator:
         self.pow_rounding_certified = True
         self.initialize()
 
+    # ``sample_stats`` (:19) and ``samples_class`` (:20) are rebuilt from the [n_images, C] count matrix of a run the first
+    # time somebody looks at them (``save_data`` on rank 0, a test, the training code): for 12 k images that is ~40 ms of list
+    # building that the other ranks of a sharded run never need.
+    @property
+    def sample_stats(self):
+        self._materialize_stats()
+        return self._sample_stats
+
+    @sample_stats.setter
+    def sample_stats(self, value):
+        self._sample_stats = value
+
+    @property
+    def samples_class(self):
+        self._materialize_stats()
+        return self._samples_class
+
+    @samples_class.setter
+    def samples_class(self, value):
+        self._samples_class = value
+
+    def _materialize_stats(self):
+        pend = self.__dict__.pop('_stats_pending', None)
+        if pend is not None:
+            self._record_images(*pend)
+
     @staticmethod
     def _default_workers():
         """File-writer threads: the host cores this rank may use (cores / ranks on the node) minus the interpreter's own,
@@ -264,12 +290,11 @@ class BasePseudoGenerator:
             d = dict(zip(cols_l[a:b], vals[a:b]))
             d['file'] = paths[i]
             stats.append(d)
-        self.sample_stats = stats
-        self.samples_class = {}
+        self._sample_stats = stats
+        self._samples_class = {}
         for c in range(C):
             idx = np.flatnonzero(counts[:, c])
-            self.samples_class[c] = [[paths[i], v] for i, v in zip(idx.tolist(), counts[idx, c].tolist())]
-        self.statics_class = np.array([0] * C) + (counts.sum(axis=0) if n else 0)
+            self._samples_class[c] = [[paths[i], v] for i, v in zip(idx.tolist(), counts[idx, c].tolist())]
 
     def _cp_gamma(self):
         return float(_cfg_get(self.cfg, 'preprocessor.copy_paste.gamma', 0.99))
@@ -388,7 +413,10 @@ class BasePseudoGenerator:
                 engine.thr_state.copy_(torch.from_numpy(np.asarray(self.class_threshold, dtype=np.float64)))
         pipe.finish()
         self._wait_png()
+        import time
+        t0 = time.perf_counter()
         self._collect(pipe, scan, rank, world, pg)
+        self.pipeline_trace['collect'] = time.perf_counter() - t0
 
     def _iterate_logits(self, get_pipe=lambda: None):
         """Yields (logits [B,C,H,W] on the device or LowResLogits, image_paths, staging slot) as :189-192 produces them."""
@@ -444,7 +472,9 @@ class BasePseudoGenerator:
             confsums.append(confsum[:g])
             all_counts.append(counts)
             all_paths += paths
-        self._record_images(np.concatenate(all_counts) if all_counts else np.zeros((0, C), dtype=np.int64), all_paths)
+        counts_all = np.concatenate(all_counts) if all_counts else np.zeros((0, C), dtype=np.int64)
+        self.statics_class = np.array([0] * C) + (counts_all.sum(axis=0) if len(all_paths) else 0)
+        self._stats_pending = (counts_all, all_paths)            # sample_stats / samples_class: built on first access
         if order:
             dev = e.thr_state.device
             e.mean_state.copy_(torch.from_numpy(np.asarray(self.class_mean_probs, dtype=np.float64)))
@@ -480,6 +510,9 @@ class _WindowPipeline:
         self._host_jobs = {}
         # where the host's time goes (seconds): waiting for a window's completion, closing windows, everything else is the loader loop
         self.trace = {'wait_completion': 0.0, 'close': 0.0, 'windows': 0, 't0': None, 'total': 0.0}
+        # HIAST_PIPE_EVENTS=<dir>: device timeline of every window (timing events on the three streams), dumped per rank
+        self._ev_dir = os.environ.get('HIAST_PIPE_EVENTS')
+        self._evs = []
         self.emitter = self.writer = None
         if self.cuda:
             dev = engine.device
@@ -566,8 +599,18 @@ class _WindowPipeline:
         self._close_inner()
         self.trace['close'] += time.perf_counter() - t_close
 
+    def _mark(self, name, j, stream):
+        if self._ev_dir and self.cuda:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(stream)
+            self._evs.append((name, j, ev))
+
     def _close_inner(self):
+        if self._ev_dir and self.cuda:
+            self._mark('A_begin', self.j, self.main)
         self.flush_queued()
+        if self._ev_dir and self.cuda:
+            self._mark('A_end', self.j, self.main)
         if self.cuda:
             self.ev_a[self.j % self.N_SLOTS].record(self.main)
         self.closed.append((self.filled, self.paths))
@@ -603,6 +646,13 @@ class _WindowPipeline:
         if self.trace['t0'] is not None:
             self.trace['total'] = time.perf_counter() - self.trace['t0']
         self.gen.pipeline_trace = dict(self.trace)
+        if self._ev_dir and self._evs:
+            torch.cuda.synchronize()
+            base = self._evs[0][2]
+            rows = [(name, j, round(base.elapsed_time(ev), 3)) for name, j, ev in self._evs]
+            os.makedirs(self._ev_dir, exist_ok=True)
+            with open(os.path.join(self._ev_dir, 'pipe_events_rank%d_%d.json' % (self.rank, len(rows))), 'w') as f:
+                json.dump(rows, f)
 
     # ---------------------------------------------------------------- the schedule
     def _advance(self, final):
@@ -641,7 +691,9 @@ class _WindowPipeline:
         if self.ev_out[j % self.N_SLOTS] is not None:        # window j-3's thresholds have been copied out of this slot
             self.side.wait_event(self.ev_out[j % self.N_SLOTS])
         with torch.cuda.stream(self.side):
+            self._mark('chain_begin', j, self.side)
             body()
+            self._mark('chain_end', j, self.side)
             self.ev_b[j % self.N_SLOTS].record(self.side)
 
     def _peer(self, step):
@@ -674,7 +726,10 @@ class _WindowPipeline:
             self.main.wait_event(self.ev_b[es])
         if self.ev_out[es] is not None:                      # the copies of window j-3 have left this slot's device buffers
             self.main.wait_event(self.ev_out[es])
+        self._mark('emit_begin', j, self.main)
         copied = self.emitter.emit(es, first, n, stream=self.main_ptr, copy_stream=self.out_ptr)
+        self._mark('emit_end', j, self.main)
+        self._mark('copy_end', j, self.out)
         s = self.emitter.slots[es]
         rec = dict(j=j, w=w, n=n, paths=paths, copied=copied)
         if self.mode == 'files':

@@ -403,10 +403,11 @@ def test_cli_script_end_to_end(tmp_path, monkeypatch):
     assert sorted(order) == ['city/img_%02d.png' % i for i in range(N)]
     ds = ToyTarget(None, None, None)
     idx = [int(p[-6:-4]) for p in order]
-    with torch.no_grad():
-        logits = ref_model.cuda()(ds.imgs[idx].cuda())['logits']
+    ref_model = ref_model.cuda()
+    with torch.no_grad():                                   # batch by batch like the generator (cuDNN picks per shape)
+        batches = [(ref_model(ds.imgs[idx[i:i + 2]].cuda())['logits'], order[i:i + 2]) for i in range(0, N, 2)]
     oracle = oias.IASOracle(C, 0.5, 0.9, 8.0, 0.99)
-    oracle.run([(logits[i:i + 2], order[i:i + 2]) for i in range(0, N, 2)])
+    oracle.run(batches)
     assert np.array_equal(gen.class_threshold, oracle.class_threshold)
     assert gen.sample_stats == oracle.sample_stats
     for i, p in enumerate(order):
