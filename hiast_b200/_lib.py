@@ -46,6 +46,12 @@ _SIGNATURES = {
     'hiast_ias_upsample_softmax_hist': (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     'hiast_ias_conf_hist': (_i, [_vp, _vp, _i, _i, _i64, _i, _i, _i, _i, _vp, _vp, _vp]),
     'hiast_ias_threshold_scan': (_i, [_vp, _i, _i, _i, _d, _d, _d, _vp, _vp, _vp, _vp, _vp]),
+    'hiast_ias_threshold_scan_ring': (_i, [_vp, _i, _i, _i, _d, _d, _d, _vp, _vp, _vp, _vp, _vp, C.c_uint64, _vp, C.c_uint64, _vp]),
+    'hiast_ring_mailbox_bytes': (_sz, []),
+    'hiast_ring_create': (_i, [C.POINTER(_vp), _vp]),
+    'hiast_ring_open': (_i, [_vp, C.POINTER(_vp)]),
+    'hiast_ring_close': (_i, [_vp]),
+    'hiast_ring_destroy': (_i, [_vp]),
     'hiast_ias_select': (_i, [_vp, _vp, _vp, _i, _i64, _i, _i, _vp, _vp, _vp, _vp]),
     'hiast_ias_meanprob_scan': (_i, [_vp, _vp, _i, _i, _i, _i, _d, _vp, _vp]),
     'hiast_ias_fused_workspace_bytes': (_sz, [_i, _i]),

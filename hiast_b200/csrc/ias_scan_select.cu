@@ -1,5 +1,7 @@
 // (1c) IAS phases B and C: threshold chain (workflows/pseudo_label_generator.py:171-179,207-209), threshold-and-mask
 // pass (:71-89), mean-confidence EMA (:95-105), and the histogram from caller-provided conf / label.
+#include <string.h>
+
 #include "ias_common.cuh"
 
 namespace hiast {
@@ -63,10 +65,38 @@ __global__ void __launch_bounds__(kThreadsP) k_hist_prefix(uint32_t* __restrict_
 // buffered, so the serial chain touches only shared memory.  Warp 0 runs the step (all lanes compute the
 // same scalars; the two order-statistic searches are warp-cooperative), the other warps only stage.
 constexpr int kThreadsS = 128;
+// Token ring over peer memory (multi-GPU).  The only cross-GPU dependency of the path is the threshold state f64[C]
+// (pseudo_label_generator.py:207-209 carries it from batch to batch).  Instead of an NCCL receive kernel in front of the scan
+// and a send kernel behind it, the scan kernel itself takes the hand-off: CTA c (class c) waits until slot c of THIS GPU's
+// mailbox carries sequence number >= in_seq, starts from the value found there, and at the end stores its final threshold
+// into slot c of the NEXT GPU's mailbox (a peer pointer: the store travels over NVLink) and releases that slot's sequence
+// number.  19 independent flags, no cross-CTA synchronisation, no host involvement per hop.
+struct RingToken {
+  double value[HIAST_MAX_CLASSES + 1];
+  unsigned long long seq[HIAST_MAX_CLASSES + 1];
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
+  return t;
+}
+constexpr unsigned long long kRingTimeoutNs = 10ull * 1000ull * 1000ull * 1000ull;   // then error bit 8, never a hang
+
 __global__ void __launch_bounds__(kThreadsS) k_threshold_scan(const uint32_t* __restrict__ prefix, int n_groups, int C,
                                                               int key_lo, int nb, double alpha, double beta, double gamma,
                                                               double* __restrict__ thr_state, double* __restrict__ thr_groups,
-                                                              float* __restrict__ temp_groups, int* __restrict__ error_flag) {
+                                                              float* __restrict__ temp_groups, int* __restrict__ error_flag,
+                                                              const RingToken* token_in, unsigned long long in_seq,
+                                                              RingToken* token_out, unsigned long long out_seq) {
   extern __shared__ __align__(128) uint32_t s_rows[];  // [2][nbs]
   const int c = blockIdx.x;
   const int nbs = row_stride(nb);
@@ -81,7 +111,23 @@ __global__ void __launch_bounds__(kThreadsS) k_threshold_scan(const uint32_t* __
   };
   double thr = thr_state[c];
   int err = 0;
-  if (n_groups > 0) stage(0, 0);
+  if (n_groups > 0) stage(0, 0);               // the first row is on its way while the token is awaited
+  if (token_in) {
+    __shared__ double s_token;
+    if (threadIdx.x == 0) {
+      const unsigned long long t0 = global_timer_ns();
+      while (ld_acquire_sys_u64(&token_in->seq[c]) < in_seq) {
+        __nanosleep(100);
+        if (global_timer_ns() - t0 > kRingTimeoutNs) {
+          err |= 8;
+          break;
+        }
+      }
+      s_token = *reinterpret_cast<const volatile double*>(&token_in->value[c]);
+    }
+    __syncthreads();
+    thr = s_token;
+  }
   for (int g = 0; g < n_groups; ++g) {
     if (g + 1 < n_groups) {
       stage(g + 1, (g + 1) & 1);
@@ -104,6 +150,11 @@ __global__ void __launch_bounds__(kThreadsS) k_threshold_scan(const uint32_t* __
   }
   if (threadIdx.x == 0) {
     thr_state[c] = thr;
+    if (token_out) {
+      *reinterpret_cast<volatile double*>(&token_out->value[c]) = thr;
+      __threadfence_system();
+      st_release_sys_u64(&token_out->seq[c], out_seq);
+    }
     if (err && error_flag) atomicOr(error_flag, err);
   }
 }
@@ -392,21 +443,72 @@ extern "C" int hiast_ias_conf_hist(const float* conf, const void* label, int lab
   return HIAST_OK;
 }
 
-extern "C" int hiast_ias_threshold_scan(uint32_t* hist, int n_groups, int C, int key_lo, double alpha, double beta,
-                                        double gamma, double* thr_state, double* thr_groups, float* temp_groups,
-                                        int* error_flag, void* stream) {
+extern "C" int hiast_ias_threshold_scan_ring(uint32_t* hist, int n_groups, int C, int key_lo, double alpha, double beta,
+                                             double gamma, double* thr_state, double* thr_groups, float* temp_groups,
+                                             int* error_flag, const void* token_in, uint64_t in_seq, void* token_out,
+                                             uint64_t out_seq, void* stream) {
   if (!hist || !thr_state || !thr_groups) return HIAST_ERR_INVALID_ARG;
   if (n_groups < 0 || C < 1 || C > HIAST_MAX_CLASSES || key_lo < 0 || key_lo > HIAST_KEY_ONE) return HIAST_ERR_INVALID_ARG;
-  if (n_groups == 0) return HIAST_OK;
+  if (n_groups == 0 && !token_in && !token_out) return HIAST_OK;
   cudaStream_t st = as_stream(stream);
   const int nb = HIAST_KEY_ONE - key_lo + 1;
-  k_hist_prefix<<<n_groups * C, kThreadsP, 0, st>>>(hist, nb);
-  HIAST_CHECK_LAUNCH();
+  if (n_groups > 0) {
+    k_hist_prefix<<<n_groups * C, kThreadsP, 0, st>>>(hist, nb);
+    HIAST_CHECK_LAUNCH();
+  }
   const size_t smem = 2 * static_cast<size_t>(row_stride(nb)) * sizeof(uint32_t);
   HIAST_TRY(ensure_dyn_smem(k_threshold_scan, smem));
   k_threshold_scan<<<C, kThreadsS, smem, st>>>(hist, n_groups, C, key_lo, nb, alpha, beta, gamma, thr_state, thr_groups,
-                                               temp_groups, error_flag);
+                                               temp_groups, error_flag, static_cast<const RingToken*>(token_in), in_seq,
+                                               static_cast<RingToken*>(token_out), out_seq);
   HIAST_CHECK_LAUNCH();
+  return HIAST_OK;
+}
+
+extern "C" int hiast_ias_threshold_scan(uint32_t* hist, int n_groups, int C, int key_lo, double alpha, double beta,
+                                        double gamma, double* thr_state, double* thr_groups, float* temp_groups,
+                                        int* error_flag, void* stream) {
+  return hiast_ias_threshold_scan_ring(hist, n_groups, C, key_lo, alpha, beta, gamma, thr_state, thr_groups, temp_groups,
+                                       error_flag, nullptr, 0, nullptr, 0, stream);
+}
+
+// Mailbox of the token ring: 4 KB of device memory that other processes on the node can map (CUDA IPC).
+extern "C" size_t hiast_ring_mailbox_bytes(void) { return sizeof(RingToken); }
+
+extern "C" int hiast_ring_create(void** local_box_out, void* ipc_handle_out) {
+  if (!local_box_out || !ipc_handle_out) return HIAST_ERR_INVALID_ARG;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "the handle travels as 64 opaque bytes");
+  void* p = nullptr;
+  HIAST_CUDA_TRY(cudaMalloc(&p, sizeof(RingToken)));
+  cudaError_t e = cudaMemset(p, 0, sizeof(RingToken));
+  cudaIpcMemHandle_t h;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    return cuda_fail(e);
+  }
+  memcpy(ipc_handle_out, &h, sizeof(h));
+  *local_box_out = p;
+  return HIAST_OK;
+}
+
+extern "C" int hiast_ring_open(const void* ipc_handle, void** peer_box_out) {
+  if (!ipc_handle || !peer_box_out) return HIAST_ERR_INVALID_ARG;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, ipc_handle, sizeof(h));
+  void* p = nullptr;
+  HIAST_CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  *peer_box_out = p;
+  return HIAST_OK;
+}
+
+extern "C" int hiast_ring_close(void* peer_box) {
+  if (peer_box) HIAST_CUDA_TRY(cudaIpcCloseMemHandle(peer_box));
+  return HIAST_OK;
+}
+
+extern "C" int hiast_ring_destroy(void* local_box) {
+  if (local_box) HIAST_CUDA_TRY(cudaFree(local_box));
   return HIAST_OK;
 }
 

@@ -105,11 +105,13 @@ class IASEngine:
         ops.ias_conf_hist(self.conf[sl], label.reshape(n, self.H, self.W).contiguous(), self.C, self.B, self.key_lo,
                           self.hist[g0:g0 + self._groups(n)], accumulate=False, label_u8_out=self.label[sl])
 
-    def phase_b(self, first_image, n_images):
+    def phase_b(self, first_image, n_images, token=None):
+        """``token``: (mailbox_in, in_seq, mailbox_out, out_seq) of the multi-GPU token ring (sharded.TokenRing), fused into
+        the scan kernel; None on one GPU or when the state travels through torch.distributed send / recv."""
         g0, g = first_image // self.B, self._groups(n_images)
         ops.ias_threshold_scan(self.hist[g0:g0 + g], g, self.C, self.key_lo, self.alpha, self.beta, self.gamma,
                                self.thr_state, self.thr_groups[g0:g0 + g], self.temp_groups[g0:g0 + g],
-                               self.error_flag)
+                               self.error_flag, token=token)
 
     def phase_c(self, first_image, n_images):
         g0, g = first_image // self.B, self._groups(n_images)
@@ -170,6 +172,8 @@ class IASEngine:
         flag = int(self.error_flag.item())
         if flag & 4:
             raise RuntimeError('hiast_ias_fused_window gave up waiting for a group to close (internal error)')
+        if flag & 8:
+            raise RuntimeError('the threshold token of the multi-GPU ring did not arrive within 10 s (a rank died or fell out of step)')
         if flag & 1:
             raise ValueError('Quantiles must be in the range [0, 1]')
         return not (flag & 2)

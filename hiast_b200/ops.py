@@ -129,8 +129,10 @@ def ias_conf_hist(conf, label, num_classes, group_size, key_lo=0, hist=None, acc
 
 
 def ias_threshold_scan(hist, n_groups, num_classes, key_lo, alpha, beta, gamma, thr_state, thr_groups=None,
-                       temp_groups=None, error_flag=None):
-    """Phase B.  hist becomes prefix sums in place; thr_state f64[C] is updated in place.
+                       temp_groups=None, error_flag=None, token=None):
+    """Phase B.  hist becomes prefix sums in place; thr_state f64[C] is updated in place.  ``token`` =
+    (mailbox_in_ptr or None, in_seq, mailbox_out_ptr or None, out_seq): the multi-GPU hand-off over peer memory fused into
+    the scan kernel (``hiast_ias_threshold_scan_ring``).
 
     Returns (thr_groups f64 [G,C], temp_groups f32 [G,C])."""
     require_cuda(hist, torch.int32, 'hist')
@@ -140,9 +142,17 @@ def ias_threshold_scan(hist, n_groups, num_classes, key_lo, alpha, beta, gamma, 
         thr_groups = torch.empty((n_groups, num_classes), dtype=torch.float64, device=dev)
     if temp_groups is None:
         temp_groups = torch.empty((n_groups, num_classes), dtype=torch.float32, device=dev)
-    check(lib().hiast_ias_threshold_scan(ptr(hist), int(n_groups), int(num_classes), int(key_lo), float(alpha),
-                                         float(beta), float(gamma), ptr(thr_state), ptr(thr_groups), ptr(temp_groups),
-                                         ptr(error_flag), stream_ptr(dev)), 'hiast_ias_threshold_scan')
+    if token is None:
+        check(lib().hiast_ias_threshold_scan(ptr(hist), int(n_groups), int(num_classes), int(key_lo), float(alpha),
+                                             float(beta), float(gamma), ptr(thr_state), ptr(thr_groups), ptr(temp_groups),
+                                             ptr(error_flag), stream_ptr(dev)), 'hiast_ias_threshold_scan')
+    else:
+        t_in, in_seq, t_out, out_seq = token
+        check(lib().hiast_ias_threshold_scan_ring(ptr(hist), int(n_groups), int(num_classes), int(key_lo), float(alpha),
+                                                  float(beta), float(gamma), ptr(thr_state), ptr(thr_groups), ptr(temp_groups),
+                                                  ptr(error_flag), C.c_void_p(t_in) if t_in else None, int(in_seq),
+                                                  C.c_void_p(t_out) if t_out else None, int(out_seq), stream_ptr(dev)),
+              'hiast_ias_threshold_scan_ring')
     return thr_groups, temp_groups
 
 

@@ -500,6 +500,10 @@ class _WindowPipeline:
         self._window_images = window_images
         self.n_windows_total = None if n_total is None else (n_total + self.window - 1) // self.window
         self.cuda = torch.is_tensor(engine.plbl) and engine.plbl.is_cuda
+        self.ring = None
+        if self.cuda and world > 1 and self.scan:
+            from .sharded import TokenRing
+            self.ring = TokenRing.get(engine.device, rank, world, pg)      # None: torch.distributed send / recv
         self.j = 0                    # local window being filled
         self.filled, self.paths, self.staged = 0, [], []
         self.queued = []              # stride-8 batches of the current window awaiting their single phase-A launch
@@ -509,7 +513,7 @@ class _WindowPipeline:
         self.pending = {}
         self._host_jobs = {}
         # where the host's time goes (seconds): waiting for a window's completion, closing windows, everything else is the loader loop
-        self.trace = {'wait_completion': 0.0, 'close': 0.0, 'windows': 0, 't0': None, 'total': 0.0}
+        self.trace = {'wait_completion': 0.0, 'close': 0.0, 'chain_host': 0.0, 'flush_host': 0.0, 'windows': 0, 't0': None, 'total': 0.0}
         # HIAST_PIPE_EVENTS=<dir>: device timeline of every window (timing events on the three streams), dumped per rank
         self._ev_dir = os.environ.get('HIAST_PIPE_EVENTS')
         self._evs = []
@@ -608,7 +612,10 @@ class _WindowPipeline:
     def _close_inner(self):
         if self._ev_dir and self.cuda:
             self._mark('A_begin', self.j, self.main)
+        import time
+        t_f = time.perf_counter()
         self.flush_queued()
+        self.trace['flush_host'] += time.perf_counter() - t_f
         if self._ev_dir and self.cuda:
             self._mark('A_end', self.j, self.main)
         if self.cuda:
@@ -642,6 +649,8 @@ class _WindowPipeline:
         if self.emitter is not None:
             self.gen._wait_png()
             self.emitter.done()
+        if self.ring is not None:
+            self.ring.advance(self.n_windows_total)
         import time
         if self.trace['t0'] is not None:
             self.trace['total'] = time.perf_counter() - self.trace['t0']
@@ -660,7 +669,10 @@ class _WindowPipeline:
         b_target = n_closed if (final or not self.scan) else n_closed - 1
         while self.b_done < b_target:
             if self.scan:
+                import time
+                t_c = time.perf_counter()
                 self._chain(self.b_done)
+                self.trace['chain_host'] += time.perf_counter() - t_c
             self.b_done += 1
         c_target = self.b_done if (final or not self.scan) else self.b_done - 1
         while self.c_done < c_target:
@@ -678,6 +690,9 @@ class _WindowPipeline:
         ring = self.world > 1
 
         def body():
+            if self.ring is not None:                 # hand-off fused into the scan kernel, over peer memory
+                e.phase_b(slot, n, token=self.ring.token(w, self.n_windows_total))
+                return
             if ring and w > 0:
                 dist.recv(e.thr_state, src=self._peer(-1), group=self.pg)
             e.phase_b(slot, n)

@@ -45,6 +45,76 @@ def device_stream(device, kind):
     return st
 
 
+class TokenRing:
+    """Mailboxes of the peer-memory token ring (``hiast_ring_*`` / ``hiast_ias_threshold_scan_ring``): every rank owns one
+    4 KB mailbox on its GPU and maps the mailbox of the NEXT rank through CUDA IPC.  Creation is collective (one
+    ``all_gather_object`` of the 64-byte handles).  ``token(w, n_windows_total)`` gives the scan kernel of global window w
+    its (mailbox_in, in_seq, mailbox_out, out_seq); sequence numbers keep growing across runs (``advance``).
+
+    ``TokenRing.get`` returns None -- and the callers fall back to ``torch.distributed`` send / recv -- on CPU, with one
+    rank, when ``HIAST_RING=nccl`` is set, or when any rank could not create or map a mailbox (ranks on different nodes)."""
+
+    _cache = {}
+
+    def __init__(self, local_ptr, next_ptr, rank, world):
+        self.local, self.next, self.rank, self.world = local_ptr, next_ptr, rank, world
+        self.base = 0
+
+    @classmethod
+    def get(cls, device, rank, world, pg=None):
+        import ctypes as C
+        import os
+        from ._lib import lib
+        device = torch.device(device)
+        if world < 2 or device.type != 'cuda' or os.environ.get('HIAST_RING', 'peer') == 'nccl':
+            return None
+        key = (id(pg), device.index if device.index is not None else torch.cuda.current_device(), rank, world)
+        if key in cls._cache:
+            return cls._cache[key]
+        ring = None
+        local, handle = C.c_void_p(), (C.c_ubyte * 64)()
+        with torch.cuda.device(device):
+            ok = lib().hiast_ring_create(C.byref(local), C.cast(handle, C.c_void_p)) == 0
+            infos = [None] * world
+            dist.all_gather_object(infos, (ok, bytes(handle), _host_id()), group=pg)
+            nxt = infos[(rank + 1) % world]
+            peer = C.c_void_p()
+            if ok and all(i[0] for i in infos) and len({i[2] for i in infos}) == 1:
+                buf = (C.c_ubyte * 64).from_buffer_copy(nxt[1])
+                ok = lib().hiast_ring_open(C.cast(buf, C.c_void_p), C.byref(peer)) == 0
+            else:
+                ok = False
+            oks = [None] * world
+            dist.all_gather_object(oks, ok, group=pg)
+            if all(oks):
+                ring = cls(local.value, peer.value, rank, world)
+            else:
+                if peer.value:
+                    lib().hiast_ring_close(peer)
+                if local.value:
+                    lib().hiast_ring_destroy(local)
+        cls._cache[key] = ring
+        return ring
+
+    def token(self, w, n_windows_total):
+        t_in = self.local if w > 0 else None
+        t_out = self.next if w < n_windows_total - 1 else None
+        return (t_in, self.base + w, t_out, self.base + w + 1)
+
+    def advance(self, n_windows_total):
+        """Every rank calls this once per finished job: the next job's sequence numbers start above this one's."""
+        self.base += n_windows_total + 1
+
+
+def _host_id():
+    import socket
+    try:
+        with open('/proc/sys/kernel/random/boot_id') as f:
+            return socket.gethostname() + ':' + f.read().strip()
+    except OSError:
+        return socket.gethostname()
+
+
 def window_owner(w, world_size):
     return w % world_size
 
@@ -90,6 +160,8 @@ class ShardedIAS:
         self.n_windows_total = (self.n_total + self.window_size - 1) // self.window_size
         self.my_windows = local_windows(self.n_windows_total, self.rank, self.world)
         self.cuda = torch.is_tensor(engine.plbl) and engine.plbl.is_cuda
+        self.ring = TokenRing.get(engine.device, self.rank, self.world, process_group) \
+            if (self.cuda and use_dist and self.world > 1) else None
         if self.cuda:
             self.side = device_stream(engine.device, 'chain')
             self.ev_a = [torch.cuda.Event() for _ in range(self.n_slots)]
@@ -154,6 +226,9 @@ class ShardedIAS:
         ring = self.world > 1
 
         def body():
+            if self.ring is not None:                 # hand-off fused into the scan kernel, over peer memory
+                e.phase_b(self._slot(j), self._n(j), token=self.ring.token(w, self.n_windows_total))
+                return
             if ring and w > 0:
                 dist.recv(e.thr_state, src=self._global((self.rank - 1) % self.world), group=self.pg)
             e.phase_b(self._slot(j), self._n(j))
@@ -191,6 +266,8 @@ class ShardedIAS:
         dev = e.thr_state.device
         if self.cuda:
             torch.cuda.current_stream(e.device).wait_stream(self.side)
+        if self.ring is not None:
+            self.ring.advance(self.n_windows_total)
         packed = torch.zeros((kmax * gw * 2 + 1, C), dtype=torch.int64, device=dev)
         nloc = len(self.my_windows)
         if nloc and self._stash_conf is not None:

@@ -118,6 +118,26 @@ HIAST_API int hiast_ias_threshold_scan(uint32_t* hist, int n_groups, int C, int 
                              double* thr_state, double* thr_groups, float* temp_groups,
                              int* error_flag, void* stream);
 
+/* a3+a4 with the multi-GPU hand-off of the threshold state fused in (the only cross-GPU dependency of the path
+ * is this f64[C] state; the reference is single-process).  Token ring over peer memory: a MAILBOX is hiast_ring_mailbox_bytes()
+ * of device memory created by hiast_ring_create, which also returns a 64-byte CUDA IPC handle that another process on the node
+ * turns into a peer pointer with hiast_ring_open.  The scan kernel of window w
+ *   - token_in  != NULL: CTA c waits until slot c of THIS GPU's mailbox carries a sequence number >= in_seq and starts from
+ *                        the threshold stored there instead of thr_state[c];
+ *   - token_out != NULL: stores its final threshold into slot c of the NEXT GPU's mailbox (peer pointer: the store travels
+ *                        over NVLink) and releases out_seq there (st.release.sys).
+ * No receive / send kernel, no host involvement per hop.  A wait of more than 10 s sets bit 8 of *error_flag instead of
+ * hanging.  With both tokens NULL this is hiast_ias_threshold_scan.  Sequence numbers must grow along the ring.          */
+HIAST_API size_t hiast_ring_mailbox_bytes(void);
+HIAST_API int hiast_ring_create(void** local_box_out, void* ipc_handle_out /* 64 bytes, host */);
+HIAST_API int hiast_ring_open(const void* ipc_handle /* 64 bytes, host */, void** peer_box_out);
+HIAST_API int hiast_ring_close(void* peer_box);
+HIAST_API int hiast_ring_destroy(void* local_box);
+HIAST_API int hiast_ias_threshold_scan_ring(uint32_t* hist, int n_groups, int C, int key_lo,
+                                  double alpha, double beta, double gamma,
+                                  double* thr_state, double* thr_groups, float* temp_groups, int* error_flag,
+                                  const void* token_in, uint64_t in_seq, void* token_out, uint64_t out_seq, void* stream);
+
 /* a5+a6+a7(sums)  :71-89, :96-99
  * plbl = conf < thr[group][label] ? 255 : label (float32 conf compared with the float64
  * threshold); per-image counts of the kept labels; per-group fixed-point (2^-32) sums of the

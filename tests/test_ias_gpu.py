@@ -435,3 +435,36 @@ def test_engine_from_lowres_logits_equals_full_resolution_path():
         e.phase_c(0, 4)
         e.mean_prob(0, 4)
     assert torch.equal(a.plbl, b.plbl) and torch.equal(a.thr_groups, b.thr_groups) and torch.equal(a.mean_state, b.mean_state)
+
+
+def test_token_ring_hand_off_inside_the_scan_kernel():
+    """hiast_ias_threshold_scan_ring on ONE GPU with the mailbox looped back to itself: the scan of window 0 publishes its final
+    thresholds (token_out), the scan of window 1 starts from the mailbox (token_in) although its thr_state holds garbage;
+    together they equal one scan over both windows.  (The two-process version over CUDA IPC is tests/test_sharded_gpu.py.)"""
+    import ctypes as C
+    from hiast_b200 import _lib
+    o = ops()
+    L = _lib.lib()
+    Cn, H, W, B, n = 19, 32, 64, 2, 12
+    g = torch.Generator().manual_seed(41)
+    logits = torch.cat([gi.diffuse_logits(g, n // 2, Cn, H, W), gi.peaked_logits(g, n // 2, Cn, H, W)]).cuda()
+    key_lo = o.ias_key_lo(Cn)
+    _, _, hist = o.ias_softmax_hist(logits, B)
+    state = torch.full((Cn,), 0.9, dtype=torch.float64, device='cuda')
+    want, _ = o.ias_threshold_scan(hist.clone(), n // B, Cn, key_lo, 0.5, 0.9, 8.0, state)
+    box, handle = C.c_void_p(), (C.c_ubyte * 64)()
+    assert L.hiast_ring_mailbox_bytes() >= 256 * 16
+    _lib.check(L.hiast_ring_create(C.byref(box), C.cast(handle, C.c_void_p)), 'ring_create')
+    try:
+        half = n // B // 2
+        s0 = torch.full((Cn,), 0.9, dtype=torch.float64, device='cuda')
+        first, _ = o.ias_threshold_scan(hist[:half].clone(), half, Cn, key_lo, 0.5, 0.9, 8.0, s0, token=(None, 0, box.value, 5))
+        s1 = torch.full((Cn,), -123.0, dtype=torch.float64, device='cuda')          # must be ignored: the token wins
+        flag = torch.zeros(1, dtype=torch.int32, device='cuda')
+        second, _ = o.ias_threshold_scan(hist[half:].clone(), n // B - half, Cn, key_lo, 0.5, 0.9, 8.0, s1, error_flag=flag,
+                                         token=(box.value, 5, None, 0))
+        assert torch.equal(torch.cat([first, second]), want)
+        assert torch.equal(s1, state) and int(flag.item()) == 0
+    finally:
+        torch.cuda.synchronize()
+        L.hiast_ring_destroy(box)

@@ -25,7 +25,7 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, slots=3, ring='peer'):
     import sys
     sys.path.insert(0, os.path.dirname(__file__))
     sys.path.insert(0, os.path.dirname(os.path.dirname(__file__)))
@@ -33,13 +33,14 @@ def _worker(rank, world, port, out_dir):
     from hiast_b200.sharded import ShardedIAS, window_images
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
+    os.environ['HIAST_RING'] = ring
     torch.cuda.set_device(rank)
     dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
     try:
         s = SPEC
         logits = torch.cat([lg for lg, _ in gi.ias_batches(s)]).cuda()
         window = 2 * s['B']
-        eng = IASEngine(s['C'], s['H'], s['W'], s['B'], s['alpha'], s['beta'], s['gamma'], s['cp_gamma'], 2 * window,
+        eng = IASEngine(s['C'], s['H'], s['W'], s['B'], s['alpha'], s['beta'], s['gamma'], s['cp_gamma'], slots * window,
                         device=torch.device('cuda', rank))
         got = {}
 
@@ -50,7 +51,14 @@ def _worker(rank, world, port, out_dir):
             i0, n = window_images(w, window, s['N'])
             return logits[i0:i0 + n]
 
-        thr, mean, statics = ShardedIAS(eng, window, s['N']).run(window_logits, on_window)
+        drv = ShardedIAS(eng, window, s['N'])
+        assert (drv.ring is not None) == (ring == 'peer'), 'hand-off mode: wanted %s' % ring
+        for rep in range(2):                              # twice: the ring's sequence numbers carry over from job to job
+            got.clear()
+            eng.thr_state.fill_(0.9)
+            eng.mean_state.zero_()
+            thr, mean, statics = drv.run(window_logits, on_window)
+        assert eng.check_errors()
         torch.cuda.synchronize()
         np.savez(os.path.join(out_dir, 'rank%d.npz' % rank), thr=thr.cpu().numpy(), mean=mean.cpu().numpy(),
                  statics=statics.cpu().numpy(), windows=np.array(sorted(got)),
@@ -60,9 +68,12 @@ def _worker(rank, world, port, out_dir):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
-def test_nccl_threshold_handoff_is_bit_identical(tmp_path):
+@pytest.mark.parametrize('slots,ring', [(3, 'peer'), (3, 'nccl'), (2, 'peer')])
+def test_threshold_handoff_is_bit_identical(slots, ring, tmp_path):
+    """Windows striped over 2-4 GPUs == the single-process oracle, with the state handed over inside the scan kernel through
+    peer memory ('peer': hiast_ias_threshold_scan_ring over CUDA IPC mailboxes) and through NCCL send / recv ('nccl')."""
     world = min(torch.cuda.device_count(), 4)
-    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), slots, ring), nprocs=world, join=True)
     s = SPEC
     oracle = oias.IASOracle(s['C'], s['alpha'], s['beta'], s['gamma'], s['cp_gamma'])
     oracle.run([(lg.cuda(), p) for lg, p in gi.ias_batches(s)])

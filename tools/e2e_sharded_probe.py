@@ -27,13 +27,14 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--windows', type=int, default=46)
     ap.add_argument('--png', action='store_true')
+    ap.add_argument('--lazy-init', action='store_true', help='init_process_group without device_id (per-pair P2P communicators)')
     args = ap.parse_args()
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (('RANK', '0'), ('WORLD_SIZE', '1'), ('LOCAL_RANK', '0')))
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        dist.init_process_group('nccl', device_id=dev)
+        dist.init_process_group('nccl', **({} if args.lazy_init else {'device_id': dev}))
     h_lr, w_lr = H // 8 + 1, W // 8 + 1
     host = torch.empty((8, C, h_lr, w_lr)).pin_memory()
     host.copy_(torch.randn(8, C, h_lr, w_lr, generator=torch.Generator().manual_seed(5)) * 4)
