@@ -271,9 +271,9 @@ def gpu_arm(args):
             a_events.append((e0, e1))
             launches['n'] += 1                      # k_softmax_hist_grs
 
-        def phase_b(self, first_image, n_images):
-            engine.phase_b(first_image, n_images)
-            launches['n'] += 2                      # k_hist_prefix + k_threshold_scan
+        def phase_b(self, first_image, n_images, **kw):
+            engine.phase_b(first_image, n_images, **kw)
+            launches['n'] += 2                      # k_hist_prefix + k_threshold_scan (token hand-off inside at N > 1)
 
         def phase_c(self, first_image, n_images):
             engine.phase_c(first_image, n_images)
@@ -351,7 +351,8 @@ def gpu_arm(args):
                        'parallelism': ('one rank, three windows in flight: phase A(j) | threshold chain(j-1) on a side stream '
                                        'beside phase C(j-2); no collective' if world == 1 else
                                        'windows striped over %d ranks, three windows in flight per rank; 19-double threshold '
-                                       'state via NCCL send/recv on the chain stream; one all-gather at the end' % world)},
+                                       'state handed over INSIDE the scan kernel through peer memory (CUDA IPC mailboxes over '
+                                       'NVLink; HIAST_RING=nccl selects NCCL send/recv); one NCCL all-gather at the end' % world)},
             'hbm_frac_of_peak': ALG_BYTES_PER_IMAGE * value / world / 1e9 / peak,
             'roofline': {'kernel': 'k_softmax_hist_grs (phase A)', 'bound': 'hbm', 'achieved': achieved, 'peak': peak,
                          'unit': 'GB/s', 'frac': achieved / peak, 'traffic': ncu_traffic(), 'peak_source': peak_src,

@@ -566,6 +566,8 @@ class _WindowPipeline:
             e.phase_a(logits, first)
             if staged_slot is not None:
                 self.gen._release_staged([staged_slot])             # consumed by the launch just queued
+        if self._ev_dir and self.cuda and self.filled == 0 and self.gen._stager is not None:
+            self._mark('h2d_first_done', self.j, self.gen._stager.copy_stream)
         self.filled += b
         self.paths += paths
         if self.filled == want or (self.n_total is None and b != e.B):
@@ -611,6 +613,8 @@ class _WindowPipeline:
 
     def _close_inner(self):
         if self._ev_dir and self.cuda:
+            if self.gen._stager is not None:
+                self._mark('h2d_last_done', self.j, self.gen._stager.copy_stream)
             self._mark('A_begin', self.j, self.main)
         import time
         t_f = time.perf_counter()
