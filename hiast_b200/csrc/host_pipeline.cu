@@ -32,8 +32,11 @@ namespace {
 
 struct Stager {
   int device = 0;
-  std::vector<cudaEvent_t> ready, freed;
-  std::vector<char> freed_valid;
+  std::vector<cudaEvent_t> ready;        // per slot: its copy has landed (recorded on the copy stream)
+  std::vector<cudaEvent_t> freed;        // per RELEASE (round robin): the consumer stream has consumed the released slots
+  std::vector<long long> slot_gen;       // per slot: generation of the release that freed it (0 = never used)
+  long long gen = 0;                     // releases so far
+  long long waited_gen = 0;              // newest generation the copy stream already waits for
 };
 
 }  // namespace
@@ -43,12 +46,10 @@ extern "C" int hiast_stager_create(int n_slots, void** handle_out) {
   std::unique_ptr<Stager> s(new Stager);
   HIAST_CUDA_TRY(cudaGetDevice(&s->device));
   s->ready.resize(n_slots);
-  s->freed.resize(n_slots);
-  s->freed_valid.assign(n_slots, 0);
-  for (int i = 0; i < n_slots; ++i) {
-    HIAST_CUDA_TRY(cudaEventCreateWithFlags(&s->ready[i], cudaEventDisableTiming));
-    HIAST_CUDA_TRY(cudaEventCreateWithFlags(&s->freed[i], cudaEventDisableTiming));
-  }
+  s->freed.resize(n_slots + 1);          // a slot's generation is at most n_slots releases old when it is pushed again
+  s->slot_gen.assign(n_slots, 0);
+  for (auto& e : s->ready) HIAST_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  for (auto& e : s->freed) HIAST_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   *handle_out = s.release();
   return HIAST_OK;
 }
@@ -68,7 +69,14 @@ extern "C" int hiast_stager_push(void* handle, int slot, void* dst_device, const
   if (!s || slot < 0 || slot >= static_cast<int>(s->ready.size()) || (nbytes && (!dst_device || !src_host)))
     return HIAST_ERR_INVALID_ARG;
   cudaStream_t cs = as_stream(copy_stream), ms = as_stream(consumer_stream);
-  if (s->freed_valid[slot]) HIAST_CUDA_TRY(cudaStreamWaitEvent(cs, s->freed[slot], 0));
+  // Releases happen in order on ONE consumer stream, so waiting for generation g covers every older one: the copy stream
+  // waits once per release it has not seen yet -- not once per copy.  (A cross-stream wait in front of every 5 MB copy
+  // kept the DMA engine from running copies back to back: 175 us instead of 95 us per copy with four ranks on the node.)
+  const long long g = s->slot_gen[slot];
+  if (g > s->waited_gen) {
+    HIAST_CUDA_TRY(cudaStreamWaitEvent(cs, s->freed[g % static_cast<long long>(s->freed.size())], 0));
+    s->waited_gen = g;
+  }
   if (nbytes) HIAST_CUDA_TRY(cudaMemcpyAsync(dst_device, src_host, nbytes, cudaMemcpyHostToDevice, cs));
   HIAST_CUDA_TRY(cudaEventRecord(s->ready[slot], cs));
   HIAST_CUDA_TRY(cudaStreamWaitEvent(ms, s->ready[slot], 0));
@@ -80,14 +88,10 @@ extern "C" int hiast_stager_release(void* handle, int first_slot, int n_slots, v
   if (!s || first_slot < 0 || n_slots < 0 || first_slot + n_slots > static_cast<int>(s->ready.size()))
     return HIAST_ERR_INVALID_ARG;
   if (n_slots == 0) return HIAST_OK;
-  // one record covers the whole run of slots: they were all consumed by work already queued on the stream
-  cudaStream_t ms = as_stream(consumer_stream);
-  HIAST_CUDA_TRY(cudaEventRecord(s->freed[first_slot], ms));
-  s->freed_valid[first_slot] = 1;
-  for (int i = 1; i < n_slots; ++i) {
-    HIAST_CUDA_TRY(cudaEventRecord(s->freed[first_slot + i], ms));
-    s->freed_valid[first_slot + i] = 1;
-  }
+  // one event for the whole run of slots: they were all consumed by work already queued on the consumer stream
+  const long long g = ++s->gen;
+  HIAST_CUDA_TRY(cudaEventRecord(s->freed[g % static_cast<long long>(s->freed.size())], as_stream(consumer_stream)));
+  for (int i = 0; i < n_slots; ++i) s->slot_gen[first_slot + i] = g;
   return HIAST_OK;
 }
 

@@ -364,7 +364,10 @@ class BasePseudoGenerator:
                 raise HiastError('staging ring exhausted')
             pipe.flush_queued()                                      # launches the queued phase A and releases its slots
         self._stage_cursor += 1
-        return st.push(slot, images, self._main_stream_ptr()), slot
+        view = st.push(slot, images, self._main_stream_ptr())
+        if pipe is not None and pipe._ev_dir and 10 <= pipe.j <= 12:
+            pipe._mark('h2d_copy', pipe.j, st.copy_stream)
+        return view, slot
 
     def _main_stream_ptr(self):
         """The current stream of the device as a void* (looked up once per run: the lookup costs ~15 us in torch)."""
