@@ -586,7 +586,9 @@ def measure_e2e(args, device, rank, world, barrier):
         t = torch.tensor([secs], dtype=torch.float64, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         secs = float(t[0])
+    lr_gbs = steps_lr * WINDOW * world * C * h_lr * w_lr * 4 / secs / 1e9
     res['from_stride8_logits'] = {'value': steps_lr * WINDOW * world / secs, 'unit': UNIT, 'steps': steps_lr,
+                                  'h2d_achieved_gbs': lr_gbs, 'h2d_frac_of_ceiling': lr_gbs / ceiling_gbs,
                                   'h2d_bytes_per_step': WINDOW * C * h_lr * w_lr * 4,
                                   'd2h_bytes_per_step': res['d2h_bytes_per_step'],
                                   'api': "same call, model returns {'logits_lr': [B,19,129,257]}: fused up-sampling + IAS"}
@@ -650,6 +652,7 @@ def measure_e2e(args, device, rank, world, barrier):
                   'note': 'host time of rank 0 inside run(): blocked on a window\'s completion / closing windows (launches, token '
                           'calls, emit) / total between the first close and the end'}
     png = {'value': steps_lr * WINDOW * world / secs, 'unit': UNIT, 'steps': steps_lr, 'files_written': n_files,
+           'h2d_frac_of_ceiling': steps_lr * WINDOW * world * C * h_lr * w_lr * 4 / secs / 1e9 / ceiling_gbs,
            'mean_file_bytes': n_bytes / max(1, n_files), 'd2h_bytes_per_step': n_bytes / steps_lr + WINDOW * C * 8,
            'files_dir': files_root('fast'), 'host_trace': host_trace,
            'api': 'same call with the PNG files written (device encoder, native writer pool with %d POSIX writers per rank, completion deferred by three windows)' % IASPseudoGenerator._default_workers()}

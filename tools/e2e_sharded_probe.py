@@ -27,6 +27,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--windows', type=int, default=46)
     ap.add_argument('--png', action='store_true')
+    ap.add_argument('--profile', action='store_true', help='cProfile of rank 0')
     ap.add_argument('--lazy-init', action='store_true', help='init_process_group without device_id (per-pair P2P communicators)')
     args = ap.parse_args()
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (('RANK', '0'), ('WORLD_SIZE', '1'), ('LOCAL_RANK', '0')))
@@ -83,7 +84,16 @@ def main():
     run(WINDOW)
     if ev_dir:
         os.environ['HIAST_PIPE_EVENTS'] = ev_dir
-    t_init, t_run, trace = run(args.windows * WINDOW)
+    if args.profile and rank == 0:
+        import cProfile
+        import pstats
+        pr = cProfile.Profile()
+        pr.enable()
+        t_init, t_run, trace = run(args.windows * WINDOW)
+        pr.disable()
+        pstats.Stats(pr).sort_stats('tottime').print_stats(16)
+    else:
+        t_init, t_run, trace = run(args.windows * WINDOW)
     print(json.dumps({'rank': rank, 'init_s': round(t_init, 4), 'run_s': round(t_run, 4), 'images_per_s_this_rank': round(args.windows * WINDOW / (t_init + t_run)),
                       'trace': {k: (round(v, 4) if isinstance(v, float) else v) for k, v in trace.items()}}), flush=True)
     if world > 1:
