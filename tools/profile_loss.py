@@ -20,7 +20,9 @@ img = torch.randint(0, 256, (4, 1024, 2048, 3), dtype=torch.uint8, device='cuda'
 lbl = torch.randint(0, 19, (4, 1024, 2048), dtype=torch.uint8, device='cuda')
 mask = torch.full((4, 1024, 2048), 255, dtype=torch.uint8, device='cuda')
 dlbl = (torch.arange(4 * 1024 * 2048, device='cuda') // 5000 % 19).to(torch.uint8).view(4, 1024, 2048)
+gw = torch.tensor([1.0, 0.1, 1.0, 0.5], device='cuda')
 for _ in range(3):
+    ops.st_loss_fused(z, t, plbl, gw, 'ignored', grad=grad)
     ops.st_loss_fwd(z, t, plbl, 'ignored')
     ops.st_loss_bwd(z, t, plbl, scales, 'ignored', grad=grad)
     ops.confusion_matrix(pred, tgt, 19)
