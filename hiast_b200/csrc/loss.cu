@@ -1152,7 +1152,9 @@ extern "C" int hiast_st_loss_fused(const float* z, const float* t, const void* p
   Partial* parts = reinterpret_cast<Partial*>(static_cast<char*>(workspace) + 64);
   HIAST_CUDA_TRY(cudaMemsetAsync(lc, 0, sizeof(LabelCounts), st));
   const long long n = static_cast<long long>(B) * HW;
-  const int cgrid = static_cast<int>(std::max<long long>(1, std::min<long long>((n / 16 + 255) / 256, sm_count() * 4)));
+  // two or three 16-byte loads per thread, every load of a thread in flight together: a latency-bound 8 MB read
+  const long long vecs = plbl_bytes == 8 ? n / 2 : n / 16;
+  const int cgrid = static_cast<int>(std::max<long long>(1, std::min<long long>((vecs + 255) / 256, sm_count() * 8)));
   k_label_count<<<cgrid, 256, 0, st>>>(plbl, plbl_bytes, n, lc);
   HIAST_CHECK_LAUNCH();
   const int grid = std::min(loss_grid(n), sm_count() * 2);

@@ -581,7 +581,9 @@ class Stager:
 
     def __init__(self, n_slots, slot_bytes, device, copy_stream):
         self.n_slots, self.device, self.copy_stream = int(n_slots), torch.device(device), copy_stream
-        self.slot_bytes = (int(slot_bytes) + 255) // 256 * 256
+        # slots are packed back to back (4-byte granularity): consecutive stride-8 batches of a window form ONE contiguous
+        # [n, C, h, w] tensor in the ring, so their single phase-A launch needs no torch.cat (a 161 MB copy per window)
+        self.slot_bytes = (int(slot_bytes) + 3) // 4 * 4
         self.ring = torch.empty(self.n_slots * self.slot_bytes, dtype=torch.uint8, device=self.device)
         self._busy = [False] * self.n_slots
         h = C.c_void_p()

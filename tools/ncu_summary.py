@@ -69,26 +69,26 @@ def main():
     for rep in args.reports:
         allres[rep.split('/')[-1]] = read(rep)
     json.dump(allres, open(args.out + '.json', 'w'), indent=1)
+    cols = [(rep, i, r) for rep, rs in allres.items() for i, r in enumerate(rs)]       # one column per captured launch
     with open(args.out + '.md', 'w') as f:
-        f.write('# ncu summary (`ncu --set full --clock-control none --import-source on`, one launch, %d maps of '
-                '19x1024x2048)\n\n%s\n\n' % (args.images, args.note))
+        f.write('# ncu summary (`ncu --set full --clock-control none --import-source on`; per-launch times under ncu are cold-cache '
+                'and serialised)\n\n%s\n\n' % args.note)
         names = [n for _, n in KEYS]
-        f.write('| metric | ' + ' | '.join(allres) + ' |\n|---|' + '---|' * len(allres) + '\n')
-        f.write('| kernel | ' + ' | '.join(r[0]['kernel'][:48] for r in allres.values()) + ' |\n')
+        f.write('| metric | ' + ' | '.join('%s #%d' % (rep.replace('.ncu-rep', ''), i) for rep, i, _ in cols) + ' |\n|---|' + '---|' * len(cols) + '\n')
+        f.write('| kernel | ' + ' | '.join(r['kernel'].split('(')[0][:40] for _, _, r in cols) + ' |\n')
         for n in names:
             cells = []
-            for r in allres.values():
-                v = r[0].get(n)
+            for _, _, r in cols:
+                v = r.get(n)
                 if v is None:
                     cells.append('')
                 elif n == 'duration':
                     cells.append('%.1f us' % (v * 1e6))
                 elif n in ('dram_read', 'dram_write'):
-                    cells.append('%.1f MB (%.2f MB/image)' % (v / 1e6, v / 1e6 / args.images))
+                    cells.append('%.1f MB' % (v / 1e6))
                 else:
                     cells.append('%.3g' % v)
             f.write('| %s | ' % n + ' | '.join(cells) + ' |\n')
-        f.write('\nAlgorithmic bytes: 161.48 MB/image (77 B/px); unavoidable extra: +5 B/px conf/label spill = 10.5 MB/image.\n')
     print(open(args.out + '.md').read())
 
 
