@@ -528,22 +528,31 @@ def measure_e2e(args, device, rank, world, barrier):
         gen.run()
         return gen
 
+    # PCIe throughput on these VMs varies from run to run on the same box (the same call measured 341 and 259 images/s
+    # back to back): every e2e leg is timed REPS times, the fastest repetition is reported, all are listed.
+    REPS = 2
+
+    def timed(fn):
+        """Seconds of fn() as the slowest rank sees them: max(wall clock, CUDA events), max over ranks."""
+        barrier()
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        secs = max(time.perf_counter() - t0, e0.elapsed_time(e1) / 1e3)
+        if world > 1:
+            t = torch.tensor([secs], dtype=torch.float64, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            secs = float(t[0])
+        return secs
+
     run(WINDOW)                                    # warm-up
-    barrier()
-    t0 = time.perf_counter()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    run(steps * WINDOW)
-    e1.record()
-    torch.cuda.synchronize()
-    wall = time.perf_counter() - t0
-    secs = max(wall, e0.elapsed_time(e1) / 1e3)
-    if world > 1:
-        import torch.distributed as dist
-        t = torch.tensor([secs], dtype=torch.float64, device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        secs = float(t[0])
+    reps_full = [timed(lambda: run(steps * WINDOW)) for _ in range(REPS)]
+    secs = min(reps_full)
     res = {'value': steps * WINDOW * world / secs, 'unit': UNIT, 'steps': steps,
+           'repetitions_images_per_s': [steps * WINDOW * world / t for t in reps_full], 'reported': 'fastest of %d repetitions' % REPS,
            'h2d_ceiling_gbs': ceiling_gbs, 'h2d_achieved_gbs': steps * WINDOW * world * C * H * W * 4 / secs / 1e9,
            'h2d_frac_of_ceiling': steps * WINDOW * world * C * H * W * 4 / secs / 1e9 / ceiling_gbs,
            'h2d_bytes_per_step': WINDOW * C * H * W * 4,
@@ -576,18 +585,11 @@ def measure_e2e(args, device, rank, world, barrier):
 
     steps_lr = max(4 * steps, 46)             # 46 windows = 2944 images, the size of the Cityscapes train set (2975)
     run_lr(WINDOW)
-    barrier()
-    t0 = time.perf_counter()
-    run_lr(steps_lr * WINDOW)
-    torch.cuda.synchronize()
-    secs = time.perf_counter() - t0
-    if world > 1:
-        import torch.distributed as dist
-        t = torch.tensor([secs], dtype=torch.float64, device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        secs = float(t[0])
+    reps_lr = [timed(lambda: run_lr(steps_lr * WINDOW)) for _ in range(REPS)]
+    secs = min(reps_lr)
     lr_gbs = steps_lr * WINDOW * world * C * h_lr * w_lr * 4 / secs / 1e9
     res['from_stride8_logits'] = {'value': steps_lr * WINDOW * world / secs, 'unit': UNIT, 'steps': steps_lr,
+                                  'repetitions_images_per_s': [steps_lr * WINDOW * world / t for t in reps_lr],
                                   'h2d_achieved_gbs': lr_gbs, 'h2d_frac_of_ceiling': lr_gbs / ceiling_gbs,
                                   'h2d_bytes_per_step': WINDOW * C * h_lr * w_lr * 4,
                                   'd2h_bytes_per_step': res['d2h_bytes_per_step'],
@@ -640,18 +642,23 @@ def measure_e2e(args, device, rank, world, barrier):
             shutil.rmtree(d, ignore_errors=True)
 
     run_png(WINDOW, 'device')
-    barrier()
-    secs, n_files, n_bytes = run_png(steps_lr * WINDOW, 'device')
-    if world > 1:
-        t = torch.tensor([secs], dtype=torch.float64, device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        secs = float(t[0])
+    reps_png = []
+    for _ in range(REPS):
+        barrier()
+        secs_k, n_files, n_bytes = run_png(steps_lr * WINDOW, 'device')
+        if world > 1:
+            t = torch.tensor([secs_k], dtype=torch.float64, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            secs_k = float(t[0])
+        reps_png.append(secs_k)
+    secs = min(reps_png)
     assert n_files == steps_lr * WINDOW
     tr = dict(last_trace)
     host_trace = {'rank0_seconds': {k: round(v, 4) for k, v in tr.items() if k in ('wait_completion', 'close', 'total', 'collect')},
                   'note': 'host time of rank 0 inside run(): blocked on a window\'s completion / closing windows (launches, token '
                           'calls, emit) / total between the first close and the end'}
     png = {'value': steps_lr * WINDOW * world / secs, 'unit': UNIT, 'steps': steps_lr, 'files_written': n_files,
+           'repetitions_images_per_s': [steps_lr * WINDOW * world / t for t in reps_png],
            'h2d_frac_of_ceiling': steps_lr * WINDOW * world * C * h_lr * w_lr * 4 / secs / 1e9 / ceiling_gbs,
            'mean_file_bytes': n_bytes / max(1, n_files), 'd2h_bytes_per_step': n_bytes / steps_lr + WINDOW * C * 8,
            'files_dir': files_root('fast'), 'host_trace': host_trace,
