@@ -43,13 +43,22 @@ def register_all():
 
 
 def install_into(reference_registries, suffix=''):
-    """Put the B200 implementations into the reference's own registry module.
+    """Put the B200 implementations into the reference's own registry module, and make the reference's backbone / dataset /
+    trainer entries visible to this package's registries.
 
-    ``suffix=''`` overrides the reference's entries (same keys); a non-empty suffix (e.g. ``'_B200'``)
-    adds new keys next to them (``PSEUDO_POLICY['IAS_B200']``).
+    ``suffix=''`` overrides the reference's entries (same keys); a non-empty suffix (e.g. ``'_B200'``) adds new keys next to
+    them (``PSEUDO_POLICY['IAS_B200']``).  Either way ``SEG_MODEL``, ``DATASET``, ``TRAINER`` and the ``MODEL`` / ``LOSS`` /
+    ``PREPROCESSOR`` entries this package does not provide are copied FROM the reference's registries, so that
+    ``MODEL['SelfTrainingSegmentor'](cfg)`` finds its backbone through ``SEG_MODEL[cfg.model.seg_model.type]`` and a
+    one-argument ``PSEUDO_POLICY[type](cfg)`` finds the target dataset class (``utils.load_model`` and
+    ``generate_pseudo_labels.py`` keep working with the overridden keys).
     """
     register_all()
     for name, reg in _ALL.items():
         target = getattr(reference_registries, name)
-        for key, obj in reg.items():
-            dict.__setitem__(target, key + suffix, obj)
+        for key, obj in list(target.items()):              # the reference's entries -> this package (never overriding ours)
+            if key not in reg:
+                dict.__setitem__(reg, key, obj)
+        for key, obj in list(reg.items()):
+            if obj is not target.get(key):                 # ours -> the reference
+                dict.__setitem__(target, key + suffix, obj)

@@ -21,7 +21,7 @@ from torch.nn import functional as F
 
 from ._lib import TERM_CE, TERM_CST, TERM_ENT, TERM_KLD
 from .losses import IGNORE, GradHint, fused_terms
-from .registry import LOSS, MODEL
+from .registry import LOSS, MODEL, SEG_MODEL
 
 # What build_region_weight hands to _kld / _entropy instead of a dense [B,C,H,W] tensor.
 RegionWeight = namedtuple('RegionWeight', ['plbl', 'region'])
@@ -58,6 +58,13 @@ class SelfTrainingSegmentor(nn.Module):
     def __init__(self, cfg, seg_model=None):
         super().__init__()
         self.cfg = cfg
+        if seg_model is None:
+            # ``build_seg_model(cfg)`` (sseg/models/modules/seg_models/__init__.py:5-8) =
+            # SEG_MODEL[cfg.model.seg_model.type](num_classes=..., output_dim=...): the backbone is the host project's
+            # (registered there, or brought in by registry.install_into); without one the segmentor only computes losses
+            sm = getattr(getattr(cfg, 'model', None), 'seg_model', None)
+            if sm is not None and getattr(sm, 'type', None) in SEG_MODEL:
+                seg_model = SEG_MODEL[sm.type](num_classes=cfg.dataset.num_classes, output_dim=getattr(sm, 'output_dim', 256))
         self.seg_model = seg_model
         seg_type = cfg.model.predictor.seg_loss.type if hasattr(cfg.model.predictor.seg_loss, 'type') else 'CE'
         self.seg_loss_fun = LOSS[seg_type]

@@ -143,3 +143,34 @@ def test_one_argument_constructor_resolves_model_and_dataset_through_the_registr
     with pytest.raises(RuntimeError, match="MODEL\\['Nope'\\] is not registered"):
         PSEUDO_POLICY['IAS'](CfgNode({'dataset': {'num_classes': 7}, 'model': {'type': 'Nope'},
                                       'pseudo_policy': {'resume_from': None, 'save_dir': str(tmp_path / 'x')}}), device='cpu')
+
+
+def test_install_into_overriding_keys_keeps_the_reference_script_working():
+    """registry.install_into(reference_registries, suffix='') overrides 'IAS', 'SelfTrainingSegmentor', ... in the
+    reference's registries AND brings the reference's backbone / dataset entries into this package's, so that
+    MODEL['SelfTrainingSegmentor'](cfg) builds its backbone through SEG_MODEL like build_seg_model(cfg) does."""
+    from types import SimpleNamespace
+    import hiast_b200
+    from hiast_b200 import registry as ours
+
+    class Backbone(torch.nn.Module):
+        def __init__(self, num_classes, output_dim):
+            super().__init__()
+            self.args = (num_classes, output_dim)
+
+    ref = SimpleNamespace(**{name: ours.Registry() for name in ours._ALL})
+    ref.SEG_MODEL.register('ToyNet_for_install_test', Backbone)
+    ref.MODEL.register('SelfTrainingSegmentor', object)           # the reference's own entry, to be overridden
+    ref.PSEUDO_POLICY.register('IAS', object)
+    try:
+        ours.install_into(ref, suffix='')
+        assert ref.PSEUDO_POLICY['IAS'] is ours.PSEUDO_POLICY['IAS'] and ref.PSEUDO_POLICY['IAS'] is not object
+        assert ref.MODEL['SelfTrainingSegmentor'] is ours.MODEL['SelfTrainingSegmentor']
+        assert ours.SEG_MODEL['ToyNet_for_install_test'] is Backbone
+        cfg = default_cfg()
+        cfg.model.seg_model.type = 'ToyNet_for_install_test'
+        cfg.dataset.num_classes = 7
+        seg = ref.MODEL['SelfTrainingSegmentor'](cfg)
+        assert isinstance(seg.seg_model, Backbone) and seg.seg_model.args == (7, 256)
+    finally:
+        dict.pop(ours.SEG_MODEL, 'ToyNet_for_install_test', None)
