@@ -54,6 +54,7 @@ def parse_args():
     ap.add_argument('--e2e-steps', type=int, default=4)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-extra', action='store_true', help='skip the legs for BASELINE configs[2], [3], [4]')
+    ap.add_argument('--extra-timeout', type=int, default=240, help='seconds after which the extra legs are abandoned (the headline line is printed without them)')
     ap.add_argument('--cpu-images', type=int, default=8)
     return ap.parse_args()
 
@@ -331,12 +332,7 @@ def gpu_arm(args):
     # ---- e2e through the reference-facing API with host buffers (every rank its own replica of the call)
     e2e = measure_e2e(args, device, rank, world, barrier)
 
-    extra = None
-    if not args.no_extra:
-        del pool
-        torch.cuda.empty_cache()
-        extra = measure_extra(device, rank, world, barrier)
-
+    line = None
     if rank == 0:
         peak, peak_src = peaks()
         achieved = ALG_BYTES_PER_IMAGE * WINDOW / (a_ms / 1e3) / 1e9
@@ -365,13 +361,40 @@ def gpu_arm(args):
         }
         if parity is not None:
             line['parity'] = parity
-        if extra is not None:
-            line['extra'] = extra
         if world == 1 and not args.no_cpu_baseline:
             v, secs, threads, kind = run_cpu_arm(args.cpu_images)
             line['cpu_baseline'] = {
                 'value': v, 'unit': UNIT, 'cores': threads, 'kind': kind, 'host_cpus': os.cpu_count(), 'note': CPU_NOTE[kind],
                 'sample': '%d maps of 19x1024x2048, batch 2 (%.1f s of host work); PNG write excluded' % (args.cpu_images, secs)}
+
+    # The legs for the other BASELINE configs come last and must never cost the headline: a watchdog prints the line without them
+    # (and ends the process) if they hang -- a rank that dropped out of a collective would otherwise block the others for good.
+    if not args.no_extra:
+        done = threading.Event()
+
+        def watchdog():
+            if not done.wait(args.extra_timeout):
+                if rank == 0:
+                    line['extra'] = {'error': 'the extra legs did not finish within %d s' % args.extra_timeout}
+                    print(json.dumps(line), flush=True)
+                os._exit(0)
+        threading.Thread(target=watchdog, daemon=True).start()
+        del pool
+        torch.cuda.empty_cache()
+        try:
+            extra = measure_extra(device, rank, world, barrier)
+        except Exception as exc:                          # noqa: BLE001
+            extra = {'error': '%s: %s' % (type(exc).__name__, exc)}
+            if world > 1:                                 # the other ranks may sit in a collective: end everybody, headline first
+                if rank == 0:
+                    line['extra'] = extra
+                    print(json.dumps(line), flush=True)
+                time.sleep(1.0)
+                os._exit(0)
+        done.set()
+        if rank == 0:
+            line['extra'] = extra
+    if rank == 0:
         print(json.dumps(line), flush=True)
     if parity is not None and not (parity['thr_equal'] and parity['plbl_sha_equal']):
         raise SystemExit('sharded run differs from the single-rank replay: %r' % (parity,))
