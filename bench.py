@@ -39,6 +39,7 @@ sys.path.insert(0, ROOT)
 C, H, W, GROUP = 19, 1024, 2048, 2
 ALPHA, BETA, GAMMA, CP_GAMMA = 0.5, 0.9, 8.0, 0.99
 WINDOW = 64                      # images per step per GPU
+RESERVE_SMS = 0                  # see gpu_arm
 ALG_BYTES_PER_IMAGE = H * W * (4 * C + 1)     # read logits + write uint8 label = 161 480 704 B
 METRIC = 'pseudo-labelled 19x1024x2048 images/s'
 UNIT = 'images/s'
@@ -248,6 +249,9 @@ def gpu_arm(args):
     pool = make_pool(device, args.dist, WINDOW)
     # three window slots: phase A of window j, the threshold chain of j-1 and phase C of j-2 are in flight together
     engine = IASEngine(C, H, W, GROUP, ALPHA, BETA, GAMMA, CP_GAMMA, 3 * WINDOW, device=device)
+    # SMs phase A leaves free for the threshold chain and phase C of the window before (they then run CONCURRENTLY with phase A
+    # on the chain stream instead of between two launches; hiast_b200/sharded.py, "concurrent" schedule).  0 = serial schedule.
+    engine.reserve_sms = int(os.environ.get('HIAST_RESERVE_SMS', RESERVE_SMS))
 
     def barrier():
         torch.cuda.synchronize()

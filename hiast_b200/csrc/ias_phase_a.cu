@@ -908,7 +908,7 @@ int launch_phase_a_ldg(PhaseAArgs a, cudaStream_t st) {
 
 // Shared-memory budget of the group-resident kernel: 227 KB per CTA minus the cp.async staging buffers.
 template <int C, int HINT, int STATIC = 0>
-int launch_phase_a_gr(PhaseAArgs a, cudaStream_t st) {
+int launch_phase_a_gr(PhaseAArgs a, cudaStream_t st, int reserve_sms = 0) {
   constexpr size_t kStage = sizeof(float4) * C * kThreadsG;
   constexpr size_t kBudget = 227 * 1024 - 1024;   // static shared memory + reserve
   static_assert(kStage + 4096 < kBudget, "staging does not fit");
@@ -945,7 +945,10 @@ int launch_phase_a_gr(PhaseAArgs a, cudaStream_t st) {
   ga.a = a;
   if constexpr (STATIC) {
     HIAST_TRY(ensure_dyn_smem(k_softmax_hist_grs<C, HINT>, kBudget));
-    const int grid_s = static_cast<int>(std::min<long long>(sms, a.n_tiles));
+    // reserve_sms: SMs left WITHOUT a phase-A CTA.  A CTA of this kernel takes a whole SM (512 threads x 128 registers), so nothing
+    // else can share an SM with it; the SMs left free are where the threshold chain and phase C of the windows before run
+    // CONCURRENTLY with this launch (hiast_b200/sharded.py) instead of between two launches.
+    const int grid_s = static_cast<int>(std::min<long long>(std::max(1, sms - std::max(0, reserve_sms)), a.n_tiles));
     k_softmax_hist_grs<C, HINT><<<grid_s, kThreadsG, smem, st>>>(ga);
     HIAST_CHECK_LAUNCH();
     return HIAST_OK;
@@ -971,11 +974,13 @@ int launch_phase_a_gr(PhaseAArgs a, cudaStream_t st) {
 constexpr int kDefaultHistMode = 83;
 
 template <int C>
-int launch_phase_a(const PhaseAArgs& a, int mode, cudaStream_t st) {
+int launch_phase_a(const PhaseAArgs& a, int mode_and_reserve, cudaStream_t st) {
+  int mode = mode_and_reserve & 0xff;
+  const int reserve_sms = (mode_and_reserve >> 8) & 0xff;
   if (mode == 0) mode = kDefaultHistMode;
   switch (mode) {
     case 1: return launch_phase_a_ldg<C, 1, 4>(a, st);        // plain kernel, one global RED per pixel: the cross-check
-    case 83: return launch_phase_a_gr<C, 0, 1>(a, st);        // the product kernel
+    case 83: return launch_phase_a_gr<C, 0, 1>(a, st, reserve_sms);   // the product kernel
 #ifdef HIAST_DEV_VARIANTS
     // measured and dropped (profiles/): compiled only into the development build
     case 2: return launch_phase_a_ldg<C, 2, 4>(a, st);
@@ -1024,7 +1029,7 @@ extern "C" int hiast_ias_softmax_hist(const float* logits, int n_images, int C, 
   if (!logits || !conf || !label || !hist) return HIAST_ERR_INVALID_ARG;
   if (n_images < 0 || C < 1 || C > HIAST_MAX_CLASSES || H < 1 || W < 1 || group_size < 1) return HIAST_ERR_INVALID_ARG;
   if (key_lo < 0 || key_lo > HIAST_KEY_ONE) return HIAST_ERR_INVALID_ARG;
-  if (hist_mode < 0 || hist_mode > 99) return HIAST_ERR_INVALID_ARG;
+  if (hist_mode < 0 || (hist_mode & 0xff) > 99 || (hist_mode >> 16) != 0) return HIAST_ERR_INVALID_ARG;
   cudaStream_t st = as_stream(stream);
   const int n_groups = (n_images + group_size - 1) / group_size;
   if (!accumulate) HIAST_CUDA_TRY(cudaMemsetAsync(hist, 0, hiast_ias_hist_bytes(n_groups, C, key_lo), st));

@@ -54,6 +54,9 @@ class IASEngine:
         self.fused_ws = ops.ias_fused_workspace(n, self.B, dev)
         self.groups_in_flight = 0
         self.keep_spill = False
+        # SMs phase A leaves free (its CTAs take whole SMs): the sharded driver runs the threshold chain and phase C of the
+        # window before on them, CONCURRENTLY with phase A of the next window (sharded.ShardedIAS, "concurrent" schedule)
+        self.reserve_sms = 0
 
     # ------------------------------------------------------------------ phases
     def _groups(self, n_images):
@@ -69,7 +72,7 @@ class IASEngine:
         g0 = first_image // self.B
         ops.ias_softmax_hist(logits, self.B, self.key_lo, self.conf[first_image:first_image + n],
                              self.label[first_image:first_image + n], self.hist[g0:g0 + self._groups(n)],
-                             accumulate=False, hist_mode=self.hist_mode)
+                             accumulate=False, hist_mode=self.hist_mode | (int(self.reserve_sms) << 8))
 
     def phase_a_lowres(self, logits_lr, first_image=0):
         """Phase A from the network's LOW-RESOLUTION logits f32 [n,C,h,w]: the bilinear up-sampling to (H,W) of

@@ -189,6 +189,8 @@ class ShardedIAS:
         k = max(len(wins), 1)
         self._stash_conf = torch.zeros((k, gw, e.C), dtype=torch.int64, device=dev)
         self._stash_counts = torch.zeros((k, self.window_size, e.C), dtype=torch.int64, device=dev)
+        if self.cuda and self.n_slots >= 3 and int(getattr(e, 'reserve_sms', 0) or 0) > 0:
+            return self._run_concurrent(window_logits, on_window)
         lag = self.n_slots - 2                    # windows between a window's chain and its outputs
         main = torch.cuda.current_stream(e.device) if self.cuda else None
         b_done = c_done = 0
@@ -220,6 +222,50 @@ class ShardedIAS:
         advance(len(wins), final=True)
         return self.finish_state()
 
+    def _run_concurrent(self, window_logits, on_window):
+        """Schedule with SMs reserved from phase A (``engine.reserve_sms`` > 0): a phase-A CTA takes a whole SM, so the launch
+        leaves ``reserve_sms`` SMs empty, and the chain stream runs the scan (token hand-off inside) AND phase C of window j there
+        while phase A of window j+1 streams on the others:
+
+            main stream    A(j) .......... A(j+1) .......... A(j+2) ...        (A(j+3) waits until C(j) has left its slot)
+            chain stream         scan(j) C(j)       scan(j+1) C(j+1)
+
+        Phase C moves 6 B/px against phase A's 81: it fits in phase A's shadow on a handful of SMs, and its traffic fills the DRAM
+        cycles phase A leaves idle instead of being queued between two launches."""
+        e = self.engine
+        main = torch.cuda.current_stream(e.device)
+        ev_c = [None] * self.n_slots
+        for j, w in enumerate(self.my_windows):
+            s = j % self.n_slots
+            if ev_c[s] is not None:
+                main.wait_event(ev_c[s])                  # window j-3 has left this slot
+            logits = window_logits(w)
+            n = self._n(j)
+            if logits.shape[0] != n:
+                raise ValueError('window %d must hold %d images, got %d' % (w, n, logits.shape[0]))
+            e.phase_a(logits, self._slot(j))
+            self.ev_a[s].record(main)
+            self.side.wait_event(self.ev_a[s])
+            with torch.cuda.stream(self.side):
+                self._chain_body(j)
+                self._outputs(j, None, on_window)
+                ev_c[s] = torch.cuda.Event()
+                ev_c[s].record(self.side)
+        return self.finish_state()
+
+    def _chain_body(self, j):
+        e = self.engine
+        w = self.my_windows[j]
+        ring = self.world > 1
+        if self.ring is not None:                     # hand-off fused into the scan kernel, over peer memory
+            e.phase_b(self._slot(j), self._n(j), token=self.ring.token(w, self.n_windows_total))
+            return
+        if ring and w > 0:
+            dist.recv(e.thr_state, src=self._global((self.rank - 1) % self.world), group=self.pg)
+        e.phase_b(self._slot(j), self._n(j))
+        if ring and w < self.n_windows_total - 1:
+            dist.send(e.thr_state, dst=self._global((self.rank + 1) % self.world), group=self.pg)
+
     def _chain(self, j, latest_closed):
         e = self.engine
         w = self.my_windows[j]
@@ -246,7 +292,7 @@ class ShardedIAS:
     def _outputs(self, j, main, on_window):
         e = self.engine
         slot, n = self._slot(j), self._n(j)
-        if self.cuda:
+        if self.cuda and main is not None:
             main.wait_event(self.ev_b[j % self.n_slots])
         e.phase_c(slot, n)
         g0, g = slot // e.B, (n + e.B - 1) // e.B

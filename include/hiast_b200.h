@@ -80,7 +80,9 @@ HIAST_API size_t hiast_ias_hist_bytes(int n_groups, int C, int key_lo);
  * softmax over C + first-index max (bit-exact with ATen's CUDA softmax -> max(dim=1)), fused
  * with the per-(group, class) histogram of fp16_rn(conf) bit patterns.  Image i belongs to
  * group i / group_size (the reference's DataLoader batch).  `accumulate` = 0 zeroes `hist`
- * first.  `hist_mode` selects the histogram strategy (0 = library default).
+ * first.  `hist_mode`: bits 0-7 select the histogram strategy (0 = library default); bits 8-15 = number of SMs the
+ * default kernel leaves WITHOUT one of its CTAs (its CTAs take whole SMs; the free SMs are where a caller runs the
+ * threshold scan and the mask pass of earlier windows concurrently on another stream).
  *   logits f32 [n_images,C,H,W];  conf f32 [n_images,H,W];  label u8 [n_images,H,W]          */
 HIAST_API int hiast_ias_softmax_hist(const float* logits, int n_images, int C, int H, int W,
                            int group_size, int key_lo, int accumulate, int hist_mode,
