@@ -39,7 +39,7 @@ sys.path.insert(0, ROOT)
 C, H, W, GROUP = 19, 1024, 2048, 2
 ALPHA, BETA, GAMMA, CP_GAMMA = 0.5, 0.9, 8.0, 0.99
 WINDOW = 64                      # images per step per GPU
-RESERVE_SMS = 0                  # see gpu_arm
+RESERVE_SMS = 12                 # SMs phase A leaves to the threshold chain and phase C (see gpu_arm)
 ALG_BYTES_PER_IMAGE = H * W * (4 * C + 1)     # read logits + write uint8 label = 161 480 704 B
 METRIC = 'pseudo-labelled 19x1024x2048 images/s'
 UNIT = 'images/s'
@@ -348,9 +348,12 @@ def gpu_arm(args):
                        'images_per_step_per_gpu': WINDOW, 'images_total': images, 'alpha': ALPHA, 'beta': BETA,
                        'gamma': GAMMA, 'distribution': args.dist, 'resident_pool_maps': WINDOW,
                        'l2': 'inputs exceed L2 (10.2 GB streamed per step)',
-                       'parallelism': ('one rank, three windows in flight: phase A(j) | threshold chain(j-1) on a side stream '
-                                       'beside phase C(j-2); no collective' if world == 1 else
-                                       'windows striped over %d ranks, three windows in flight per rank; 19-double threshold '
+                       'reserved_sms': engine.reserve_sms,
+                       'parallelism': ('one rank: phase A(j+1) on %d SMs while the threshold chain and phase C of window j run on the '
+                                       'other %d (chain stream); no collective' % (148 - engine.reserve_sms, engine.reserve_sms)
+                                       if world == 1 else
+                                       'windows striped over %d ranks; per rank phase A(j+1) beside chain + phase C of window j on '
+                                       'reserved SMs; 19-double threshold '
                                        'state handed over INSIDE the scan kernel through peer memory (CUDA IPC mailboxes over '
                                        'NVLink; HIAST_RING=nccl selects NCCL send/recv); one NCCL all-gather at the end' % world)},
             'hbm_frac_of_peak': ALG_BYTES_PER_IMAGE * value / world / 1e9 / peak,

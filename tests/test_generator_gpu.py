@@ -130,8 +130,11 @@ def test_reference_method_surface(tmp_path):
     assert sorted(os.listdir(str(tmp_path / 'pl'))) == ['a_pseudo_label.png', 'b_pseudo_label.png']
 
 
-def test_windowed_ring_driver_single_rank_equals_oracle():
-    """ShardedIAS with world_size 1 (the bench path): windows of 2 groups, double-buffered engine."""
+@pytest.mark.parametrize('slots,reserve', [(2, 0), (3, 0), (3, 8), (3, 40)])
+def test_windowed_ring_driver_single_rank_equals_oracle(slots, reserve):
+    """ShardedIAS with world_size 1 (the bench path), windows of 2 groups: two slots (outputs behind the chain), three slots
+    (chain of window j-1 beside the outputs of j-2) and the CONCURRENT schedule (reserve > 0: phase A leaves SMs free, scan
+    and phase C of window j run there on the chain stream while phase A of window j+1 runs)."""
     from hiast_b200.ias_engine import IASEngine
     from hiast_b200.sharded import ShardedIAS, window_images
     spec = gi.IAS_SPECS['ias_small']
@@ -139,7 +142,8 @@ def test_windowed_ring_driver_single_rank_equals_oracle():
     logits = torch.cat([lg for lg, _ in batches]).cuda()
     window = 2 * spec['B']
     eng = IASEngine(spec['C'], spec['H'], spec['W'], spec['B'], spec['alpha'], spec['beta'], spec['gamma'],
-                    spec['cp_gamma'], 2 * window)
+                    spec['cp_gamma'], slots * window)
+    eng.reserve_sms = reserve
     got = {}
 
     def on_window(w, plbl, counts, thr_groups):
@@ -150,6 +154,7 @@ def test_windowed_ring_driver_single_rank_equals_oracle():
         return logits[i0:i0 + n]
 
     thr, mean, statics = ShardedIAS(eng, window, spec['N'], 0, 1).run(window_logits, on_window)
+    torch.cuda.synchronize()
     oracle = oias.IASOracle(spec['C'], spec['alpha'], spec['beta'], spec['gamma'], spec['cp_gamma'])
     oracle.run([(lg.cuda(), p) for lg, p in batches])
     assert np.array_equal(thr.cpu().numpy(), oracle.class_threshold)

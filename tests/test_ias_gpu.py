@@ -468,3 +468,36 @@ def test_token_ring_hand_off_inside_the_scan_kernel():
     finally:
         torch.cuda.synchronize()
         L.hiast_ring_destroy(box)
+
+
+def test_full_resolution_concurrent_schedule_equals_serial_schedule():
+    """The concurrent schedule (phase A on 148 - 12 SMs, scan + phase C of the window before on the rest) at full resolution:
+    12 maps in windows of 4, every threshold, label and count equal to the serial three-kernel path (which
+    test_full_resolution_engine_vs_oracle pins against the oracle)."""
+    from hiast_b200.ias_engine import IASEngine
+    from hiast_b200.sharded import ShardedIAS, window_images
+    C, H, W, B, N, window = 19, 1024, 2048, 2, 12, 4
+    g = torch.Generator(device='cuda').manual_seed(77)
+    logits = torch.randn(N, C, H, W, generator=g, device='cuda') * 3
+    low = torch.randn(N // 2, C, 32, 64, generator=g, device='cuda') * 4
+    logits[1::2] = torch.nn.functional.interpolate(low, size=(H, W), mode='bilinear', align_corners=True) + logits[1::2] / 6
+    out = {}
+    for reserve in (0, 12):
+        eng = IASEngine(C, H, W, B, 0.5, 0.9, 8.0, 0.99, 3 * window)
+        eng.reserve_sms = reserve
+        got = {}
+
+        def on_window(w, plbl, counts, thr_groups, got=got):
+            got[w] = (plbl.clone(), counts.clone(), thr_groups.clone())
+
+        thr, mean, statics = ShardedIAS(eng, window, N, 0, 1).run(
+            lambda w: logits[window_images(w, window, N)[0]:window_images(w, window, N)[0] + window_images(w, window, N)[1]], on_window)
+        torch.cuda.synchronize()
+        assert eng.check_errors()
+        out[reserve] = (got, thr.clone(), mean.clone(), statics.clone())
+    a, b = out[0], out[12]
+    assert sorted(a[0]) == sorted(b[0]) == [0, 1, 2]
+    for w in a[0]:
+        for x, y in zip(a[0][w], b[0][w]):
+            assert torch.equal(x, y), w
+    assert torch.equal(a[1], b[1]) and torch.equal(a[2], b[2]) and torch.equal(a[3], b[3])

@@ -25,7 +25,7 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, out_dir, slots=3, ring='peer'):
+def _worker(rank, world, port, out_dir, slots=3, ring='peer', reserve=0):
     import sys
     sys.path.insert(0, os.path.dirname(__file__))
     sys.path.insert(0, os.path.dirname(os.path.dirname(__file__)))
@@ -42,6 +42,7 @@ def _worker(rank, world, port, out_dir, slots=3, ring='peer'):
         window = 2 * s['B']
         eng = IASEngine(s['C'], s['H'], s['W'], s['B'], s['alpha'], s['beta'], s['gamma'], s['cp_gamma'], slots * window,
                         device=torch.device('cuda', rank))
+        eng.reserve_sms = reserve
         got = {}
 
         def on_window(w, plbl, counts, thr_groups):
@@ -68,12 +69,13 @@ def _worker(rank, world, port, out_dir, slots=3, ring='peer'):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
-@pytest.mark.parametrize('slots,ring', [(3, 'peer'), (3, 'nccl'), (2, 'peer')])
-def test_threshold_handoff_is_bit_identical(slots, ring, tmp_path):
+@pytest.mark.parametrize('slots,ring,reserve', [(3, 'peer', 0), (3, 'nccl', 0), (2, 'peer', 0), (3, 'peer', 12), (3, 'nccl', 12)])
+def test_threshold_handoff_is_bit_identical(slots, ring, reserve, tmp_path):
     """Windows striped over 2-4 GPUs == the single-process oracle, with the state handed over inside the scan kernel through
-    peer memory ('peer': hiast_ias_threshold_scan_ring over CUDA IPC mailboxes) and through NCCL send / recv ('nccl')."""
+    peer memory ('peer': hiast_ias_threshold_scan_ring over CUDA IPC mailboxes) and through NCCL send / recv ('nccl');
+    reserve > 0: the concurrent schedule (scan and phase C on the SMs phase A leaves free)."""
     world = min(torch.cuda.device_count(), 4)
-    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), slots, ring), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), slots, ring, reserve), nprocs=world, join=True)
     s = SPEC
     oracle = oias.IASOracle(s['C'], s['alpha'], s['beta'], s['gamma'], s['cp_gamma'])
     oracle.run([(lg.cuda(), p) for lg, p in gi.ias_batches(s)])
