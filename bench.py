@@ -174,6 +174,16 @@ class ClockSampler:
         self.thread = threading.Thread(target=self._read, daemon=True)
         self.thread.start()
 
+    def wait_first(self, timeout=8.0):
+        """Blocks until nvidia-smi has delivered its first sample.  Its start-up (NVML attaches to every GPU of the box, under
+        driver-wide locks) takes 0.1-0.5 s on a loaded host and stalls CUDA calls of other processes while it lasts: it must be
+        over BEFORE the timed region starts, not inside it (seen once at N = 4: 14 samples instead of 68 and one 43 ms gap in a
+        36 ms timed region)."""
+        t_end = time.perf_counter() + timeout
+        while self.proc is not None and not self.samples and time.perf_counter() < t_end and self.proc.poll() is None:
+            time.sleep(0.01)
+        return bool(self.samples)
+
     def _read(self):
         for line in self.proc.stdout:
             self.samples.append(line.strip())
@@ -295,13 +305,14 @@ def gpu_arm(args):
 
     # warm-up (also creates the NCCL p2p communicators)
     run_job(Wm, timed=False)
+    ShardedIAS(engine, WINDOW, K * world * WINDOW, rank, world).warm_collective()   # the timed job's all-gather shape
     engine.thr_state.fill_(0.9)
     engine.mean_state.zero_()
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-        time.sleep(0.05)
+        sampler.wait_first()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     wall0 = time.perf_counter()
@@ -316,8 +327,14 @@ def gpu_arm(args):
     a_ms = sum(e0.elapsed_time(e1) for e0, e1 in a_events) / max(len(a_events), 1)
     # The timed region of a short run is a few tens of milliseconds: keep the SAME load running (untimed) until the clock
     # sampler has seen it for at least 0.3 s, so that the clocks line rests on enough samples.
+    # Every rank must run the SAME number of these jobs (each one ends in a collective): rank 0's clock decides.
     t_end = time.perf_counter() + max(0.0, 0.3 - (wall1 - wall0))
-    while time.perf_counter() < t_end:
+    while True:
+        go = torch.tensor([1 if time.perf_counter() < t_end else 0], dtype=torch.int32, device=device)
+        if world > 1:
+            dist.broadcast(go, src=0)
+        if not int(go.item()):
+            break
         run_job(max(K, 10), timed=False)
         torch.cuda.synchronize()
     barrier()

@@ -301,6 +301,19 @@ class ShardedIAS:
         if on_window is not None:
             on_window(self.my_windows[j], e.plbl[slot:slot + n], e.counts[slot:slot + n], e.thr_groups[g0:g0 + g])
 
+    def warm_collective(self):
+        """Runs the end-of-job all-gather once with THIS job's shapes on zeros (collective: every rank calls it).  NCCL
+        connects the transports of an algorithm / protocol at its first use (tens of milliseconds), and which one it picks
+        depends on the message size; a caller that times the job (bench.py) or cannot afford the hiccup at the end of the
+        first job calls this beforehand."""
+        if self.world < 2:
+            return
+        e = self.engine
+        gw = self.window_size // e.B
+        kmax = max((self.n_windows_total + self.world - 1) // self.world, 1)
+        packed = torch.zeros((kmax * gw * 2 + 1, e.C), dtype=torch.int64, device=e.thr_state.device)
+        dist.all_gather([torch.empty_like(packed) for _ in range(self.world)], packed, group=self.pg)
+
     def finish_state(self):
         """ONE all-gather carries every rank's per-group confidence sums and kept-pixel counts plus its threshold state;
         every rank then replays the mean-prob EMA over all groups in global order and takes the final thresholds from the

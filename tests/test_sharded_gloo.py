@@ -47,6 +47,7 @@ def _worker(rank, world, port, out_dir, slots=2):
         window = 2 * s['B']                               # 2 groups per window -> 4 windows for 13 images
         eng = HostEngine(s['C'], s['H'], s['W'], s['B'], s['alpha'], s['beta'], s['gamma'], s['cp_gamma'], slots * window)
         drv = ShardedIAS(eng, window, s['N'])
+        drv.warm_collective()                             # collective with the job's shapes; must not disturb the job
         got = {}
 
         def on_window(w, plbl, counts, thr_groups):
