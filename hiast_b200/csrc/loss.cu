@@ -288,7 +288,34 @@ struct LossStage {
     }
     asm volatile("cp.async.commit_group;\n" ::: "memory");   // an empty group keeps the group count uniform
   }
+  // The same with the pair's position (image b, pair index p2 inside the image) carried along by the caller: the packed kernels
+  // advance it incrementally (PairPos) instead of dividing a 64-bit index three times per iteration.
+  __device__ __forceinline__ void prefetch_z_at(int b, int64_t p2) const {
+    const float2* zs = reinterpret_cast<const float2*>(a.z + static_cast<size_t>(b) * C * a.HW) + p2;
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(my_u32 + c * kThreadsL * 8),
+                   "l"(zs + static_cast<size_t>(c) * HW2) : "memory");
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  }
+  __device__ __forceinline__ void prefetch_t_at(int b, int64_t p2) const {
+    if (need_t) {
+      const float2* ts = reinterpret_cast<const float2*>(a.t + static_cast<size_t>(b) * C * a.HW) + p2;
+#pragma unroll
+      for (int c = 0; c < C; ++c)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(my_u32 + (C + c) * kThreadsL * 8),
+                     "l"(ts + static_cast<size_t>(c) * HW2) : "memory");
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");   // an empty group keeps the group count uniform
+  }
   __device__ __forceinline__ void wait_older() const { asm volatile("cp.async.wait_group 1;\n" ::: "memory"); }
+  // z of the labels' channels, read from the staging column by index (two LDS instead of a 19-deep select chain per lane);
+  // labels outside [0, C) -- ignore, out of range -- read channel 0, the callers discard the value.  Folded into the guard.
+  __device__ __forceinline__ float load_zy(int ya, int yb, float& zya, float& zyb) const {
+    zya = my[(static_cast<unsigned>(ya) < static_cast<unsigned>(C) ? ya : 0) * kThreadsL].x;
+    zyb = my[(static_cast<unsigned>(yb) < static_cast<unsigned>(C) ? yb : 0) * kThreadsL].y;
+    return fmaxf(zya, zyb);
+  }
   __device__ __forceinline__ float load_z(float (&z)[kPxL][C]) const {
     float guard = 0.f;
 #pragma unroll
@@ -392,14 +419,40 @@ __global__ void __launch_bounds__(kThreadsL, 2) k_loss_bwd(LossArgs a, const flo
 // ---- packed-pair kernels (consistency kind SoftCE, the HIAST configuration) --------------------------------------------
 // The scalar kernels above spend 1232 (backward) instructions per pixel -- up to three accurate expf per channel -- and
 // are issue-bound at 60 % of the HBM roofline.  Here the two pixels of a thread go through the f32x2 forms (packed_math.cuh):
-// the exponentials of a pass are recomputed instead of kept (registers hold z and t of both pixels), log-softmax keeps
-// ATen's operation sequence ((z - m) - log(sum), sum in channel order) so that the data-dependent SoftCE divisor
-// #(prod != 0) stays exact, and the count of non-zero products is C unless min_c |prod_c| == 0 (then it is recounted).
+// ONE exact exponential per channel and pair (the softmax sum); the entropy inner product, the sum of log-probabilities and the
+// label's log-probability fall out of that loop, and the gradient pass takes p from ex2.approx (round 2: 108 -> ~60 issued
+// instructions per channel and pair).  log-softmax keeps ATen's operation sequence ((z - m) - log(sum), sum in channel order)
+// so that the data-dependent SoftCE divisor #(prod != 0) stays exact, and the count of non-zero products is C unless
+// min_c |prod_c| == 0 (then it is recounted).
+
+// expf for the gradient pass: ex2.approx of d * log2(e) -- three issue slots per pair instead of the dozen of the exact
+// pair exponential.  |relative error| <= 2^-22 + 1.45 |d| 2^-24 (and whatever is lost below e^-87 is below 1e-37 absolute),
+// far inside the 1e-5 the gradients are held to.  The SUM of exponentials -- which decides log-softmax and through it the
+// exact SoftCE divisor #(prod != 0) -- keeps pk::exp2x.
+__device__ __forceinline__ pk::u64 exp_fast2(pk::u64 d2) {
+  float fa, fb;
+  pk::unpack(pk::mul2(d2, pk::splat(1.4426950408889634f)), fa, fb);
+  return pk::pack(pk::ex2_ftz(fa), pk::ex2_ftz(fb));
+}
+
+// lanes of a packed pair kept (mask all ones) or replaced by +0.0f (mask 0)
+__device__ __forceinline__ pk::u64 lane_mask(bool a, bool b) {
+  return (a ? 0x00000000ffffffffull : 0ull) | (b ? 0xffffffff00000000ull : 0ull);
+}
+
+// Log-softmax pieces of a pixel pair.  The softmax pass computes e_c = exp(z_c - m) once per channel anyway; the scalars
+// the forward sums need fall out of the same loop instead of a second exponential per channel:
+//   sum_c p_c logp_c (= -entropy)   = (sum_c e_c d_c) / s - log s          d_c = z_c - m
+//   sum_c logp_c     (KL to uniform) = sum_c d_c - C log s
+//   logp_y           (cross entropy) = d_y - log s                          (the very bits of (z_y - m) - log s)
+// (kernels that do not use one of them pay nothing: the dead chains are eliminated.)
 template <int C>
 struct PairLS {
   float ma, mb, sa, sb;
-  pk::u64 negm, logs2, inv2;
-  __device__ __forceinline__ void init(const float (&za)[C], const float (&zb)[C]) {
+  pk::u64 negm, logs2, inv2, h2, sl2, lpy2;
+  // (zya, zyb) = z of the labels' channels (LossStage::load_zy); a label outside [0, C) contributes logp_y = 0 like the select
+  // chain `c == y ? lp : 0` it replaces
+  __device__ __forceinline__ void init(const float (&za)[C], const float (&zb)[C], int ya, int yb, float zya, float zyb) {
     ma = za[0];
     mb = zb[0];
 #pragma unroll
@@ -408,23 +461,25 @@ struct PairLS {
       mb = fmaxf(mb, zb[c]);
     }
     negm = pk::pack(-ma, -mb);
-    pk::u64 s2 = 0;
+    pk::u64 s2 = 0, ed2 = 0, sd2 = 0;
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-      const pk::u64 e2 = pk::exp2x(pk::add2(pk::pack(za[c], zb[c]), negm));
+      const pk::u64 d2 = pk::add2(pk::pack(za[c], zb[c]), negm);
+      const pk::u64 e2 = pk::exp2x(d2);
       s2 = (c == 0) ? e2 : pk::add2(s2, e2);
+      ed2 = (c == 0) ? pk::mul2(e2, d2) : pk::fma2(e2, d2, ed2);
+      sd2 = (c == 0) ? d2 : pk::add2(sd2, d2);
     }
     pk::unpack(s2, sa, sb);
     logs2 = pk::pack(logf(sa), logf(sb));
     inv2 = pk::pack(1.0f / sa, 1.0f / sb);
+    h2 = pk::sub2(pk::mul2(ed2, inv2), logs2);
+    sl2 = pk::fma2(pk::splat(-static_cast<float>(C)), logs2, sd2);
+    lpy2 = pk::sub2(pk::add2(pk::pack(zya, zyb), negm), logs2) &
+           lane_mask(static_cast<unsigned>(ya) < static_cast<unsigned>(C), static_cast<unsigned>(yb) < static_cast<unsigned>(C));
   }
   __device__ __forceinline__ pk::u64 d(float a, float b) const { return pk::add2(pk::pack(a, b), negm); }
 };
-
-// lanes of a packed pair kept (mask all ones) or replaced by +0.0f (mask 0)
-__device__ __forceinline__ pk::u64 lane_mask(bool a, bool b) {
-  return (a ? 0x00000000ffffffffull : 0ull) | (b ? 0xffffffff00000000ull : 0ull);
-}
 
 // rare path: some -logp * t of the pixel at (b, p) is exactly zero; count the non-zero ones from global memory
 // (the registers and the staging slots have moved on)
@@ -438,32 +493,24 @@ __device__ __noinline__ int recount_nonzero(const LossArgs& a, int b, int64_t p,
   return nz;
 }
 
+// SoftCE pass over the channels of a pair (the only forward term that needs one): sum_c logp_c t_c with log-softmax in ATen's
+// operation sequence ((z - m) - log(sum)), the smallest |product| per pixel (the count of non-zero products is C unless it is
+// 0) and the teacher mass T = sum_c t_c the gradient uses.
 template <int C>
-__device__ __forceinline__ float pair_forward_softce(const float (&za)[C], const float (&zb)[C], const LossStage<C>& st,
-                                                    int ya, int yb, int region, int terms, const LossArgs& a, int b,
-                                                    int64_t p0, PixelSums& acc) {
-  PairLS<C> ls;
-  ls.init(za, zb);
-  st.wait_older();   // this pair's teacher probabilities have landed in the staging slots
-  const bool iga = (ya == HIAST_IGNORE_LABEL), igb = (yb == HIAST_IGNORE_LABEL);
-  acc.n_ign += static_cast<int>(iga) + static_cast<int>(igb);
-  acc.n_conf += static_cast<int>(!iga) + static_cast<int>(!igb);
-  const bool want_ent = (terms & HIAST_TERM_ENT) && (iga || igb);
-  const bool want_cst = (terms & HIAST_TERM_CST) != 0;
-  pk::u64 sl2 = 0, h2 = 0, sc2 = 0;
-  float lpya = 0.f, lpyb = 0.f, mna = INFINITY, mnb = INFINITY;
+struct PairCst {
+  pk::u64 sc2, T2;
+  float mna, mnb;
+  __device__ __forceinline__ void run(const float (&za)[C], const float (&zb)[C], const PairLS<C>& ls, const LossStage<C>& st) {
+    sc2 = 0;
+    T2 = 0;
+    mna = INFINITY;
+    mnb = INFINITY;
 #pragma unroll
-  for (int c = 0; c < C; ++c) {
-    const pk::u64 d2 = ls.d(za[c], zb[c]);
-    const pk::u64 lp2 = pk::sub2(d2, ls.logs2);
-    sl2 = (c == 0) ? lp2 : pk::add2(sl2, lp2);
-    float lpa, lpb;
-    pk::unpack(lp2, lpa, lpb);
-    lpya = (c == ya) ? lpa : lpya;
-    lpyb = (c == yb) ? lpb : lpyb;
-    if (want_ent) h2 = pk::fma2(pk::mul2(pk::exp2x(d2), ls.inv2), lp2, h2);
-    if (want_cst) {
-      const pk::u64 pr2 = pk::mul2(lp2, st.t2(c));   // = -(-lp * t), same magnitude and zero-ness
+    for (int c = 0; c < C; ++c) {
+      const pk::u64 lp2 = pk::sub2(ls.d(za[c], zb[c]), ls.logs2);
+      const pk::u64 t2 = st.t2(c);
+      T2 = (c == 0) ? t2 : pk::add2(T2, t2);
+      const pk::u64 pr2 = pk::mul2(lp2, t2);   // = -(-lp * t), same magnitude and zero-ness
       sc2 = (c == 0) ? pr2 : pk::add2(sc2, pr2);
       float pa, pb;
       pk::unpack(pr2, pa, pb);
@@ -471,28 +518,110 @@ __device__ __forceinline__ float pair_forward_softce(const float (&za)[C], const
       mnb = fminf(mnb, fabsf(pb));
     }
   }
-  float sla, slb, ha, hb, sca, scb;
-  pk::unpack(sl2, sla, slb);
-  pk::unpack(h2, ha, hb);
-  pk::unpack(sc2, sca, scb);
-  auto finish = [&](bool ign, int64_t p, float m, float logs, float lpy, float sl, float h, float sc, float mn) {
-    if (!ign) {
-      if (terms & HIAST_TERM_CE) acc.ce += static_cast<double>(-lpy);
-      if (terms & HIAST_TERM_KLD) acc.kld += static_cast<double>(-sl * (1.0f / C));
-    } else if (terms & HIAST_TERM_ENT) {
-      acc.ent += static_cast<double>(-h);
-    }
-    if (want_cst && in_region(region, ign)) {
-      acc.cst += static_cast<double>(-sc);
-      acc.n_nz += (mn > 0.f) ? C : recount_nonzero<C>(a, b, p, m, logs);   // a zero (or NaN) product: count the slow way
-    }
-  };
-  float logsa, logsb;
-  pk::unpack(ls.logs2, logsa, logsb);
-  finish(iga, p0, ls.ma, logsa, lpya, sla, ha, sca, mna);
-  finish(igb, p0 + 1, ls.mb, logsb, lpyb, slb, hb, scb, mnb);
-  return fminf(mna, mnb);   // never NaN; depends on every read of the t slots (they may be refilled once it is known)
+};
+
+// One pixel's contributions to the forward sums; `add(k, v)` accumulates v into sum k (0 CE, 1 KLD, 2 ENT, 3 CST, 4 n_conf,
+// 5 n_ign, 6 n_nz) -- registers in the forward kernel, shared-memory columns in the one-pass kernel.
+template <int C, class Add>
+__device__ __forceinline__ void pixel_sums(bool ign, int terms, int region, float lpy, float sl, float h, float scv, float mn,
+                                           const LossArgs& a, int b, int64_t p, float m, float logs, Add add) {
+  if (!ign) {
+    if (terms & HIAST_TERM_CE) add(0, static_cast<double>(-lpy));
+    if (terms & HIAST_TERM_KLD) add(1, static_cast<double>(-sl * (1.0f / C)));
+    add(4, 1.0);
+  } else {
+    if (terms & HIAST_TERM_ENT) add(2, static_cast<double>(-h));
+    add(5, 1.0);
+  }
+  if ((terms & HIAST_TERM_CST) && in_region(region, ign)) {
+    add(3, static_cast<double>(-scv));
+    add(6, static_cast<double>((mn > 0.f) ? C : recount_nonzero<C>(a, b, p, m, logs)));   // a zero (or NaN) product: the slow way
+  }
 }
+
+template <int C, class Add>
+__device__ __forceinline__ void pair_sums(const PairLS<C>& ls, const PairCst<C>& cs, bool iga, bool igb, const LossArgs& a,
+                                          int b, int64_t p0, Add add) {
+  float lpya, lpyb, sla, slb, ha, hb, sca, scb, logsa, logsb;
+  pk::unpack(ls.lpy2, lpya, lpyb);
+  pk::unpack(ls.sl2, sla, slb);
+  pk::unpack(ls.h2, ha, hb);
+  pk::unpack(cs.sc2, sca, scb);
+  pk::unpack(ls.logs2, logsa, logsb);
+  pixel_sums<C>(iga, a.terms, a.region, lpya, sla, ha, sca, cs.mna, a, b, p0, ls.ma, logsa, add);
+  pixel_sums<C>(igb, a.terms, a.region, lpyb, slb, hb, scb, cs.mnb, a, b, p0 + 1, ls.mb, logsb, add);
+}
+
+// Coefficients of a pair's gradient:  g_c = A p_c + K - [c == y] ce - ENT p_c (logp_c - h) - CST (t_c - p_c T)
+struct GradScales {
+  float s_ce, s_kld, s_ent, s_cst;
+  pk::u64 poison2;   // NaN iff an enabled scale is non-finite (empty region in the reference: every gradient is NaN)
+  __device__ __forceinline__ void init(const float (&sc)[4], int terms) {
+    float poison = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (terms & (1 << k)) poison += 0.f * sc[k];
+    poison2 = pk::splat(poison);
+    s_ce = (terms & HIAST_TERM_CE) ? sc[0] : 0.f;
+    s_kld = (terms & HIAST_TERM_KLD) ? sc[1] : 0.f;
+    s_ent = (terms & HIAST_TERM_ENT) ? sc[2] : 0.f;
+    s_cst = (terms & HIAST_TERM_CST) ? sc[3] : 0.f;
+  }
+};
+
+// Writes the gradient of a pair channel by channel right before the store; returns a value that depends on every read of
+// the t slots (they may be refilled once it is known).
+template <int C>
+__device__ __forceinline__ float pair_gradient_store(const float (&za)[C], const float (&zb)[C], const PairLS<C>& ls,
+                                                     const LossStage<C>& st, const GradScales& gs, int ya, int yb, bool iga,
+                                                     bool igb, bool csa, bool csb, pk::u64 T2, float2* out, int64_t HW2) {
+  const pk::u64 A2 = pk::pack(iga ? 0.f : gs.s_ce + gs.s_kld, igb ? 0.f : gs.s_ce + gs.s_kld);
+  const pk::u64 K2 = pk::add2(pk::pack(iga ? 0.f : -(gs.s_kld * (1.0f / C)), igb ? 0.f : -(gs.s_kld * (1.0f / C))), gs.poison2);
+  const pk::u64 NE2 = pk::pack(iga ? -gs.s_ent : 0.f, igb ? -gs.s_ent : 0.f);
+  const pk::u64 NC2 = pk::pack(csa ? -gs.s_cst : 0.f, csb ? -gs.s_cst : 0.f);
+  const float cea = iga ? 0.f : gs.s_ce, ceb = igb ? 0.f : gs.s_ce;
+  const pk::u64 ign_mask = lane_mask(iga, igb);
+  const pk::u64 NT2 = T2 ^ 0x8000000080000000ull;
+  const pk::u64 hm2 = ls.h2 & ign_mask;
+  float tguard = 0.f;
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    const pk::u64 d2 = ls.d(za[c], zb[c]);
+    const pk::u64 p2 = pk::mul2(exp_fast2(d2), ls.inv2);
+    const pk::u64 lpm2 = pk::sub2(d2, ls.logs2) & ign_mask;       // confident lanes: p * (0 - 0) * 0
+    const pk::u64 t2 = st.t2(c);
+    pk::u64 g2 = pk::fma2(p2, A2, K2);
+    g2 = pk::fma2(pk::mul2(p2, pk::sub2(lpm2, hm2)), NE2, g2);    // - ent p (lp - h)
+    g2 = pk::fma2(pk::fma2(p2, NT2, t2), NC2, g2);                // - cst (t - p T)
+    float ga, gb, t0, t1;
+    pk::unpack(g2, ga, gb);
+    pk::unpack(t2, t0, t1);
+    tguard = fmaxf(tguard, t0);
+    if (c == ya) ga -= cea;
+    if (c == yb) gb -= ceb;
+    __stcs(out + static_cast<size_t>(c) * HW2, make_float2(ga, gb));
+  }
+  return tguard;
+}
+
+// Position of a thread's pixel pair: image b and pair index p2 inside the image, advanced by the grid stride without a division.
+struct PairPos {
+  int b;
+  int64_t p2;
+  __device__ __forceinline__ void init(long long i, int64_t HW2) {
+    b = static_cast<int>(i / HW2);
+    p2 = i - static_cast<long long>(b) * HW2;
+  }
+  __device__ __forceinline__ PairPos next(long long stride, int64_t HW2) const {
+    PairPos n = {b, p2 + stride};
+    while (n.p2 >= HW2) {
+      n.p2 -= HW2;
+      ++n.b;
+    }
+    return n;
+  }
+  __device__ __forceinline__ size_t label_pos(int64_t HW) const { return static_cast<size_t>(b) * HW + p2 * kPxL; }
+};
 
 template <int C>
 __global__ void __launch_bounds__(kThreadsL, 2) k_loss_fwd_pk(LossArgs a, Partial* __restrict__ partials) {
@@ -500,40 +629,54 @@ __global__ void __launch_bounds__(kThreadsL, 2) k_loss_fwd_pk(LossArgs a, Partia
   const LossStage<C> st(s_loss_stage, a);
   const long long total = static_cast<long long>(a.B) * st.HW2;
   const long long stride = static_cast<long long>(gridDim.x) * kThreadsL;
-  PixelSums acc = {0.0, 0.0, 0.0, 0.0, 0, 0, 0};
+  const bool want_cst = (a.terms & HIAST_TERM_CST) != 0;
+  double acc[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
   long long i = static_cast<long long>(blockIdx.x) * kThreadsL + threadIdx.x;
-  auto label_pos = [&](long long idx) {
-    const int bb = static_cast<int>(idx / st.HW2);
-    return static_cast<size_t>(bb) * a.HW + (idx - static_cast<long long>(bb) * st.HW2) * kPxL;
-  };
+  PairPos pos = {0, 0};
   int ya = 0, yb = 0;
   if (i < total) {
-    st.prefetch_z(i);
-    st.prefetch_t(i);
-    load_label_pair(a.plbl, a.plbl_bytes, label_pos(i), ya, yb);
+    pos.init(i, st.HW2);
+    st.prefetch_z_at(pos.b, pos.p2);
+    st.prefetch_t_at(pos.b, pos.p2);
+    load_label_pair(a.plbl, a.plbl_bytes, pos.label_pos(a.HW), ya, yb);
   }
   for (; i < total; i += stride) {
     st.wait_older();                       // z of this pair (its t may still be in flight)
     float z[kPxL][C];
-    const float guard = st.load_z(z);
+    float zya, zyb;
+    const float guard = fmaxf(st.load_z(z), st.load_zy(ya, yb, zya, zyb));
     const bool more = i + stride < total;
+    const PairPos nxt = pos.next(stride, st.HW2);
     int nya = 0, nyb = 0;
     if (more && guard == guard) {
-      st.prefetch_z(i + stride);
-      load_label_pair(a.plbl, a.plbl_bytes, label_pos(i + stride), nya, nyb);
+      st.prefetch_z_at(nxt.b, nxt.p2);
+      load_label_pair(a.plbl, a.plbl_bytes, nxt.label_pos(a.HW), nya, nyb);
     } else {
       asm volatile("cp.async.commit_group;\n" ::: "memory");
     }
-    const int b = static_cast<int>(i / st.HW2);
-    const float tguard = pair_forward_softce<C>(z[0], z[1], st, ya, yb, a.region, a.terms, a, b,
-                                                (i - static_cast<long long>(b) * st.HW2) * kPxL, acc);
-    if (more && tguard == tguard) st.prefetch_t(i + stride);
+    const bool iga = (ya == HIAST_IGNORE_LABEL), igb = (yb == HIAST_IGNORE_LABEL);
+    PairLS<C> ls;
+    ls.init(z[0], z[1], ya, yb, zya, zyb);
+    st.wait_older();                       // this pair's teacher probabilities have landed in the staging slots
+    PairCst<C> cs;
+    cs.sc2 = cs.T2 = 0;
+    cs.mna = cs.mnb = INFINITY;
+    if (want_cst) cs.run(z[0], z[1], ls, st);
+    pair_sums<C>(ls, cs, iga, igb, a, pos.b, pos.p2 * kPxL, [&](int k, double v) { acc[k] += v; });
+    const float tguard = fminf(cs.mna, cs.mnb);   // never NaN; depends on every read of the t slots
+    if (more && tguard == tguard) st.prefetch_t_at(nxt.b, nxt.p2);
     else asm volatile("cp.async.commit_group;\n" ::: "memory");
+    pos = nxt;
     ya = nya;
     yb = nyb;
   }
   asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-  block_reduce_store(acc, partials);
+  PixelSums sums;
+  sums.ce = acc[0]; sums.kld = acc[1]; sums.ent = acc[2]; sums.cst = acc[3];
+  sums.n_conf = static_cast<long long>(acc[4]);      // counts as exact doubles (< 2^53)
+  sums.n_ign = static_cast<long long>(acc[5]);
+  sums.n_nz = static_cast<long long>(acc[6]);
+  block_reduce_store(sums, partials);
 }
 
 template <int C>
@@ -553,89 +696,50 @@ __global__ void __launch_bounds__(kThreadsL, 2) k_loss_bwd_pk(LossArgs a, const 
       if (a.terms & (1 << k)) same = same && (__float_as_uint(sc[k]) == __float_as_uint(scales_used[k]));
     if (same) return;
   }
-  float poison = 0.f;   // NaN iff an enabled scale is non-finite (empty region in the reference: every gradient is NaN)
-#pragma unroll
-  for (int k = 0; k < 4; ++k)
-    if (a.terms & (1 << k)) poison += 0.f * sc[k];
-  const pk::u64 poison2 = pk::splat(poison);
-  const float s_ce = (a.terms & HIAST_TERM_CE) ? sc[0] : 0.f;
-  const float s_kld = (a.terms & HIAST_TERM_KLD) ? sc[1] : 0.f;
-  const float s_ent = (a.terms & HIAST_TERM_ENT) ? sc[2] : 0.f;
-  const float s_cst = (a.terms & HIAST_TERM_CST) ? sc[3] : 0.f;
+  GradScales gsc;
+  gsc.init(sc, a.terms);
+  const bool want_cst = (a.terms & HIAST_TERM_CST) != 0;
   long long i = static_cast<long long>(blockIdx.x) * kThreadsL + threadIdx.x;
-  auto label_pos = [&](long long idx) {
-    const int bb = static_cast<int>(idx / st.HW2);
-    return static_cast<size_t>(bb) * a.HW + (idx - static_cast<long long>(bb) * st.HW2) * kPxL;
-  };
+  PairPos pos = {0, 0};
   int ya = 0, yb = 0;
   if (i < total) {
-    st.prefetch_z(i);
-    st.prefetch_t(i);
-    load_label_pair(a.plbl, a.plbl_bytes, label_pos(i), ya, yb);
+    pos.init(i, st.HW2);
+    st.prefetch_z_at(pos.b, pos.p2);
+    st.prefetch_t_at(pos.b, pos.p2);
+    load_label_pair(a.plbl, a.plbl_bytes, pos.label_pos(a.HW), ya, yb);
   }
   for (; i < total; i += stride) {
     st.wait_older();                       // z of this pair
     float z[kPxL][C];
-    const float guard = st.load_z(z);
+    float zya, zyb;
+    const float guard = fmaxf(st.load_z(z), st.load_zy(ya, yb, zya, zyb));
     const bool more = i + stride < total;
+    const PairPos nxt = pos.next(stride, st.HW2);
     int nya = 0, nyb = 0;
     if (more && guard == guard) {
-      st.prefetch_z(i + stride);
-      load_label_pair(a.plbl, a.plbl_bytes, label_pos(i + stride), nya, nyb);
+      st.prefetch_z_at(nxt.b, nxt.p2);
+      load_label_pair(a.plbl, a.plbl_bytes, nxt.label_pos(a.HW), nya, nyb);
     } else {
       asm volatile("cp.async.commit_group;\n" ::: "memory");
     }
-    const int b = static_cast<int>(i / st.HW2);
-    const int64_t p2i = i - static_cast<long long>(b) * st.HW2;
+    const int b = pos.b;
+    const int64_t p2i = pos.p2;
     const bool iga = (ya == HIAST_IGNORE_LABEL), igb = (yb == HIAST_IGNORE_LABEL);
     PairLS<C> ls;
-    ls.init(z[0], z[1]);
-    // per-lane coefficients:  g = A p + K - [c == y] ce - ENT p (lp - h) - CST (t - p T)
-    const bool csa = (a.terms & HIAST_TERM_CST) && in_region(a.region, iga);
-    const bool csb = (a.terms & HIAST_TERM_CST) && in_region(a.region, igb);
-    const pk::u64 A2 = pk::pack(iga ? 0.f : s_ce + s_kld, igb ? 0.f : s_ce + s_kld);
-    const pk::u64 K2 = pk::pack(iga ? 0.f : -(s_kld * (1.0f / C)), igb ? 0.f : -(s_kld * (1.0f / C)));
-    const pk::u64 NE2 = pk::pack(iga ? -s_ent : 0.f, igb ? -s_ent : 0.f);
-    const pk::u64 NC2 = pk::pack(csa ? -s_cst : 0.f, csb ? -s_cst : 0.f);
-    const float cea = iga ? 0.f : s_ce, ceb = igb ? 0.f : s_ce;
-    const pk::u64 ign_mask = lane_mask(iga, igb);
-    pk::u64 h2 = 0, T2 = 0;
-    if ((a.terms & HIAST_TERM_ENT) && (iga || igb)) {
-#pragma unroll
-      for (int c = 0; c < C; ++c) {
-        const pk::u64 d2 = ls.d(z[0][c], z[1][c]);
-        const pk::u64 lpm2 = pk::sub2(d2, ls.logs2) & ign_mask;    // confident lanes contribute p * 0
-        h2 = pk::fma2(pk::mul2(pk::exp2x(d2), ls.inv2), lpm2, h2);
-      }
-    }
+    ls.init(z[0], z[1], ya, yb, zya, zyb);
+    const bool csa = want_cst && in_region(a.region, iga);
+    const bool csb = want_cst && in_region(a.region, igb);
     st.wait_older();                       // this pair's teacher probabilities
+    pk::u64 T2 = 0;
     if (csa || csb) {
 #pragma unroll
       for (int c = 0; c < C; ++c) T2 = (c == 0) ? st.t2(c) : pk::add2(T2, st.t2(c));
     }
-    const pk::u64 NT2 = T2 ^ 0x8000000080000000ull;
     float2* gs = reinterpret_cast<float2*>(grad + static_cast<size_t>(b) * C * a.HW) + p2i;
-    float tguard = 0.f;
-#pragma unroll
-    for (int c = 0; c < C; ++c) {
-      const pk::u64 d2 = ls.d(z[0][c], z[1][c]);
-      const pk::u64 p2 = pk::mul2(pk::exp2x(d2), ls.inv2);
-      const pk::u64 lpm2 = pk::sub2(d2, ls.logs2) & ign_mask;
-      const pk::u64 t2 = st.t2(c);
-      pk::u64 g2 = pk::fma2(p2, A2, K2);
-      g2 = pk::fma2(pk::mul2(p2, pk::sub2(lpm2, h2)), NE2, g2);      // - ent p (lp - h)   (0 on confident lanes)
-      g2 = pk::fma2(pk::fma2(p2, NT2, t2), NC2, g2);                  // - cst (t - p T)
-      g2 = pk::add2(g2, poison2);
-      float ga, gb, t0, t1;
-      pk::unpack(g2, ga, gb);
-      pk::unpack(t2, t0, t1);
-      tguard = fmaxf(tguard, t0);
-      if (c == ya) ga -= cea;
-      if (c == yb) gb -= ceb;
-      __stcs(gs + static_cast<size_t>(c) * st.HW2, make_float2(ga, gb));
-    }
-    if (more && tguard == tguard) st.prefetch_t(i + stride);          // the t slots have been read
+    const float tguard = pair_gradient_store<C>(z[0], z[1], ls, st, gsc, ya, yb, iga, igb, csa, csb, T2, gs, st.HW2);
+    if (more && tguard == tguard) st.prefetch_t_at(nxt.b, nxt.p2);    // the t slots have been read
     else asm volatile("cp.async.commit_group;\n" ::: "memory");
+    pos = nxt;
     ya = nya;
     yb = nyb;
   }
@@ -653,8 +757,18 @@ struct LabelCounts {
   unsigned long long n_conf, n_ign;
 };
 
+// Programmatic dependent launch (sm_90+): a kernel launched with the stream-serialisation attribute may start while its
+// predecessor in the stream is still running; it must execute pdl_wait() before touching anything the predecessor writes.
+// pdl_launch_dependents() in the predecessor lets the dependent grid be scheduled from that point on (otherwise: at its exit).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+
+// Label-only pre-pass: block k writes its (n_conf, n_ign) to out[k] -- no atomics, hence no memset in front of it.  The grid is
+// one wave, and every block releases the dependent launch at once: the one-pass kernel starts beside it and only waits
+// (pdl_wait) when it first needs the counts.
 __global__ void __launch_bounds__(256) k_label_count(const void* __restrict__ plbl, int plbl_bytes, long long n,
                                                      LabelCounts* __restrict__ out) {
+  pdl_launch_dependents();
   long long ign = 0, tot = 0;
   const long long tid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long nth = static_cast<long long>(gridDim.x) * blockDim.x;
@@ -687,12 +801,46 @@ __global__ void __launch_bounds__(256) k_label_count(const void* __restrict__ pl
       tot += 1;
     }
   }
+  __shared__ long long s_ign[8], s_tot[8];
   ign = warp_sum(ign);
   tot = warp_sum(tot);
-  if (lane_id() == 0 && tot) {
-    atomicAdd(&out->n_ign, static_cast<unsigned long long>(ign));
-    atomicAdd(&out->n_conf, static_cast<unsigned long long>(tot - ign));
+  if (lane_id() == 0) {
+    s_ign[threadIdx.x >> 5] = ign;
+    s_tot[threadIdx.x >> 5] = tot;
   }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) {
+      ign += s_ign[w];
+      tot += s_tot[w];
+    }
+    out[blockIdx.x].n_ign = static_cast<unsigned long long>(ign);
+    out[blockIdx.x].n_conf = static_cast<unsigned long long>(tot - ign);
+  }
+}
+
+// every thread of the block returns the totals of the pre-pass's per-block counts
+__device__ __forceinline__ LabelCounts sum_label_counts(const LabelCounts* __restrict__ parts, int n_parts) {
+  __shared__ unsigned long long s_c[kThreadsL / 32], s_i[kThreadsL / 32];
+  unsigned long long nc = 0, ni = 0;
+  for (int k = threadIdx.x; k < n_parts; k += kThreadsL) {
+    nc += parts[k].n_conf;
+    ni += parts[k].n_ign;
+  }
+  nc = static_cast<unsigned long long>(warp_sum(static_cast<long long>(nc)));
+  ni = static_cast<unsigned long long>(warp_sum(static_cast<long long>(ni)));
+  if (lane_id() == 0) {
+    s_c[threadIdx.x >> 5] = nc;
+    s_i[threadIdx.x >> 5] = ni;
+  }
+  __syncthreads();
+  LabelCounts r = {0, 0};
+#pragma unroll
+  for (int w = 0; w < kThreadsL / 32; ++w) {
+    r.n_conf += s_c[w];
+    r.n_ign += s_i[w];
+  }
+  return r;
 }
 
 // scales of the gradient for upstream gradients gw[4]: float(double(gw) / divisor), the arithmetic of the autograd
@@ -710,27 +858,11 @@ template <int C>
 __global__ void __launch_bounds__(kThreadsL, 2) k_loss_fused_pk(LossArgs a, const LabelCounts* __restrict__ lc,
                                                                 const float* __restrict__ grad_weights,
                                                                 float* __restrict__ scales_used, float* __restrict__ grad,
-                                                                Partial* __restrict__ partials) {
+                                                                Partial* __restrict__ partials, int n_count_parts) {
   extern __shared__ __align__(128) float2 s_loss_stage[];
   const LossStage<C> st(s_loss_stage, a);
   const long long total = static_cast<long long>(a.B) * st.HW2;
   const long long stride = static_cast<long long>(gridDim.x) * kThreadsL;
-  float sc[4];
-  {
-    const LabelCounts c0 = *lc;
-    const float gw[4] = {grad_weights[0], grad_weights[1], grad_weights[2], grad_weights[3]};
-    fused_scales(c0, gw, C, a.region, sc);
-    if (blockIdx.x == 0 && threadIdx.x < 4) scales_used[threadIdx.x] = sc[threadIdx.x];
-  }
-  float poison = 0.f;   // NaN iff an enabled scale is non-finite (empty region in the reference: every gradient is NaN)
-#pragma unroll
-  for (int k = 0; k < 4; ++k)
-    if (a.terms & (1 << k)) poison += 0.f * sc[k];
-  const pk::u64 poison2 = pk::splat(poison);
-  const float s_ce = (a.terms & HIAST_TERM_CE) ? sc[0] : 0.f;
-  const float s_kld = (a.terms & HIAST_TERM_KLD) ? sc[1] : 0.f;
-  const float s_ent = (a.terms & HIAST_TERM_ENT) ? sc[2] : 0.f;
-  const float s_cst = (a.terms & HIAST_TERM_CST) ? sc[3] : 0.f;
   const bool want_cst = (a.terms & HIAST_TERM_CST) != 0;
   // the seven forward accumulators live in a per-thread column of shared memory, not in registers: the gradient pass needs
   // every register the two-pass backward kernel uses (128 per thread at two CTAs per SM)
@@ -738,121 +870,68 @@ __global__ void __launch_bounds__(kThreadsL, 2) k_loss_fused_pk(LossArgs a, cons
 #pragma unroll
   for (int k = 0; k < 7; ++k) sacc[k * kThreadsL] = 0.0;
   long long i = static_cast<long long>(blockIdx.x) * kThreadsL + threadIdx.x;
-  auto label_pos = [&](long long idx) {
-    const int bb = static_cast<int>(idx / st.HW2);
-    return static_cast<size_t>(bb) * a.HW + (idx - static_cast<long long>(bb) * st.HW2) * kPxL;
-  };
+  PairPos pos = {0, 0};
   int ya = 0, yb = 0;
   if (i < total) {
-    st.prefetch_z(i);
-    st.prefetch_t(i);
-    load_label_pair(a.plbl, a.plbl_bytes, label_pos(i), ya, yb);
+    pos.init(i, st.HW2);
+    st.prefetch_z_at(pos.b, pos.p2);
+    st.prefetch_t_at(pos.b, pos.p2);
+    load_label_pair(a.plbl, a.plbl_bytes, pos.label_pos(a.HW), ya, yb);
   }
+  // The label counts come from the pre-pass this grid was launched beside (programmatic dependent launch): the first pair's
+  // logits, teacher probabilities and labels are already on their way when the block waits for it.  Every thread of the block
+  // takes part (block-wide sum of the pre-pass's per-block counts), also those without a pair.
+  pdl_wait();
+  float sc[4];
+  {
+    const LabelCounts c0 = sum_label_counts(lc, n_count_parts);
+    const float gw[4] = {grad_weights[0], grad_weights[1], grad_weights[2], grad_weights[3]};
+    fused_scales(c0, gw, C, a.region, sc);
+    if (blockIdx.x == 0 && threadIdx.x < 4) scales_used[threadIdx.x] = sc[threadIdx.x];
+  }
+  GradScales gsc;
+  gsc.init(sc, a.terms);
   for (; i < total; i += stride) {
     st.wait_older();                       // z of this pair
     float z[kPxL][C];
-    const float guard = st.load_z(z);
+    float zya, zyb;
+    const float guard = fmaxf(st.load_z(z), st.load_zy(ya, yb, zya, zyb));
     const bool more = i + stride < total;
+    const PairPos nxt = pos.next(stride, st.HW2);
     int nya = 0, nyb = 0;
     if (more && guard == guard) {
-      st.prefetch_z(i + stride);
-      load_label_pair(a.plbl, a.plbl_bytes, label_pos(i + stride), nya, nyb);
+      st.prefetch_z_at(nxt.b, nxt.p2);
+      load_label_pair(a.plbl, a.plbl_bytes, nxt.label_pos(a.HW), nya, nyb);
     } else {
       asm volatile("cp.async.commit_group;\n" ::: "memory");
     }
-    const int b = static_cast<int>(i / st.HW2);
-    const int64_t p2i = i - static_cast<long long>(b) * st.HW2;
+    const int b = pos.b;
+    const int64_t p2i = pos.p2;
     const bool iga = (ya == HIAST_IGNORE_LABEL), igb = (yb == HIAST_IGNORE_LABEL);
     PairLS<C> ls;
-    ls.init(z[0], z[1]);
+    ls.init(z[0], z[1], ya, yb, zya, zyb);           // softmax pass: everything CE / KLD / ENT need falls out of it
     const bool csa = want_cst && in_region(a.region, iga);
     const bool csb = want_cst && in_region(a.region, igb);
-    const pk::u64 A2 = pk::pack(iga ? 0.f : s_ce + s_kld, igb ? 0.f : s_ce + s_kld);
-    const pk::u64 K2 = pk::pack(iga ? 0.f : -(s_kld * (1.0f / C)), igb ? 0.f : -(s_kld * (1.0f / C)));
-    const pk::u64 NE2 = pk::pack(iga ? -s_ent : 0.f, igb ? -s_ent : 0.f);
-    const pk::u64 NC2 = pk::pack(csa ? -s_cst : 0.f, csb ? -s_cst : 0.f);
-    const float cea = iga ? 0.f : s_ce, ceb = igb ? 0.f : s_ce;
-    const pk::u64 ign_mask = lane_mask(iga, igb);
-    const bool want_ent = (a.terms & HIAST_TERM_ENT) && (iga || igb);
     st.wait_older();                       // this pair's teacher probabilities
-    // pass 1 over the channels: everything the forward sums need, the entropy inner product and the teacher mass
-    pk::u64 sl2 = 0, h2 = 0, sc2 = 0, T2 = 0;
-    float lpya = 0.f, lpyb = 0.f, mna = INFINITY, mnb = INFINITY;
-#pragma unroll
-    for (int c = 0; c < C; ++c) {
-      const pk::u64 d2 = ls.d(z[0][c], z[1][c]);
-      const pk::u64 lp2 = pk::sub2(d2, ls.logs2);
-      sl2 = (c == 0) ? lp2 : pk::add2(sl2, lp2);
-      float lpa, lpb;
-      pk::unpack(lp2, lpa, lpb);
-      lpya = (c == ya) ? lpa : lpya;
-      lpyb = (c == yb) ? lpb : lpyb;
-      if (want_ent) h2 = pk::fma2(pk::mul2(pk::exp2x(d2), ls.inv2), lp2 & ign_mask, h2);   // confident lanes: p * 0
-      if (want_cst) {
-        const pk::u64 t2 = st.t2(c);
-        T2 = (c == 0) ? t2 : pk::add2(T2, t2);
-        const pk::u64 pr2 = pk::mul2(lp2, t2);   // = -(-lp * t), same magnitude and zero-ness
-        sc2 = (c == 0) ? pr2 : pk::add2(sc2, pr2);
-        float pa, pb;
-        pk::unpack(pr2, pa, pb);
-        mna = fminf(mna, fabsf(pa));
-        mnb = fminf(mnb, fabsf(pb));
-      }
-    }
-    {
-      float sla, slb, ha, hb, sca, scb, logsa, logsb;
-      pk::unpack(sl2, sla, slb);
-      pk::unpack(h2, ha, hb);
-      pk::unpack(sc2, sca, scb);
-      pk::unpack(ls.logs2, logsa, logsb);
-      auto finish = [&](bool ign, int64_t p, float m, float logs, float lpy, float sl, float h, float scv, float mn) {
-        if (!ign) {
-          if (a.terms & HIAST_TERM_CE) sacc[0 * kThreadsL] += static_cast<double>(-lpy);
-          if (a.terms & HIAST_TERM_KLD) sacc[1 * kThreadsL] += static_cast<double>(-sl * (1.0f / C));
-          sacc[4 * kThreadsL] += 1.0;          // counts as exact doubles (< 2^53)
-        } else {
-          if (a.terms & HIAST_TERM_ENT) sacc[2 * kThreadsL] += static_cast<double>(-h);
-          sacc[5 * kThreadsL] += 1.0;
-        }
-        if (want_cst && in_region(a.region, ign)) {
-          sacc[3 * kThreadsL] += static_cast<double>(-scv);
-          sacc[6 * kThreadsL] += static_cast<double>((mn > 0.f) ? C : recount_nonzero<C>(a, b, p, m, logs));
-        }
-      };
-      finish(iga, p2i * kPxL, ls.ma, logsa, lpya, sla, ha, sca, mna);
-      finish(igb, p2i * kPxL + 1, ls.mb, logsb, lpyb, slb, hb, scb, mnb);
-    }
+    PairCst<C> cs;
+    cs.sc2 = cs.T2 = 0;
+    cs.mna = cs.mnb = INFINITY;
+    if (want_cst) cs.run(z[0], z[1], ls, st);   // pass 1 (SoftCE only): the sum of products, their zero-ness, the teacher mass
+    pair_sums<C>(ls, cs, iga, igb, a, b, p2i * kPxL, [&](int k, double v) { sacc[k * kThreadsL] += v; });
     // pass 2: the gradient, channel by channel right before the store
-    const pk::u64 NT2 = T2 ^ 0x8000000080000000ull;
     float2* gs = reinterpret_cast<float2*>(grad + static_cast<size_t>(b) * C * a.HW) + p2i;
-    float tguard = 0.f;
-#pragma unroll
-    for (int c = 0; c < C; ++c) {
-      const pk::u64 d2 = ls.d(z[0][c], z[1][c]);
-      const pk::u64 p2 = pk::mul2(pk::exp2x(d2), ls.inv2);
-      const pk::u64 lpm2 = pk::sub2(d2, ls.logs2) & ign_mask;
-      const pk::u64 t2 = st.t2(c);
-      pk::u64 g2 = pk::fma2(p2, A2, K2);
-      g2 = pk::fma2(pk::mul2(p2, pk::sub2(lpm2, h2)), NE2, g2);      // - ent p (lp - h)   (0 on confident lanes)
-      g2 = pk::fma2(pk::fma2(p2, NT2, t2), NC2, g2);                  // - cst (t - p T)
-      g2 = pk::add2(g2, poison2);
-      float ga, gb, t0, t1;
-      pk::unpack(g2, ga, gb);
-      pk::unpack(t2, t0, t1);
-      tguard = fmaxf(tguard, t0);
-      if (c == ya) ga -= cea;
-      if (c == yb) gb -= ceb;
-      __stcs(gs + static_cast<size_t>(c) * st.HW2, make_float2(ga, gb));
-    }
-    if (more && tguard == tguard) st.prefetch_t(i + stride);          // the t slots have been read
+    const float tguard = pair_gradient_store<C>(z[0], z[1], ls, st, gsc, ya, yb, iga, igb, csa, csb, cs.T2, gs, st.HW2);
+    if (more && tguard == tguard) st.prefetch_t_at(nxt.b, nxt.p2);    // the t slots have been read
     else asm volatile("cp.async.commit_group;\n" ::: "memory");
+    pos = nxt;
     ya = nya;
     yb = nyb;
   }
   asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+  pdl_launch_dependents();                 // the finalize kernel may be scheduled; it waits for this grid before it reads
   PixelSums acc;
   acc.ce = sacc[0 * kThreadsL]; acc.kld = sacc[1 * kThreadsL]; acc.ent = sacc[2 * kThreadsL]; acc.cst = sacc[3 * kThreadsL];
-  acc.n_conf = static_cast<long long>(sacc[4 * kThreadsL]);
+  acc.n_conf = static_cast<long long>(sacc[4 * kThreadsL]);      // counts as exact doubles (< 2^53)
   acc.n_ign = static_cast<long long>(sacc[5 * kThreadsL]);
   acc.n_nz = static_cast<long long>(sacc[6 * kThreadsL]);
   block_reduce_store(acc, partials);
@@ -990,6 +1069,7 @@ __global__ void __launch_bounds__(kThreadsL) k_loss_bwd_generic(LossArgs a, cons
 __global__ void k_loss_finalize(const Partial* __restrict__ partials, int n, double* __restrict__ sums,
                                 long long* __restrict__ counts) {
   __shared__ Partial s_part[kThreadsL / 32];
+  pdl_wait();                              // no-op unless launched as a programmatic dependent (hiast_st_loss_fused)
   PixelSums acc = {0.0, 0.0, 0.0, 0.0, 0, 0, 0};
   for (int i = threadIdx.x; i < n; i += kThreadsL) {
     const Partial p = partials[i];
@@ -1132,8 +1212,27 @@ extern "C" int hiast_st_loss_bwd(const float* z, const float* t, const void* plb
   return HIAST_OK;
 }
 
+constexpr int kCountBlocksMax = 1024;                                   // per-block label counts in front of the partial sums
+constexpr size_t kFusedHeaderBytes = kCountBlocksMax * sizeof(LabelCounts);
+
 extern "C" size_t hiast_st_loss_fused_workspace_bytes(int B, int C, int64_t HW) {
-  return hiast_st_loss_workspace_bytes(B, C, HW) + 64;
+  return hiast_st_loss_workspace_bytes(B, C, HW) + kFusedHeaderBytes;
+}
+
+// kernel<<<grid, block, smem, st>>>(args...) as a programmatic dependent of the kernel launched before it on `st`
+template <class... KArgs, class... Args>
+static cudaError_t launch_dependent(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(grid));
+  cfg.blockDim = dim3(static_cast<unsigned>(block));
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 extern "C" int hiast_st_loss_fused(const float* z, const float* t, const void* plbl, int plbl_bytes, int B, int C, int64_t HW,
@@ -1149,12 +1248,14 @@ extern "C" int hiast_st_loss_fused(const float* z, const float* t, const void* p
     return HIAST_ERR_UNSUPPORTED;         // callers take hiast_st_loss_fwd + hiast_st_loss_bwd
   cudaStream_t st = as_stream(stream);
   LabelCounts* lc = static_cast<LabelCounts*>(workspace);
-  Partial* parts = reinterpret_cast<Partial*>(static_cast<char*>(workspace) + 64);
-  HIAST_CUDA_TRY(cudaMemsetAsync(lc, 0, sizeof(LabelCounts), st));
+  Partial* parts = reinterpret_cast<Partial*>(static_cast<char*>(workspace) + kFusedHeaderBytes);
   const long long n = static_cast<long long>(B) * HW;
-  // two or three 16-byte loads per thread, every load of a thread in flight together: a latency-bound 8 MB read
+  // Three launches, chained as programmatic dependents: [label counts] -> [one-pass kernel] -> [finalize].  The pre-pass is one
+  // wave of blocks with a few 16-byte loads per thread, all in flight together (a latency-bound 8 MB read at 2x19x512x1024);
+  // the one-pass kernel starts beside it and the finalize block is scheduled as the first one-pass block exits.
   const long long vecs = plbl_bytes == 8 ? n / 2 : n / 16;
-  const int cgrid = static_cast<int>(std::max<long long>(1, std::min<long long>((vecs + 255) / 256, sm_count() * 8)));
+  const int cgrid = static_cast<int>(std::max<long long>(
+      1, std::min<long long>((vecs + 256 * 4 - 1) / (256 * 4), std::min(sm_count() * 4, kCountBlocksMax))));
   k_label_count<<<cgrid, 256, 0, st>>>(plbl, plbl_bytes, n, lc);
   HIAST_CHECK_LAUNCH();
   const int grid = std::min(loss_grid(n), sm_count() * 2);
@@ -1162,14 +1263,14 @@ extern "C" int hiast_st_loss_fused(const float* z, const float* t, const void* p
   HIAST_TRY(loss_configure_smem(C, loss_stage_bytes(C)));
   if (C == 19) {
     HIAST_TRY(ensure_dyn_smem(k_loss_fused_pk<19>, smem));
-    k_loss_fused_pk<19><<<grid, kThreadsL, smem, st>>>(a, lc, grad_weights, scales_used, grad_z, parts);
+    HIAST_CUDA_TRY(launch_dependent(k_loss_fused_pk<19>, grid, kThreadsL, smem, st, a, lc, grad_weights, scales_used, grad_z, parts,
+                                    cgrid));
   } else {
     HIAST_TRY(ensure_dyn_smem(k_loss_fused_pk<16>, smem));
-    k_loss_fused_pk<16><<<grid, kThreadsL, smem, st>>>(a, lc, grad_weights, scales_used, grad_z, parts);
+    HIAST_CUDA_TRY(launch_dependent(k_loss_fused_pk<16>, grid, kThreadsL, smem, st, a, lc, grad_weights, scales_used, grad_z, parts,
+                                    cgrid));
   }
-  HIAST_CHECK_LAUNCH();
-  k_loss_finalize<<<1, kThreadsL, 0, st>>>(parts, grid, sums, reinterpret_cast<long long*>(counts));
-  HIAST_CHECK_LAUNCH();
+  HIAST_CUDA_TRY(launch_dependent(k_loss_finalize, 1, kThreadsL, 0, st, parts, grid, sums, reinterpret_cast<long long*>(counts)));
   return HIAST_OK;
 }
 
