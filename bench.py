@@ -54,6 +54,7 @@ def parse_args():
     ap.add_argument('--dist', default='mixed', choices=['mixed', 'diffuse', 'peaked'])
     ap.add_argument('--e2e-steps', type=int, default=4)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true', help='development: skip the end-to-end legs (the line then has no e2e)')
     ap.add_argument('--no-extra', action='store_true', help='skip the legs for BASELINE configs[2], [3], [4]')
     ap.add_argument('--extra-timeout', type=int, default=240, help='seconds after which the extra legs are abandoned (the headline line is printed without them)')
     ap.add_argument('--cpu-images', type=int, default=8)
@@ -239,7 +240,7 @@ def gpu_arm(args):
     import torch.distributed as dist
     from types import SimpleNamespace
     from hiast_b200.ias_engine import IASEngine
-    from hiast_b200.sharded import ShardedIAS
+    from hiast_b200.sharded import ShardedIAS, TokenRing
 
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -305,12 +306,33 @@ def gpu_arm(args):
 
     # warm-up (also creates the NCCL p2p communicators)
     run_job(Wm, timed=False)
+    # Schedule calibration, still warm-up: the concurrent schedule squeezes phase C (issue-bound) onto the reserved SMs, where it
+    # takes about as long as one phase A -- on a box whose GPUs run power-capped it can become the longer of the two.  Four
+    # windows per rank with the reserved SMs and four without; every rank adopts the faster one (max over ranks decides).
+    ring_on = world > 1 and TokenRing.get(device, rank, world) is not None      # every rank asks (cached since the warm-up job)
+    calibration = None
+    if 'HIAST_RESERVE_SMS' not in os.environ and engine.reserve_sms > 0:
+        calibration = {}
+        for cand in (engine.reserve_sms, 0):
+            engine.reserve_sms = cand
+            run_job(2, timed=False)
+            barrier()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            run_job(4, timed=False)
+            c1.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([c0.elapsed_time(c1) / 4], dtype=torch.float64, device=device)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            calibration[cand] = float(t[0])
+        engine.reserve_sms = min(calibration, key=calibration.get)
     ShardedIAS(engine, WINDOW, K * world * WINDOW, rank, world).warm_collective()   # the timed job's all-gather shape
     engine.thr_state.fill_(0.9)
     engine.mean_state.zero_()
     barrier()
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and os.environ.get('HIAST_BENCH_SAMPLER', '1') != '0':
         sampler.start()
         sampler.wait_first()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -322,6 +344,9 @@ def gpu_arm(args):
     barrier()
     wall1 = time.perf_counter()
     ms = t0.elapsed_time(t1)
+    if os.environ.get('HIAST_BENCH_VERBOSE'):
+        print('rank %d: %.3f ms per step, phase A launches %s' % (rank, ms / K, ' '.join('%.2f' % e0.elapsed_time(e1) for e0, e1 in a_events)),
+              file=sys.stderr, flush=True)
     certified = engine.check_errors()
     n_launches = launches['n']
     a_ms = sum(e0.elapsed_time(e1) for e0, e1 in a_events) / max(len(a_events), 1)
@@ -341,7 +366,13 @@ def gpu_arm(args):
     clocks = sampler.stop() if rank == 0 else None
     if clocks is not None:
         clocks['sampled_over'] = 'the timed steps plus the same load repeated untimed for >= 0.3 s, nvidia-smi -lms 5'
+    starts = [round(t0.elapsed_time(e0), 2) for e0, _ in a_events]           # when each step's phase A started (this rank)
+    per_rank_ms = [ms / K]
     if world > 1:
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, (ms / K, starts))
+        per_rank_ms = [p[0] for p in per_rank]
+        starts = max(per_rank, key=lambda p: p[0])[1]                        # of the slowest rank
         t = torch.tensor([ms, a_ms], dtype=torch.float64, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, a_ms = float(t[0]), float(t[1])
@@ -351,7 +382,7 @@ def gpu_arm(args):
     parity = sharded_parity(engine, pool, rank, world, device, run_job) if world > 1 else None
 
     # ---- e2e through the reference-facing API with host buffers (every rank its own replica of the call)
-    e2e = measure_e2e(args, device, rank, world, barrier)
+    e2e = None if args.no_e2e else measure_e2e(args, device, rank, world, barrier)
 
     line = None
     if rank == 0:
@@ -366,18 +397,24 @@ def gpu_arm(args):
                        'gamma': GAMMA, 'distribution': args.dist, 'resident_pool_maps': WINDOW,
                        'l2': 'inputs exceed L2 (10.2 GB streamed per step)',
                        'reserved_sms': engine.reserve_sms,
-                       'parallelism': ('one rank: phase A(j+1) on %d SMs while the threshold chain and phase C of window j run on the '
-                                       'other %d (chain stream); no collective' % (148 - engine.reserve_sms, engine.reserve_sms)
-                                       if world == 1 else
-                                       'windows striped over %d ranks; per rank phase A(j+1) beside chain + phase C of window j on '
-                                       'reserved SMs; 19-double threshold '
-                                       'state handed over INSIDE the scan kernel through peer memory (CUDA IPC mailboxes over '
-                                       'NVLink; HIAST_RING=nccl selects NCCL send/recv); one NCCL all-gather at the end' % world)},
+                       'schedule_calibration_ms_per_step': calibration,
+                       'token_ring': ('none (one rank)' if world == 1 else
+                                      'peer memory (CUDA IPC mailboxes)' if ring_on else
+                                      'NCCL send/recv'),
+                       'parallelism': (('one rank: ' if world == 1 else 'windows striped over %d ranks; per rank ' % world) +
+                                       ('phase A(j+1) on %d SMs while the threshold chain and phase C of window j run on the other '
+                                        '%d (chain stream)' % (148 - engine.reserve_sms, engine.reserve_sms) if engine.reserve_sms
+                                        else 'phase A(j+1), then the chain of window j beside phase C of window j-1 (serial schedule)') +
+                                       ('; no collective' if world == 1 else
+                                        '; 19-double threshold state handed over INSIDE the scan kernel (see token_ring; '
+                                        'HIAST_RING=nccl selects NCCL send/recv); one NCCL all-gather at the end'))},
             'hbm_frac_of_peak': ALG_BYTES_PER_IMAGE * value / world / 1e9 / peak,
             'roofline': {'kernel': 'k_softmax_hist_grs (phase A)', 'bound': 'hbm', 'achieved': achieved, 'peak': peak,
                          'unit': 'GB/s', 'frac': achieved / peak, 'traffic': ncu_traffic(), 'peak_source': peak_src,
                          'algorithmic_bytes_per_launch': ALG_BYTES_PER_IMAGE * WINDOW, 'launch_ms': a_ms,
                          'share_of_step': a_ms / (ms / K)},
+            'step_timeline': {'ms_per_step_per_rank': [round(x, 4) for x in per_rank_ms],
+                              'phase_a_starts_ms_slowest_rank': starts},
             'e2e': e2e,
             'gpu_launches': n_launches,
             'clocks': clocks,
