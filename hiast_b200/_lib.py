@@ -67,6 +67,10 @@ _SIGNATURES = {
     'hiast_st_loss_fused_workspace_bytes': (_sz, [_i, _i, _i64]),
     'hiast_st_loss_fused': (_i, [_vp, _vp, _vp, _i, _i, _i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     'hiast_st_loss_bwd_checked': (_i, [_vp, _vp, _vp, _i, _i, _i, _i64, _i, _i, _vp, _vp, _vp, _vp]),
+    'hiast_st_loss_fused_terms': (_i, [_vp, _vp, _vp, _i, _i, _i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz,
+                                       _vp]),
+    'hiast_st_loss_bwd_checked_terms': (_i, [_vp, _vp, _vp, _i, _i, _i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                             _i, _vp, _vp]),
     'hiast_confusion_matrix': (_i, [_vp, _vp, _i, _i64, _i, _i, _vp, _vp, _vp]),
     'hiast_confusion_from_logits': (_i, [_vp, _vp, _i, _i, _i, _i64, _i, _i, _vp, _vp]),
     'hiast_iou_from_confusion': (_i, [_vp, _i, _vp, _vp, _vp]),

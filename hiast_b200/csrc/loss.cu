@@ -679,14 +679,41 @@ __global__ void __launch_bounds__(kThreadsL, 2) k_loss_fwd_pk(LossArgs a, Partia
   block_reduce_store(sums, partials);
 }
 
+// Upstream gradients of the four loss terms as autograd delivers them (hiast_st_loss_bwd_checked_terms): device pointers to
+// f32 scalars (nullptr: no gradient flows into that term) and the divisors the forward call wrote.  The scales are derived
+// here -- float(double(g_k) / divisor_k), the arithmetic of hiast_b200/losses.py -- instead of by four tiny torch kernels.
+struct GoutArgs {
+  const float* g[4];
+  const double* divisors;      // nullptr: take `scales` as given
+  const float* hint_weights;   // with upstream_out: *upstream_out = gout_{k0} / hint_weights[k0] (what losses.GradHint observes)
+  float* upstream_out;
+  int k0;
+  const float* term_weights;   // != nullptr: the outputs were the WEIGHTED terms w_k * loss_k, so gout_k = *g[k] * w_k (f32, as
+                               // autograd's MulBackward would have computed it)
+};
+
 template <int C>
 __global__ void __launch_bounds__(kThreadsL, 2) k_loss_bwd_pk(LossArgs a, const float* __restrict__ scales,
-                                                              float* __restrict__ grad, const float* __restrict__ scales_used) {
+                                                              float* __restrict__ grad, const float* __restrict__ scales_used,
+                                                              GoutArgs go) {
   extern __shared__ __align__(128) float2 s_loss_stage[];
   const LossStage<C> st(s_loss_stage, a);
   const long long total = static_cast<long long>(a.B) * st.HW2;
   const long long stride = static_cast<long long>(gridDim.x) * kThreadsL;
-  const float sc[4] = {scales[0], scales[1], scales[2], scales[3]};
+  float sc[4];
+  if (go.divisors) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float g = 0.f;
+      if (((a.terms >> k) & 1) && go.g[k]) g = go.term_weights ? __fmul_rn(*go.g[k], go.term_weights[k]) : *go.g[k];
+      sc[k] = (((a.terms >> k) & 1) && go.g[k]) ? static_cast<float>(static_cast<double>(g) / go.divisors[k]) : 0.f;
+      if (k == go.k0 && blockIdx.x == 0 && threadIdx.x == 0 && go.upstream_out && go.g[k])
+        *go.upstream_out = __fdiv_rn(g, go.hint_weights[k]);
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) sc[k] = scales[k];
+  }
   if (scales_used) {
     // `grad` already holds the gradient the one-pass kernel wrote for the scales it ASSUMED: nothing to do if the scales
     // autograd actually delivered are the same bits (every thread takes the same branch; no barrier has been reached)
@@ -1066,8 +1093,12 @@ __global__ void __launch_bounds__(kThreadsL) k_loss_bwd_generic(LossArgs a, cons
 }
 
 // Final deterministic reduction of the per-CTA partials (one CTA, fixed order).
+// `losses` != nullptr: also the four unweighted loss terms f32[4] = float(sum / divisor) (0 for a disabled term, NaN for an empty
+// region exactly like the reference's 0/0) and the divisors f64[4] = (n_conf, C n_conf, C n_ign, #non-zero SoftCE products) --
+// the arithmetic of hiast_b200/losses.py FusedSelfTrainingLoss.forward, in this launch instead of a dozen tiny torch kernels.
 __global__ void k_loss_finalize(const Partial* __restrict__ partials, int n, double* __restrict__ sums,
-                                long long* __restrict__ counts) {
+                                long long* __restrict__ counts, float* __restrict__ losses, double* __restrict__ divisors,
+                                int C, int terms, const float* __restrict__ term_weights) {
   __shared__ Partial s_part[kThreadsL / 32];
   pdl_wait();                              // no-op unless launched as a programmatic dependent (hiast_st_loss_fused)
   PixelSums acc = {0.0, 0.0, 0.0, 0.0, 0, 0, 0};
@@ -1092,6 +1123,15 @@ __global__ void k_loss_finalize(const Partial* __restrict__ partials, int n, dou
     }
     for (int k = 0; k < 4; ++k) sums[k] = r.s[k];
     for (int k = 0; k < 3; ++k) counts[k] = r.n[k];
+    if (losses) {
+      const double den[4] = {static_cast<double>(r.n[0]), static_cast<double>(C) * static_cast<double>(r.n[0]),
+                             static_cast<double>(C) * static_cast<double>(r.n[1]), static_cast<double>(r.n[2])};
+      for (int k = 0; k < 4; ++k) {
+        divisors[k] = den[k];
+        const float v = ((terms >> k) & 1) ? static_cast<float>(r.s[k] / den[k]) : 0.f;
+        losses[k] = term_weights ? __fmul_rn(term_weights[k], v) : v;      // w_k * loss_k in f32, as torch multiplies them
+      }
+    }
   }
 }
 
@@ -1179,7 +1219,7 @@ extern "C" int hiast_st_loss_fwd(const float* z, const float* t, const void* plb
     k_loss_fwd_generic<<<grid, kThreadsL, 0, st>>>(a, parts);
   }
   HIAST_CHECK_LAUNCH();
-  k_loss_finalize<<<1, kThreadsL, 0, st>>>(parts, grid, sums, reinterpret_cast<long long*>(counts));
+  k_loss_finalize<<<1, kThreadsL, 0, st>>>(parts, grid, sums, reinterpret_cast<long long*>(counts), nullptr, nullptr, C, terms, nullptr);
   HIAST_CHECK_LAUNCH();
   return HIAST_OK;
 }
@@ -1199,8 +1239,9 @@ extern "C" int hiast_st_loss_bwd(const float* z, const float* t, const void* plb
     HIAST_TRY(loss_configure_smem(C, smem));
     const bool packed = cst_kind_host(terms) == HIAST_CST_SOFTCE && !g_loss_scalar;
     if (packed) {
-      if (C == 19) k_loss_bwd_pk<19><<<grid, kThreadsL, smem, st>>>(a, scales, grad_z, nullptr);
-      else k_loss_bwd_pk<16><<<grid, kThreadsL, smem, st>>>(a, scales, grad_z, nullptr);
+      const GoutArgs none = {{nullptr, nullptr, nullptr, nullptr}, nullptr, nullptr, nullptr, 0, nullptr};
+      if (C == 19) k_loss_bwd_pk<19><<<grid, kThreadsL, smem, st>>>(a, scales, grad_z, nullptr, none);
+      else k_loss_bwd_pk<16><<<grid, kThreadsL, smem, st>>>(a, scales, grad_z, nullptr, none);
     } else {
       if (C == 19) k_loss_bwd<19><<<grid, kThreadsL, smem, st>>>(a, scales, grad_z);
       else k_loss_bwd<16><<<grid, kThreadsL, smem, st>>>(a, scales, grad_z);
@@ -1238,6 +1279,15 @@ static cudaError_t launch_dependent(void (*kernel)(KArgs...), int grid, int bloc
 extern "C" int hiast_st_loss_fused(const float* z, const float* t, const void* plbl, int plbl_bytes, int B, int C, int64_t HW,
                                    int region, int terms, const float* grad_weights, double* sums, int64_t* counts,
                                    float* scales_used, float* grad_z, void* workspace, size_t workspace_bytes, void* stream) {
+  return hiast_st_loss_fused_terms(z, t, plbl, plbl_bytes, B, C, HW, region, terms, grad_weights, sums, counts, scales_used, grad_z,
+                                   nullptr, nullptr, nullptr, workspace, workspace_bytes, stream);
+}
+
+extern "C" int hiast_st_loss_fused_terms(const float* z, const float* t, const void* plbl, int plbl_bytes, int B, int C,
+                                         int64_t HW, int region, int terms, const float* grad_weights, double* sums,
+                                         int64_t* counts, float* scales_used, float* grad_z, float* losses, double* divisors,
+                                         const float* term_weights, void* workspace, size_t workspace_bytes, void* stream) {
+  if ((losses == nullptr) != (divisors == nullptr)) return HIAST_ERR_INVALID_ARG;
   const int rc = check_loss_args(z, t, plbl, plbl_bytes, B, C, HW, region, terms);
   if (rc != HIAST_OK) return rc;
   if (!grad_weights || !sums || !counts || !scales_used || !grad_z || !workspace) return HIAST_ERR_INVALID_ARG;
@@ -1270,16 +1320,17 @@ extern "C" int hiast_st_loss_fused(const float* z, const float* t, const void* p
     HIAST_CUDA_TRY(launch_dependent(k_loss_fused_pk<16>, grid, kThreadsL, smem, st, a, lc, grad_weights, scales_used, grad_z, parts,
                                     cgrid));
   }
-  HIAST_CUDA_TRY(launch_dependent(k_loss_finalize, 1, kThreadsL, 0, st, parts, grid, sums, reinterpret_cast<long long*>(counts)));
+  HIAST_CUDA_TRY(launch_dependent(k_loss_finalize, 1, kThreadsL, 0, st, parts, grid, sums, reinterpret_cast<long long*>(counts),
+                                  losses, divisors, C, terms, term_weights));
   return HIAST_OK;
 }
 
-extern "C" int hiast_st_loss_bwd_checked(const float* z, const float* t, const void* plbl, int plbl_bytes, int B, int C,
-                                         int64_t HW, int region, int terms, const float* scales, const float* scales_used,
-                                         float* grad_z, void* stream) {
+static int bwd_checked_launch(const float* z, const float* t, const void* plbl, int plbl_bytes, int B, int C, int64_t HW,
+                              int region, int terms, const float* scales, const float* scales_used, float* grad_z,
+                              const GoutArgs& go, void* stream) {
   const int rc = check_loss_args(z, t, plbl, plbl_bytes, B, C, HW, region, terms);
   if (rc != HIAST_OK) return rc;
-  if (!scales || !scales_used || !grad_z) return HIAST_ERR_INVALID_ARG;
+  if ((!scales && !go.divisors) || !scales_used || !grad_z) return HIAST_ERR_INVALID_ARG;
   if (B == 0) return HIAST_OK;
   LossArgs a = {z, t, plbl, plbl_bytes, B, C, HW, region, terms};
   if (!loss_vector_ok(a, grad_z) || cst_kind_host(terms) != HIAST_CST_SOFTCE) return HIAST_ERR_UNSUPPORTED;
@@ -1287,8 +1338,26 @@ extern "C" int hiast_st_loss_bwd_checked(const float* z, const float* t, const v
   const int grid = std::min(loss_grid(static_cast<long long>(B) * HW), sm_count() * 2);
   const size_t smem = loss_stage_bytes(C);
   HIAST_TRY(loss_configure_smem(C, smem));
-  if (C == 19) k_loss_bwd_pk<19><<<grid, kThreadsL, smem, st>>>(a, scales, grad_z, scales_used);
-  else k_loss_bwd_pk<16><<<grid, kThreadsL, smem, st>>>(a, scales, grad_z, scales_used);
+  if (C == 19) k_loss_bwd_pk<19><<<grid, kThreadsL, smem, st>>>(a, scales, grad_z, scales_used, go);
+  else k_loss_bwd_pk<16><<<grid, kThreadsL, smem, st>>>(a, scales, grad_z, scales_used, go);
   HIAST_CHECK_LAUNCH();
   return HIAST_OK;
+}
+
+extern "C" int hiast_st_loss_bwd_checked(const float* z, const float* t, const void* plbl, int plbl_bytes, int B, int C,
+                                         int64_t HW, int region, int terms, const float* scales, const float* scales_used,
+                                         float* grad_z, void* stream) {
+  if (!scales) return HIAST_ERR_INVALID_ARG;
+  const GoutArgs none = {{nullptr, nullptr, nullptr, nullptr}, nullptr, nullptr, nullptr, 0, nullptr};
+  return bwd_checked_launch(z, t, plbl, plbl_bytes, B, C, HW, region, terms, scales, scales_used, grad_z, none, stream);
+}
+
+extern "C" int hiast_st_loss_bwd_checked_terms(const float* z, const float* t, const void* plbl, int plbl_bytes, int B, int C,
+                                               int64_t HW, int region, int terms, const float* gout_ce, const float* gout_kld,
+                                               const float* gout_ent, const float* gout_cst, const double* divisors,
+                                               const float* scales_used, float* grad_z, const float* term_weights,
+                                               const float* hint_weights, int k0, float* upstream_out, void* stream) {
+  if (!divisors || k0 < 0 || k0 > 3 || (upstream_out && !hint_weights)) return HIAST_ERR_INVALID_ARG;
+  const GoutArgs go = {{gout_ce, gout_kld, gout_ent, gout_cst}, divisors, hint_weights, upstream_out, k0, term_weights};
+  return bwd_checked_launch(z, t, plbl, plbl_bytes, B, C, HW, region, terms, nullptr, scales_used, grad_z, go, stream);
 }

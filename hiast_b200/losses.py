@@ -75,6 +75,66 @@ class FusedSelfTrainingLoss(torch.autograd.Function):
         return grad, None, None, None, None, None, None
 
 
+class FusedTermsLean(torch.autograd.Function):
+    """The four loss terms as FOUR outputs (0-d float32 tensors) with everything around the kernels done on the device:
+    ``hiast_st_loss_fused_terms`` divides the sums by their counts in its finalize launch, ``hiast_st_loss_bwd_checked_terms``
+    derives the gradient scales from the four upstream gradients autograd hands back and records the upstream scalar for
+    the next step's expectation.  Forward = 1 tiny multiply (the hint) + 3 chained launches; backward = 1 launch that exits at
+    once in the steady state.  (``FusedSelfTrainingLoss`` composes the same numbers from a dozen tiny torch kernels each way;
+    it remains the path for every configuration the one-pass kernel does not cover.)  Same bits as that composition."""
+
+    @staticmethod
+    def forward(ctx, z, t, plbl, region, terms, hint, weighted):
+        # weighted: the outputs are w_k * loss_k with the hint's weights (the products of self_training_segmentor.py:37-52 and
+        # their MulBackward nodes move into the two kernels as well)
+        one = ops.st_loss_fused_terms(z, t, plbl, hint.tensor(), region, terms, term_weights=hint.weights if weighted else None)
+        if one is None:
+            raise HiastError('configuration not covered by the one-pass kernel')        # callers check `lean_ok` first
+        losses, divisors, used, grad, _, _ = one
+        ctx.save_for_backward(z, t, plbl, divisors, used, grad)
+        ctx.region, ctx.terms, ctx.hint, ctx.weighted = region, terms, hint, weighted
+        ctx.set_materialize_grads(False)
+        return tuple(losses.unbind(0))
+
+    @staticmethod
+    def backward(ctx, g_ce, g_kld, g_ent, g_cst):
+        z, t, plbl, divisors, used, grad = ctx.saved_tensors
+        hint = ctx.hint
+        gouts = [g if g is None else g.to(torch.float32).contiguous() for g in (g_ce, g_kld, g_ent, g_cst)]
+        grad = ops.st_loss_bwd_checked_terms(z, t, plbl, gouts, divisors, used, grad, ctx.region, ctx.terms,
+                                             hint_weights=hint.weights, k0=hint.k0,
+                                             upstream_out=hint.upstream if gouts[hint.k0] is not None else None,
+                                             term_weights=hint.weights if ctx.weighted else None)
+        return grad, None, None, None, None, None, None
+
+
+def lean_ok(z, plbl, terms, cst_mean_all, grad_hint):
+    """The conditions under which ``hiast_st_loss_fused_terms`` launches (loss.cu: SoftCE kind, C in {16, 19}, even HW, 8-byte
+    aligned tensors) and a gradient is wanted."""
+    kind = terms & CST_SOFTCE_LOGITS
+    return (grad_hint is not None and not cst_mean_all and kind == CST_SOFTCE and z.requires_grad and torch.is_grad_enabled() and
+            z.shape[1] in (16, 19) and z[0, 0].numel() % 2 == 0 and z.shape[0] > 0 and z.data_ptr() % 8 == 0)
+
+
+def fused_terms_split(logits, plbl, target=None, region='ignored', terms=TERM_CE | TERM_KLD | TERM_ENT | TERM_CST,
+                      grad_hint=None, weighted=False):
+    """(CE, KLD, ENT, CST) as four 0-d tensors.  With a ``GradHint`` and a covered configuration: the lean one-pass path; else the
+    entries of ``fused_terms``.  ``weighted``: each term comes multiplied by its weight of the ``GradHint`` (required then) --
+    ``w * term`` in float32, exactly what the caller would compute."""
+    z = _prep_logits(logits)
+    t = None
+    if terms & TERM_CST:
+        t = _prep_logits(target)
+        assert t.shape == z.shape                                     # losses.py:50
+    y = _prep_labels(plbl)
+    if lean_ok(z, y, terms, False, grad_hint) and (t is None or t.data_ptr() % 8 == 0):
+        return FusedTermsLean.apply(z, t, y, region, terms, grad_hint, bool(weighted))
+    out = fused_terms(z, y, t, region=region, terms=terms, grad_hint=grad_hint)
+    if weighted:
+        return tuple(w * out[k] for k, w in enumerate(grad_hint.weight_values))
+    return out[0], out[1], out[2], out[3]
+
+
 class GradHint:
     """Expected upstream gradients for ``fused_terms(..., grad_hint=...)``: the caller's four loss weights times the upstream
     scalar of the LAST backward seen on this device (1.0 at first; a loss scaler's factor after one step), kept on the
@@ -86,7 +146,8 @@ class GradHint:
 
     def __init__(self, weights, device):
         self.device = torch.device(device)
-        self.weights = torch.tensor([float(w) for w in weights], dtype=torch.float32, device=self.device)
+        self.weight_values = tuple(float(w) for w in weights)
+        self.weights = torch.tensor(self.weight_values, dtype=torch.float32, device=self.device)
         key = (self.device.type, self.device.index)
         if key not in GradHint._upstream:
             GradHint._upstream[key] = torch.ones((), dtype=torch.float32, device=self.device)

@@ -364,6 +364,63 @@ def st_loss_fused(z, t, plbl, grad_weights, region='ignored', terms=TERM_CE | TE
     return sums, counts, used, grad
 
 
+def st_loss_fused_terms(z, t, plbl, grad_weights, region='ignored', terms=TERM_CE | TERM_KLD | TERM_ENT | TERM_CST, grad=None,
+                        term_weights=None):
+    """``st_loss_fused`` with the four loss terms and their divisors computed on the device as well (hiast_st_loss_fused_terms).
+    Returns (losses f32[4], divisors f64[4], scales_used f32[4], grad_z, sums f64[4], counts i64[3]) or None when the
+    configuration is not covered.  The small outputs are slices of ONE allocation (the caller keeps them for backward).
+    ``term_weights`` f32[4] (device): ``losses`` then holds the weighted terms w_k * loss_k."""
+    require_cuda(z, torch.float32, 'logits')
+    require_cuda(grad_weights, torch.float32, 'grad_weights')
+    b, c = z.shape[0], z.shape[1]
+    hw = z[0, 0].numel() if b else 1
+    if t is not None:
+        require_cuda(t, torch.float32, 'target')
+        assert t.shape == z.shape
+    _plbl_arg(plbl)
+    assert plbl.numel() == b * hw
+    dev = z.device
+    need = lib().hiast_st_loss_fused_workspace_bytes(b, c, hw)
+    key = ('fused', dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < need:
+        ws = _ws_cache[key] = torch.empty(max(need, 1 << 16), dtype=torch.uint8, device=dev)
+    small = torch.empty(15, dtype=torch.float64, device=dev)          # sums 4 | counts 3 | divisors 4 | losses 4 f32 | used 4 f32
+    sums, counts, divisors = small[0:4], small[4:7].view(torch.int64), small[7:11]
+    f32 = small[11:15].view(torch.float32)
+    losses, used = f32[0:4], f32[4:8]
+    if grad is None:
+        grad = torch.empty_like(z)
+    status = lib().hiast_st_loss_fused_terms(ptr(z), ptr(t), ptr(plbl), plbl.element_size(), b, c, hw, REGION[region], int(terms),
+                                             ptr(grad_weights), ptr(sums), ptr(counts), ptr(used), ptr(grad), ptr(losses),
+                                             ptr(divisors), ptr(term_weights), ptr(ws), ws.numel(), stream_ptr(dev))
+    if status == UNSUPPORTED:
+        return None
+    check(status, 'hiast_st_loss_fused_terms')
+    return losses, divisors, used, grad, sums, counts
+
+
+def st_loss_bwd_checked_terms(z, t, plbl, gouts, divisors, scales_used, grad, region='ignored',
+                              terms=TERM_CE | TERM_KLD | TERM_ENT | TERM_CST, hint_weights=None, k0=0, upstream_out=None,
+                              term_weights=None):
+    """``st_loss_bwd_checked`` with the scales derived on the device from the upstream gradients ``gouts`` (four 0-d f32 CUDA
+    tensors or None) and ``divisors`` f64[4]; optionally records gout[k0] / hint_weights[k0] in ``upstream_out``.  With
+    ``term_weights`` the ``gouts`` are the gradients of the WEIGHTED terms (gout_k = gouts[k] * w_k)."""
+    b, c = z.shape[0], z.shape[1]
+    hw = z[0, 0].numel() if b else 1
+    gp = []
+    for g in gouts:
+        if g is not None:
+            require_cuda(g, torch.float32, 'upstream gradient')
+        gp.append(ptr(g))
+    check(lib().hiast_st_loss_bwd_checked_terms(ptr(z), ptr(t), ptr(plbl), plbl.element_size(), b, c, hw, REGION[region],
+                                                int(terms), gp[0], gp[1], gp[2], gp[3], ptr(divisors), ptr(scales_used),
+                                                ptr(grad), ptr(term_weights), ptr(hint_weights), int(k0), ptr(upstream_out),
+                                                stream_ptr(z.device)),
+          'hiast_st_loss_bwd_checked_terms')
+    return grad
+
+
 def st_loss_bwd_checked(z, t, plbl, scales, scales_used, grad, region='ignored', terms=TERM_CE | TERM_KLD | TERM_ENT | TERM_CST):
     """``grad`` (written by ``st_loss_fused`` for ``scales_used``) is left alone if ``scales`` are the same bits, else rewritten."""
     require_cuda(scales, torch.float32, 'scales')

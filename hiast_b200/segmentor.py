@@ -20,7 +20,7 @@ from torch import nn
 from torch.nn import functional as F
 
 from ._lib import TERM_CE, TERM_CST, TERM_ENT, TERM_KLD
-from .losses import IGNORE, GradHint, fused_terms
+from .losses import IGNORE, GradHint, fused_terms, fused_terms_split
 from .registry import LOSS, MODEL, SEG_MODEL
 
 # What build_region_weight hands to _kld / _entropy instead of a dense [B,C,H,W] tensor.
@@ -122,12 +122,19 @@ class SelfTrainingSegmentor(nn.Module):
             hint = self.__dict__.setdefault('_hints', {}).get(key)
             if hint is None:
                 hint = self._hints[key] = GradHint(weights, t_logits.device)
-        out = fused_terms(t_logits, t_plbl, t_cst_lbl if use_cst else None, region=region, terms=terms, grad_hint=hint)
-        losses['target_seg_loss'] = w_seg * out[0]
+        if hint is not None:
+            # the weighted terms themselves come out of the kernels (w * loss in float32, as the products below would give)
+            out = fused_terms_split(t_logits, t_plbl, t_cst_lbl if use_cst else None, region=region, terms=terms, grad_hint=hint,
+                                    weighted=True)
+            scale = (1.0, 1.0, 1.0, 1.0)
+        else:
+            out = fused_terms_split(t_logits, t_plbl, t_cst_lbl if use_cst else None, region=region, terms=terms)
+            scale = weights
+        losses['target_seg_loss'] = out[0] if hint is not None else scale[0] * out[0]
         if w_kld > 0:
-            losses['kld_confident_loss'] = w_kld * out[1]
+            losses['kld_confident_loss'] = out[1] if hint is not None else scale[1] * out[1]
         if w_ent > 0:
-            losses['ent_ignored_loss'] = w_ent * out[2]
+            losses['ent_ignored_loss'] = out[2] if hint is not None else scale[2] * out[2]
         if use_cst:
-            losses['cst_loss'] = cfg.cst_training.cst_loss.weight * out[3]
+            losses['cst_loss'] = out[3] if hint is not None else scale[3] * out[3]
         return losses

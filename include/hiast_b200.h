@@ -237,6 +237,27 @@ HIAST_API int hiast_st_loss_bwd_checked(const float* z, const float* t, const vo
                               int64_t HW, int region, int terms, const float* scales, const float* scales_used,
                               float* grad_z, void* stream);
 
+/* The same two calls with the arithmetic AROUND the kernels done on the device as well (self_training_segmentor.py:30-53 divides
+ * every sum by its count and autograd multiplies the upstream gradients back in: a dozen tiny launches per step otherwise).
+ * hiast_st_loss_fused_terms additionally writes losses f32[4] = float(sums[k] / divisors[k]) (0 for a disabled term; NaN for an
+ * empty region, the reference's 0/0) and divisors f64[4] = {n_conf, C*n_conf, C*n_ign, counts[2]} (both or neither may be NULL).
+ * hiast_st_loss_bwd_checked_terms takes the upstream gradient of each of the four loss terms as a device pointer to one f32
+ * (NULL: no gradient flows into that term) and derives scales[k] = float(double(*gout_k) / divisors[k]) itself; if upstream_out
+ * != NULL it also stores gout_{k0} / hint_weights[k0] there (the upstream scalar the next forward call should assume).
+ * term_weights f32[4] (device, may be NULL): the caller's loss weights.  With them `losses` holds the WEIGHTED terms
+ * w_k * loss_k (float32 product, what `weight * loss` gives in torch) and the backward call takes the upstream gradients of
+ * those weighted terms: gout_k = *gout_k_ptr * w_k -- the reference's `w * loss` products and their MulBackward nodes
+ * (self_training_segmentor.py:37-52) without their eight launches.                                                         */
+HIAST_API int hiast_st_loss_fused_terms(const float* z, const float* t, const void* plbl, int plbl_bytes, int B, int C, int64_t HW,
+                              int region, int terms, const float* grad_weights, double* sums, int64_t* counts,
+                              float* scales_used, float* grad_z, float* losses, double* divisors,
+                              const float* term_weights, void* workspace, size_t workspace_bytes, void* stream);
+HIAST_API int hiast_st_loss_bwd_checked_terms(const float* z, const float* t, const void* plbl, int plbl_bytes, int B, int C,
+                                    int64_t HW, int region, int terms, const float* gout_ce, const float* gout_kld,
+                                    const float* gout_ent, const float* gout_cst, const double* divisors,
+                                    const float* scales_used, float* grad_z, const float* term_weights,
+                                    const float* hint_weights, int k0, float* upstream_out, void* stream);
+
 /* ---- (4) confusion matrix / mIoU  utils/metrics.py:6-19 --------------------------------- */
 /* cm i64 [(K+1),(K+1)] (rows = target, cols = pred, index K = value outside [0,K)),
  * ACCUMULATED over the pixels whose target != ignore_index.  If pred_masked_out != NULL it

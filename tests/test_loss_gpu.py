@@ -370,3 +370,75 @@ def test_one_pass_empty_regions_reproduce_the_reference_nans():
     assert torch.isfinite(out['target_seg_loss'])
     sum(out.values()).backward()
     assert torch.isnan(z.grad).all()
+
+
+# ------------------------------------------------------------------ lean one-pass path (hiast_st_loss_fused_terms / _bwd_checked_terms)
+@pytest.mark.parametrize('region', ['ignored', 'confident', 'all'])
+def test_fused_terms_kernel_outputs_equal_the_host_composition(region):
+    """losses / divisors written by the finalize launch == sums / counts composed with torch ops, bit for bit; the scales the
+    backward kernel derives from four upstream gradients == the host arithmetic (gradient identical to the checked call)."""
+    from hiast_b200 import ops
+    z, t, y = _loss_inputs((2, 19, 40, 64), 11)
+    gw = torch.tensor([1.0, 0.1, 1.0, 0.5], device='cuda')
+    losses, divisors, used, grad, sums, counts = ops.st_loss_fused_terms(z, t, y, gw, region)
+    sums2, counts2, used2, grad2 = ops.st_loss_fused(z, t, y, gw, region)
+    assert torch.equal(sums, sums2) and torch.equal(counts, counts2) and torch.equal(used, used2) and torch.equal(grad, grad2)
+    cnt = counts.double()
+    want_div = torch.stack([cnt[0], 19 * cnt[0], 19 * cnt[1], cnt[2]])
+    assert torch.equal(divisors, want_div)
+    assert torch.equal(losses, (sums / want_div).float())
+    # backward: upstream gradients that differ from the assumption -> rewritten with the scales the host would compute
+    gouts = [torch.tensor(v, device='cuda') for v in (3.0, 0.25, 1.5, 0.75)]
+    want_scales = (torch.stack(gouts).double() / want_div).float()
+    want = ops.st_loss_bwd(z, t, y, want_scales, region)
+    up = torch.zeros((), device='cuda')
+    got = ops.st_loss_bwd_checked_terms(z, t, y, gouts, divisors, used, grad.clone(), region, hint_weights=gw, k0=1, upstream_out=up)
+    assert torch.equal(got, want)
+    assert up.item() == np.float32(0.25) / np.float32(0.1)
+    # a term without upstream gradient counts as scale 0; equal scales leave the gradient alone
+    gouts[2] = None
+    want_scales[2] = 0.0
+    got = ops.st_loss_bwd_checked_terms(z, t, y, gouts, divisors, used, grad.clone(), region)
+    assert torch.equal(got, ops.st_loss_bwd(z, t, y, want_scales, region))
+    sentinel = torch.full_like(grad, 7.0)
+    ops.st_loss_bwd_checked_terms(z, t, y, [g for g in gw], divisors, used, sentinel, region)
+    assert bool((sentinel == 7.0).all())
+
+
+def test_lean_path_is_taken_and_equals_the_composed_path():
+    """compute_loss goes through FusedTermsLean (four outputs, no select / stack kernels) and gives the same values and the same
+    gradient bits as the composed one-pass path; an unused term (no gradient flows into it) is handled."""
+    from hiast_b200 import losses as L
+    z0, t, y = _loss_inputs((2, 19, 48, 64), 21)
+    hint = L.GradHint((1.0, 0.1, 1.0, 0.5), z0.device)
+    hint.upstream.fill_(1.0)
+    wts = (1.0, 0.1, 1.0, 0.5)
+    z = z0.clone().requires_grad_(True)
+    assert L.lean_ok(z, y, 15, False, hint)
+    lean = L.fused_terms_split(z, y, t, region='ignored', terms=15, grad_hint=hint)
+    assert all(v.dim() == 0 and v.dtype == torch.float32 for v in lean)
+    assert type(lean[0].grad_fn).__name__.startswith('FusedTermsLean')
+    sum(w * v for w, v in zip(wts, lean)).backward()
+    z2 = z0.clone().requires_grad_(True)
+    comp = L.fused_terms(z2, y, t, region='ignored', terms=15, grad_hint=hint)
+    sum(w * comp[k] for k, w in enumerate(wts)).backward()
+    assert [v.item() for v in lean] == [comp[k].item() for k in range(4)]
+    assert torch.equal(z.grad, z2.grad)
+    # only two of the four terms enter the loss
+    z3 = z0.clone().requires_grad_(True)
+    lean = L.fused_terms_split(z3, y, t, region='ignored', terms=15, grad_hint=hint)
+    (lean[0] + 0.5 * lean[3]).backward()
+    z4 = z0.clone().requires_grad_(True)
+    ref = oloss.compute_loss(z4, y, t, w_kld=0.0, w_ent=0.0)          # CE + 0.5 SoftCE('ignored') only
+    sum(ref.values()).backward()
+    grad_close(z3.grad, z4.grad)
+    # weighted outputs: w_k * term_k out of the kernels == the products composed by torch, values and gradient bits
+    z5 = z0.clone().requires_grad_(True)
+    wl = L.fused_terms_split(z5, y, t, region='ignored', terms=15, grad_hint=hint, weighted=True)
+    z6 = z0.clone().requires_grad_(True)
+    pl = L.fused_terms_split(z6, y, t, region='ignored', terms=15, grad_hint=hint)
+    prods = [w * v for w, v in zip(wts, pl)]
+    assert [v.item() for v in wl] == [v.item() for v in prods]
+    (sum(wl) * 3.0).backward()
+    (sum(prods) * 3.0).backward()
+    assert torch.equal(z5.grad, z6.grad)
