@@ -20,7 +20,12 @@ of 64 synthetic maps (10.2 GB: every step streams 80x the L2, no flush needed).
                 cores, on a bounded sample of the same workload; the oracle port only if that copy is absent.
 
 Multi-GPU (torchrun, one rank per GPU): windows are striped over ranks and the 19-double threshold state is
-handed rank to rank with NCCL send/recv (hiast_b200/sharded.py); weak scaling, per-GPU work fixed.
+handed rank to rank INSIDE the scan kernel through CUDA-IPC peer memory (NCCL send/recv as the fallback;
+hiast_b200/sharded.py); one NCCL all-gather at the end of the job; weak scaling, per-GPU work fixed.  After the
+timed job the same global job is replayed on rank 0 alone for two windows per rank: `parity`.
+
+Inside the warm-up the schedule is calibrated (`config.schedule_calibration_ms_per_step`): SMs reserved from phase A
+for the scan and the mask pass of the window before, or the serial order -- whichever is faster on this box.
 """
 
 from __future__ import annotations
