@@ -23,6 +23,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--steps', type=int, default=12)
     ap.add_argument('--out', default='gpurun_out/sharded_timeline.json')
+    ap.add_argument('--only-first', action='store_true', help='only the concurrent schedule with the peer-memory ring')
     args = ap.parse_args()
     rank, world, local = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1)), int(os.environ.get('LOCAL_RANK', 0))
     torch.cuda.set_device(local)
@@ -64,13 +65,41 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    def mark(what):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(torch.cuda.current_stream(device))
+        marks.append((what, ev))
+
+    class Probed(ShardedIAS):
+        """finish_state with marks on the main stream: fs0 = main reaches it (the last phase A has ended), ag0 / ag1 = around the
+        all-gather (ag0 comes after the chain stream has drained and the packing kernels), end = everything queued has run."""
+        def finish_state(self):
+            mark('fs0')
+            real = dist.all_gather
+
+            def timed_all_gather(*a, **k):
+                mark('ag0')
+                out = real(*a, **k)
+                mark('ag1')
+                return out
+            if world > 1:
+                dist.all_gather = timed_all_gather
+            try:
+                return super().finish_state()
+            finally:
+                dist.all_gather = real
+                mark('end')
+
     def job(k, eng):
-        drv = ShardedIAS(eng, bench.WINDOW, k * world * bench.WINDOW, rank, world)
+        drv = Probed(eng, bench.WINDOW, k * world * bench.WINDOW, rank, world)
         drv.warm_collective()
         return drv, drv.run(lambda w: pool, None)
 
     results = {}
-    for mode, reserve, ringmode in (('concurrent', 12, 'peer'), ('serial', 0, 'peer'), ('concurrent', 12, 'nccl'), ('serial', 0, 'nccl')):
+    modes = (('concurrent', 12, 'peer'), ('serial', 0, 'peer'), ('concurrent', 12, 'nccl'), ('serial', 0, 'nccl'))
+    if args.only_first:
+        modes = modes[:1]
+    for mode, reserve, ringmode in modes:
         if world == 1 and ringmode == 'nccl':
             continue
         os.environ['HIAST_RING'] = ringmode
@@ -88,7 +117,8 @@ def main():
         barrier()
         ms = t0.elapsed_time(t1)
         tl = [(what, round(t0.elapsed_time(ev), 3)) for what, ev in marks]
-        res = {'ms_per_step': ms / args.steps, 'ring': 'peer' if drv.ring is not None else 'nccl', 'timeline': tl[:60]}
+        res = {'ms_per_step': ms / args.steps, 'ring': 'peer' if drv.ring is not None else 'nccl', 'timeline': tl[:60],
+               'tail': tl[-12:], 'total_ms': ms}
         allres = [None] * world
         if world > 1:
             dist.all_gather_object(allres, res)
@@ -104,6 +134,7 @@ def main():
             print('==', key)
             for r, res in enumerate(allres):
                 print(' rank', r, ' '.join('%s@%.2f' % (w, t) for w, t in res['timeline'][:30]))
+                print('   tail', ' '.join('%s@%.2f' % (w, t) for w, t in res['tail']), 'total %.2f' % res['total_ms'])
     if world > 1:
         dist.destroy_process_group()
 
