@@ -560,6 +560,8 @@ def measure_extra(device, rank, world, barrier):
         leg('configs2_loss_fwd_bwd', bx.loss_leg, device, peak)
         leg('copy_paste_kernel', bx.copy_paste_leg, device, peak)
         leg('confusion_kernel', bx.confusion_leg, device, peak)
+        leg('configs1_by_distribution', bx.distributions_leg, device, peak, make_pool,
+            int(os.environ.get('HIAST_RESERVE_SMS', RESERVE_SMS)))
     leg('configs3_synthia_ias_copy_paste', bx.synthia_leg, device, rank, world, barrier)
     leg('configs4_full_round', bx.full_round_leg, device, rank, world, barrier)
     return out

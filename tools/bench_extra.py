@@ -5,6 +5,7 @@ Each function returns a plain dict that bench.py puts under ``extra`` in its JSO
 * ``loss_leg``        configs[2]  region-adaptive regularisation + consistency loss fwd/bwd, 2x19x512x1024, with its own roofline
 * ``copy_paste_leg``  the masked-gather kernel (13 B/px) at 1024x2048x3
 * ``confusion_leg``   the privatised bincount (16 B/px, int64 as the reference calls it)
+* ``distributions_leg`` configs[1] on each of the two logit distributions of SURVEY 8d alone (the headline pool alternates them)
 * ``synthia_leg``     configs[3]  SYNTHIA 16-class IAS + run_batch copy-paste (batch-level donor sampler) over the ranks,
                       with a sharded-vs-single-rank parity check
 * ``full_round_leg``  configs[4]  random-init DeepLabv2-ResNet101 forward -> IAS pseudo-labels -> confusion matrix / mIoU
@@ -118,6 +119,39 @@ def confusion_leg(device, peak):
     ms = _median_ms(lambda: ops.confusion_matrix(pred, tgt, 19, cm=cm))
     return {'workload': '19x19 confusion matrix, 8 maps 1024x2048, int64 prediction and target (as metrics.py:6-19 is called), random labels',
             'images_per_s': n / ms * 1e3, 'roofline': _roof(n * H * W * 16, ms, peak)}
+
+
+def distributions_leg(device, peak, make_pool, reserve_sms, steps=10, window=64):
+    """SURVEY 8d config 2 asks for BOTH logit distributions: D1 "diffuse" (randn * 3: uniform class mix, confidences spread over
+    many fp16 keys) and D2 "peaked" (a low-resolution field up-sampled x32 + noise: coherent classes, most confidences near 1.0,
+    the worst case for the histogram tables).  The headline pool alternates them; here each one alone, same pipeline, one GPU."""
+    from hiast_b200.ias_engine import IASEngine
+    from hiast_b200.sharded import ShardedIAS
+    C, H, W, B = 19, 1024, 2048, 2
+    engine = IASEngine(C, H, W, B, 0.5, 0.9, 8.0, 0.99, 3 * window, device=device)
+    engine.reserve_sms = int(reserve_sms)
+    out = {'workload': 'configs[1] per distribution: %d windows of %d maps, one GPU, device-resident' % (steps, window)}
+    for name in ('diffuse', 'peaked'):
+        pool = make_pool(device, name, window)
+
+        def job(k):
+            engine.thr_state.fill_(0.9)
+            engine.mean_state.zero_()
+            return ShardedIAS(engine, window, k * window, 0, 1).run(lambda w: pool)
+        job(3)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _, _, statics = job(steps)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        ips = window / ms * 1e3
+        out[name] = {'images_per_s': ips, 'ms_per_step': ms, 'hbm_frac_of_peak': ips * H * W * (4 * C + 1) / 1e9 / peak,
+                     'kept_pixel_fraction': float(statics.sum().item()) / (steps * window * H * W)}
+        del pool
+    engine.check_errors()
+    return out
 
 
 class _PoolDonors:
