@@ -35,13 +35,14 @@ _STREAMS = {}
 
 
 def device_stream(device, kind):
-    """One host-to-device copy stream ('copy'), one device-to-host stream ('out') and one high-priority chain stream ('chain') per device for the life of the process (NCCL and
+    """One host-to-device copy stream ('copy'), one device-to-host stream ('out'), one high-priority chain stream ('chain') and one
+    high-priority stream for phase C beside phase A ('select') per device for the life of the process (NCCL and
     the caching allocator keep per-stream state; a fresh stream per run would pay for it again)."""
     device = torch.device(device)
     key = (kind, device.index if device.index is not None else torch.cuda.current_device())
     st = _STREAMS.get(key)
     if st is None:
-        st = _STREAMS[key] = torch.cuda.Stream(device, priority=-1 if kind == 'chain' else 0)
+        st = _STREAMS[key] = torch.cuda.Stream(device, priority=-1 if kind in ('chain', 'select') else 0)
     return st
 
 
@@ -164,6 +165,7 @@ class ShardedIAS:
             if (self.cuda and use_dist and self.world > 1) else None
         if self.cuda:
             self.side = device_stream(engine.device, 'chain')
+            self.select = device_stream(engine.device, 'select')
             self.ev_a = [torch.cuda.Event() for _ in range(self.n_slots)]
             self.ev_b = [torch.cuda.Event() for _ in range(self.n_slots)]
         self._stash_conf = self._stash_counts = None
@@ -227,8 +229,9 @@ class ShardedIAS:
         leaves ``reserve_sms`` SMs empty, and the chain stream runs the scan (token hand-off inside) AND phase C of window j there
         while phase A of window j+1 streams on the others:
 
-            main stream    A(j) .......... A(j+1) .......... A(j+2) ...        (A(j+3) waits until C(j) has left its slot)
-            chain stream         scan(j) C(j)       scan(j+1) C(j+1)
+            main stream     A(j) .......... A(j+1) .......... A(j+2) ...        (A(j+3) waits until C(j) has left its slot)
+            chain stream          scan(j)           scan(j+1)
+            select stream                C(j) ..........    C(j+1) ..........
 
         Phase C moves 6 B/px against phase A's 81: it fits in phase A's shadow on a handful of SMs, and its traffic fills the DRAM
         cycles phase A leaves idle instead of being queued between two launches."""
@@ -248,9 +251,16 @@ class ShardedIAS:
             self.side.wait_event(self.ev_a[s])
             with torch.cuda.stream(self.side):
                 self._chain_body(j)
+                self.ev_b[s].record(self.side)
+            # Phase C has its own stream: the scan of window j+1 -- and with it the token the next rank is waiting for -- must
+            # not queue behind phase C of window j.  On the reserved SMs phase C takes about as long as one phase A; with the scan
+            # in front of it in ONE stream the cycle was a little longer than a phase A on the ranks the token reaches last, and
+            # that stream reached the end of the job up to a millisecond behind.
+            self.select.wait_event(self.ev_b[s])
+            with torch.cuda.stream(self.select):
                 self._outputs(j, None, on_window)
                 ev_c[s] = torch.cuda.Event()
-                ev_c[s].record(self.side)
+                ev_c[s].record(self.select)
         return self.finish_state()
 
     def _chain_body(self, j):
@@ -325,6 +335,7 @@ class ShardedIAS:
         dev = e.thr_state.device
         if self.cuda:
             torch.cuda.current_stream(e.device).wait_stream(self.side)
+            torch.cuda.current_stream(e.device).wait_stream(self.select)
         if self.ring is not None:
             self.ring.advance(self.n_windows_total)
         packed = torch.zeros((kmax * gw * 2 + 1, C), dtype=torch.int64, device=dev)
