@@ -128,3 +128,35 @@ def test_native_file_writer_is_a_host_function(built_lib, tmp_path):
     with pytest.raises(OSError) as e:
         ops.write_files([str(tmp_path / 'missing_dir' / 'x.png')], blob, [0, 4])
     assert e.value.errno == 2
+
+
+def test_lean_loss_entry_points_validate_and_have_no_cpu_path(built_lib):
+    """hiast_st_loss_fused_terms / hiast_st_loss_bwd_checked_terms: invalid arguments return before touching CUDA; the Python
+    wrappers refuse CPU tensors; FusedTermsLean is only taken for configurations the one-pass kernel covers."""
+    import torch
+    from hiast_b200 import _lib, ops
+    from hiast_b200 import losses as L
+    l = _lib.lib()
+    assert l.hiast_st_loss_fused_terms(None, None, None, 8, 1, 19, 4, 0, 15, None, None, None, None, None, None, None, None, None, 0,
+                                       None) == -1
+    assert l.hiast_st_loss_bwd_checked_terms(None, None, None, 8, 1, 19, 4, 0, 15, None, None, None, None, None, None, None, None,
+                                             None, 0, None, None) == -1
+    z = torch.zeros(1, 19, 4, 4)
+    y = torch.zeros(1, 4, 4, dtype=torch.int64)
+    gw = torch.ones(4)
+    with pytest.raises(_lib.HiastError):
+        ops.st_loss_fused_terms(z, z, y, gw)
+    with pytest.raises(_lib.HiastError):
+        ops.st_loss_bwd_checked_terms(z, z, y, [torch.ones(())] * 4, torch.ones(4, dtype=torch.float64), gw, z)
+    # which configurations take the lean path
+    hint = object()
+    zg = torch.zeros(2, 19, 4, 6, requires_grad=True)
+    assert L.lean_ok(zg, y, 15, False, hint)
+    assert not L.lean_ok(zg, y, 15, False, None)                          # no expectation of the upstream gradient
+    assert not L.lean_ok(zg, y, 15, True, hint)                           # SoftCE without refer_labels: divisor = numel
+    assert not L.lean_ok(zg, y, 15 | _lib.CST_KLDIV, False, hint)         # other consistency kinds
+    assert not L.lean_ok(torch.zeros(2, 19, 4, 6), y, 15, False, hint)    # no gradient wanted
+    assert not L.lean_ok(torch.zeros(2, 7, 4, 6, requires_grad=True), y, 15, False, hint)    # C outside {16, 19}
+    assert not L.lean_ok(torch.zeros(2, 19, 3, 5, requires_grad=True), y, 15, False, hint)   # odd HW
+    with torch.no_grad():
+        assert not L.lean_ok(zg, y, 15, False, hint)
