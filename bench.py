@@ -53,8 +53,8 @@ UNIT = 'images/s'
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=46)
-    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--steps', type=int, default=None, help='timed steps (default: 46 windows for the GPU arm, 2 runs for --impl reference)')
+    ap.add_argument('--warmup', type=int, default=None, help='untimed steps (default: 3 for the GPU arm, 1 for --impl reference)')
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--dist', default='mixed', choices=['mixed', 'diffuse', 'peaked'])
     ap.add_argument('--e2e-steps', type=int, default=4)
@@ -63,7 +63,12 @@ def parse_args():
     ap.add_argument('--no-extra', action='store_true', help='skip the legs for BASELINE configs[2], [3], [4]')
     ap.add_argument('--extra-timeout', type=int, default=240, help='seconds after which the extra legs are abandoned (the headline line is printed without them)')
     ap.add_argument('--cpu-images', type=int, default=8)
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.steps is None:
+        args.steps = 2 if args.impl == 'reference' else 46
+    if args.warmup is None:
+        args.warmup = 1 if args.impl == 'reference' else 3
+    return args
 
 
 def peaks():
@@ -117,7 +122,7 @@ def run_cpu_arm(n_images, steps=1, warmup=0):
     batches = [(logits[i:i + GROUP], ['img_%05d.png' % (i + j) for j in range(min(GROUP, n_images - i))])
                for i in range(0, n_images, GROUP)]
     kind = 'reference' if oref.available() else 'port'
-    best = None
+    times = []
     for it in range(warmup + steps):
         t0 = time.perf_counter()
         if kind == 'reference':
@@ -126,8 +131,9 @@ def run_cpu_arm(n_images, steps=1, warmup=0):
             oias.IASOracle(C, ALPHA, BETA, GAMMA, CP_GAMMA, faithful=True, keep_labels=False).run(batches)
         dt = time.perf_counter() - t0
         if it >= warmup:
-            best = dt if best is None else min(best, dt)
-    return n_images / best, best, torch.get_num_threads(), kind
+            times.append(dt)
+    mean = sum(times) / len(times)                  # every timed step counts, as in the GPU arm (total time / steps)
+    return n_images / mean, mean, torch.get_num_threads(), kind
 
 
 CPU_NOTE = {'reference': 'the unmodified reference (oracle/_ref/code: workflows/pseudo_label_generator.py IASPseudoGenerator.run) on the '
@@ -140,9 +146,12 @@ def reference_arm(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    n = args.cpu_images
-    steps = max(1, min(args.steps, 2))
-    warm = max(0, min(args.warmup, 1))     # a CPU step takes seconds: at most one untimed pass
+    # The driver launches this arm with the GPU arm's --steps K --warmup W: exactly K timed and W untimed steps, each step one
+    # run() of the reference over a bounded sample of the workload -- 4 full-resolution maps (2 groups, ~2.5 s on 16 host
+    # cores), so that 20 + 5 steps end in about a minute; with few steps the sample is --cpu-images maps (default 8).
+    steps = max(1, args.steps)
+    warm = max(0, args.warmup)
+    n = args.cpu_images if steps + warm <= 4 else min(args.cpu_images, 4)
     value, secs, threads, kind = run_cpu_arm(n, steps=steps, warmup=warm)
     sample = '%d maps of 19x1024x2048, batch 2 (%d groups), per step; PNG write excluded' % (n, (n + 1) // 2)
     line = {
@@ -150,6 +159,7 @@ def reference_arm(args):
         'warmup': warm, 'ms_per_step': secs * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': 'GTA5->Cityscapes IAS pseudo-labelling, 19x1024x2048 logit maps, batch 2 (configs[1])',
+                   'images_per_step': n, 'alpha': ALPHA, 'beta': BETA, 'gamma': GAMMA, 'distribution': 'mixed',
                    'note': CPU_NOTE[kind]},
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': kind, 'sample': sample,
                          'host_cpus': os.cpu_count(),
