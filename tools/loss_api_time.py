@@ -1,3 +1,6 @@
+#!/usr/bin/env python
+"""BASELINE configs[2] through bench.py's own loss leg (tools/bench_extra.loss_leg): kernel calls and `compute_loss` + `backward`
+through the segmentor, without the rest of the bench.  Development tool."""
 import sys, os, json, torch
 sys.path.insert(0, os.getcwd())
 from tools.bench_extra import loss_leg
